@@ -1,0 +1,308 @@
+// Device-side fp64 building blocks shared by every d2dx kernel (sm_100a).
+// Each function names the reference code it evaluates (paths relative to the reference's src/).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/d2dx.h"
+
+namespace d2dx {
+
+constexpr double kPi = 3.141592653589793;        // np.pi
+constexpr double kTwoPi = 6.283185307179586;     // 2*np.pi
+constexpr double kG = 9.81;                      // d2d/dynamic.py:9, d2d/guidance.py:39
+
+// norm_mpi_pi, d2d/utils.py:7: (v + pi) % (2 pi) - pi with NumPy's floored float modulo
+// (npy_remainder: fmod, then += b when the signs differ).  The three branches are bit-identical to
+// fmod for |a| < 4 pi (a - 2pi is exact there by Sterbenz) and skip CUDA's iterative fmod.
+__device__ __forceinline__ double wrap_pi(double v) {
+  double a = v + kPi, m;
+  if (a >= 0.0 && a < kTwoPi) m = a;
+  else if (a >= kTwoPi && a < 2.0 * kTwoPi) m = a - kTwoPi;
+  else if (a < 0.0 && a > -kTwoPi) m = a + kTwoPi;
+  else {
+    m = fmod(a, kTwoPi);
+    if (m != 0.0) { if (m < 0.0) m += kTwoPi; } else m = 0.0;
+  }
+  return m - kPi;
+}
+
+__device__ __forceinline__ double clip(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// flat output and its three time derivatives, Trajectory.get -> (4,2), d2d/trajectory.py:88-122
+struct FlatOut { double y0x, y0y, y1x, y1y, y2x, y2y, y3x, y3y; };
+
+// PolynomialOne.get, d2d/trajectory.py:74-82: Horner over all 8 slots of derivative row d, with the
+// separate multiply and add of `v *= t; v += c`; rows d >= 1 are arr(d, pow+d) * coefs[0][pow+d]
+// (:70-72), an exact small integer times the stored coefficient, so they are rebuilt on the fly.
+template <int D, typename LD>
+__device__ __forceinline__ double poly_row(LD c0, double t) {
+  double v = 0.0;   // coefs[D][7] .. coefs[D][8-D] are structural zeros for D >= 1
+  bool first = true;
+#pragma unroll
+  for (int j = 7 - D; j >= 0; --j) {
+    const int n = j + D;
+    const double f = (D == 0) ? 1.0 : (D == 1) ? double(n) : (D == 2) ? double(n * (n - 1)) : double(n * (n - 1) * (n - 2));
+    const double c = (D == 0) ? c0(n) : __dmul_rn(f, c0(n));
+    if (first) { v = c; first = false; }
+    else v = __dadd_rn(__dmul_rn(v, t), c);
+  }
+  return v;
+}
+
+// One trajectory segment evaluated at time t.  `P(k)` returns parameter slot k (include/d2dx.h).
+template <bool WANT3, typename LD>
+__device__ __forceinline__ void segment_eval(int type, LD P, double t, FlatOut& Y) {
+  Y.y2x = Y.y2y = Y.y3x = Y.y3y = 0.0;
+  switch (type) {
+    case D2DX_SEG_LINE: {            // TrajectoryLine.get, d2d/trajectory.py:136-141
+      const double dt = t - P(0);
+      Y.y1x = P(3); Y.y1y = P(4);
+      Y.y0x = __dadd_rn(P(1), __dmul_rn(Y.y1x, dt));
+      Y.y0y = __dadd_rn(P(2), __dmul_rn(Y.y1y, dt));
+    } break;
+    case D2DX_SEG_CIRCLE: {          // TrajectoryCircle.get, d2d/trajectory.py:153-160
+      const double r = P(3), om = P(4);
+      const double alpha = __dadd_rn(__dmul_rn(t - P(0), om), P(5));
+      double sa, ca;
+      sincos(alpha, &sa, &ca);
+      const double w1 = __dmul_rn(om, r), w2 = __dmul_rn(__dmul_rn(om, om), r);
+      Y.y0x = __dadd_rn(P(1), __dmul_rn(r, ca)); Y.y0y = __dadd_rn(P(2), __dmul_rn(r, sa));
+      Y.y1x = -w1 * sa; Y.y1y = w1 * ca;
+      Y.y2x = -w2 * ca; Y.y2y = -w2 * sa;
+      if (WANT3) { const double w3 = __dmul_rn(om * om * om, r); Y.y3x = w3 * sa; Y.y3y = -w3 * ca; }
+    } break;
+    case D2DX_SEG_SLALOM: {          // TrajSlalom.get, d2d/trajectory_factory.py:133-145 (a=10, om=1)
+      const double dt = t - P(0);
+      Y.y1x = P(3); Y.y1y = P(4);
+      Y.y0x = __dadd_rn(P(1), __dmul_rn(Y.y1x, dt));
+      Y.y0y = __dadd_rn(P(2), __dmul_rn(Y.y1y, dt));
+      const double alpha = __dadd_rn(dt, P(5));
+      double s, c;
+      sincos(alpha, &s, &c);
+      Y.y0y = __dadd_rn(Y.y0y, 10.0 * s);
+      Y.y1y = __dadd_rn(Y.y1y, 10.0 * c);
+      Y.y2y = -10.0 * s;
+      if (WANT3) Y.y3y = -10.0 * c;
+    } break;
+    case D2DX_SEG_POLY: {            // MinSnapPoly.get, d2d/trajectory.py:185-187
+      const double dt = t - P(0);
+      auto cx = [&](int k) { return P(1 + k); };
+      auto cy = [&](int k) { return P(9 + k); };
+      Y.y0x = poly_row<0>(cx, dt); Y.y0y = poly_row<0>(cy, dt);
+      Y.y1x = poly_row<1>(cx, dt); Y.y1y = poly_row<1>(cy, dt);
+      Y.y2x = poly_row<2>(cx, dt); Y.y2y = poly_row<2>(cy, dt);
+      if (WANT3) { Y.y3x = poly_row<3>(cx, dt); Y.y3y = poly_row<3>(cy, dt); }
+    } break;
+    default: {                       // D2DX_SEG_SI_LINE: SpaceIndexedTraj.get, d2d/trajectory.py:231-241
+      auto cl = [&](int k) { return P(5 + k); };
+      const double l0 = clip(poly_row<0>(cl, t), 0.0, 1.0);
+      const double l1 = poly_row<1>(cl, t), l2 = poly_row<2>(cl, t);
+      const double gx = P(3), gy = P(4);      // dg/dlambda of the line geometry; higher ones vanish
+      Y.y0x = __dadd_rn(P(1), __dmul_rn(gx, l0)); Y.y0y = __dadd_rn(P(2), __dmul_rn(gy, l0));
+      Y.y1x = l1 * gx; Y.y1y = l1 * gy;
+      Y.y2x = l2 * gx; Y.y2y = l2 * gy;
+      if (WANT3) { const double l3 = poly_row<3>(cl, t); Y.y3x = l3 * gx; Y.y3y = l3 * gy; }
+    } break;
+  }
+}
+
+// CompositeTraj.get, d2d/trajectory.py:202-208: which segment is active and at which local time.
+// Plain trajectories (traj_dur <= 0) evaluate their only segment at t.
+__device__ __forceinline__ int composite_locate(const d2dx_traj_table& tt, int b, double t, double& t_eval) {
+  const double dur = tt.traj_dur[b];
+  const int first = tt.first_seg[b];
+  if (!(dur > 0.0)) { t_eval = t; return first; }
+  const double lapse = fmod(t - tt.traj_t0[b], dur);
+  const int n = tt.n_segs[b];
+  int k = 0;                                   // np.argmax of an all-False mask is 0
+  for (int j = 0; j < n; ++j) if (tt.seg_end[first + j] > lapse) { k = j; break; }
+  t_eval = lapse;
+  return first + k;
+}
+
+// Aircraft.cont_dyn, d2d/dynamic.py:14-23
+struct AcPar { double wx, wy, n_inv_tau_phi, n_inv_tau_v; };   // -1/tau as the reference forms it
+
+__device__ __forceinline__ void cont_dyn(const AcPar& a, double psi, double phi, double v, double phi_c,
+                                         double v_c, double& dx, double& dy, double& dpsi, double& dphi, double& dv) {
+  double s, c;
+  sincos(psi, &s, &c);
+  dx = v * c + a.wx;
+  dy = v * s + a.wy;
+  dpsi = kG / v * tan(phi);
+  dphi = a.n_inv_tau_phi * (phi - phi_c);
+  dv = a.n_inv_tau_v * (v - v_c);
+}
+
+// Fixed-step stand-in for Aircraft.disc_dyn (d2d/dynamic.py:25-28): nsub classical RK4 sub-steps with
+// the input held, then psi wrapped once (:27).
+__device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
+  const double h = dt / nsub, hh = 0.5 * h, h6 = h / 6.0;
+  double x = X[0], y = X[1], psi = X[2], phi = X[3], v = X[4];
+  for (int s = 0; s < nsub; ++s) {
+    double k1[5], k2[5], k3[5], k4[5];
+    cont_dyn(a, psi, phi, v, phi_c, v_c, k1[0], k1[1], k1[2], k1[3], k1[4]);
+    cont_dyn(a, psi + hh * k1[2], phi + hh * k1[3], v + hh * k1[4], phi_c, v_c, k2[0], k2[1], k2[2], k2[3], k2[4]);
+    cont_dyn(a, psi + hh * k2[2], phi + hh * k2[3], v + hh * k2[4], phi_c, v_c, k3[0], k3[1], k3[2], k3[3], k3[4]);
+    cont_dyn(a, psi + h * k3[2], phi + h * k3[3], v + h * k3[4], phi_c, v_c, k4[0], k4[1], k4[2], k4[3], k4[4]);
+    x += h6 * (k1[0] + 2.0 * k2[0] + 2.0 * k3[0] + k4[0]);
+    y += h6 * (k1[1] + 2.0 * k2[1] + 2.0 * k3[1] + k4[1]);
+    psi += h6 * (k1[2] + 2.0 * k2[2] + 2.0 * k3[2] + k4[2]);
+    phi += h6 * (k1[3] + 2.0 * k2[3] + 2.0 * k3[3] + k4[3]);
+    v += h6 * (k1[4] + 2.0 * k2[4] + 2.0 * k3[4] + k4[4]);
+  }
+  X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
+}
+
+// DiffFlatness.state_and_input_from_output, d2d/guidance.py:23-47
+struct FlatState { double x, y, psi, phi, va, u_phi, u_v, vadot, psidot, z /* tan(phi) */, cpsi, spsi; };
+
+__device__ __forceinline__ void flatness(const FlatOut& Y, double wx, double wy, double tau_v, FlatState& r) {
+  const double vax = Y.y1x - wx, vay = Y.y1y - wy;
+  const double va2 = vax * vax + vay * vay, va = sqrt(va2);
+  const double inv_va = 1.0 / va;
+  r.x = Y.y0x; r.y = Y.y0y; r.va = va;
+  r.psi = atan2(vay, vax);
+  r.vadot = (vax * Y.y2x + vay * Y.y2y) / va;
+  const double num = Y.y2y * vax - Y.y2x * vay;
+  r.psidot = num / va2;
+  r.z = num / va / kG;                    // argument of the arctan at :40, i.e. tan(phi_ref)
+  r.phi = atan(r.z);
+  r.u_phi = r.phi;                        // tau_phi * Xdot[phi] + phi with Xdot[phi] never filled (:42-43)
+  r.u_v = tau_v * r.vadot + va;
+  r.cpsi = vax * inv_va; r.spsi = vay * inv_va;   // cos / sin of arctan2(vay, vax)
+}
+
+// LQR gain of DFFFController.get (d2d/guidance.py:78-82): K1 = lqr(A[:3,:3], A[:3,3:], diag(q,q,q3), diag(r1,r2))
+// with A from Aircraft.cont_jac (d2d/dynamic.py:32-43).
+//
+// Rotating the position error into the path frame (T = rot(-psi_ref) (+) 1) leaves Q unchanged (q1 = q2) and
+// turns the pair into  A' = v e2 e3^T,  B' = [[0,1],[0,0],[b1,b2]],  b1 = g/v/(1+cos^2 phi),  b2 = g tan(phi)/v^2
+// (entries replicated as the reference writes them).  With kappa_j = (sqrt(r1) K_1j, sqrt(r2) K_2j) the Riccati
+// equation reads kappa_i . kappa_j = (A'^T P + P A' + Q)_ij, whose (1,1), (2,2), (1,2) entries force
+// kappa_1 = sqrt(q) (C, S), kappa_2 = sqrt(q) (S, -C) with C^2 + S^2 = 1.  Writing kappa_3 = (al, be) and using
+// P = P^T, the remaining unknowns (theta, al) solve
+//     F1 = C al + S be + v (c2 C + e S) = 0,      F2 = al^2 + be^2 - q3 - 2 v c1 sqrt(q) S = 0,
+//     be = (c1 sqrt(q) C + e al) / c2,   c1 = sqrt(r1)/b1,  c2 = sqrt(r2),  e = b2 c1,
+// a 2x2 Newton iteration (quadratic, warm-started from the previous control step; cold start = the decoupled
+// b2 = 0 solution C = 0, S = 1, al = sqrt(q3 + 2 v c1 sqrt(q))).  K' = [[C, S, al]/sqrt(r1) ; [S, -C, be]/sqrt(r2)]
+// (times sqrt(q) on the first two columns) and K1 = K' T.  Checked against scipy.linalg.solve_continuous_are
+// over v in [0.3, 60], |phi| < 1.4 to 3e-13 (tests/test_care_math.py).
+struct CareState { double C, S, al; };
+
+struct CareConst { double sq, q3, sr1, sr2, isr1, isr2; };
+
+__device__ __forceinline__ CareConst care_const(const d2dx_dfff_gains& g) {
+  CareConst c;
+  c.sq = sqrt(g.q_pos); c.q3 = g.q_psi; c.sr1 = sqrt(g.r_phi); c.sr2 = sqrt(g.r_v);
+  c.isr1 = 1.0 / c.sr1; c.isr2 = 1.0 / c.sr2;
+  return c;
+}
+
+// returns the number of Newton iterations (-1: not converged); K0 is the 2x3 gain in the path frame
+__device__ __forceinline__ int care_gain(const CareConst& cc, double v, double b1, double b2, CareState& st,
+                                         bool cold, double* K0, int max_it = 40) {
+  const double c1 = cc.sr1 / b1, c2 = cc.sr2, ic2 = cc.isr2, e = b2 * c1;
+  const double c1q = c1 * cc.sq;
+  double C = st.C, S = st.S, al = st.al;
+  if (cold) { C = 0.0; S = 1.0; al = sqrt(cc.q3 + 2.0 * v * c1q); }
+  int it = 0;
+  bool conv = false;
+  for (; it < max_it && !conv; ++it) {
+    const double be = (c1q * C + e * al) * ic2;
+    const double dbt = -c1q * S * ic2, dba = e * ic2;
+    const double F1 = C * al + S * be + v * (c2 * C + e * S);
+    const double F2 = al * al + be * be - cc.q3 - 2.0 * v * c1q * S;
+    const double J11 = -S * al + C * be + S * dbt + v * (e * C - c2 * S), J12 = C + S * dba;
+    const double J21 = 2.0 * (be * dbt - v * c1q * C), J22 = 2.0 * (al + be * dba);
+    const double idet = 1.0 / (J11 * J22 - J12 * J21);
+    const double dth = (J12 * F2 - F1 * J22) * idet;
+    const double dal = (J21 * F1 - J11 * F2) * idet;
+    const double Cn = C - S * dth, Sn = S + C * dth;
+    const double nrm = rsqrt(Cn * Cn + Sn * Sn);
+    C = Cn * nrm; S = Sn * nrm;
+    al += dal;
+    conv = fabs(dth) < 1e-9 && fabs(dal) < 1e-9 * fabs(al);
+  }
+  st.C = C; st.S = S; st.al = al;
+  const double be = (c1q * C + e * al) * ic2;
+  K0[0] = cc.sq * C * cc.isr1; K0[1] = cc.sq * S * cc.isr1; K0[2] = al * cc.isr1;
+  K0[3] = cc.sq * S * cc.isr2; K0[4] = -cc.sq * C * cc.isr2; K0[5] = be * cc.isr2;
+  return conv ? it : -1;
+}
+
+// DFFFController.get, d2d/guidance.py:62-91, given the flat output at t.  Returns U; fills the reference
+// state, and K (2x3, world frame) when WANT_K.
+template <bool WANT_K>
+__device__ __forceinline__ void dfff_control(const FlatOut& Y, const AcPar& a, double tau_v, const double* X,
+                                             const d2dx_dfff_gains& g, const CareConst& cc, CareState& cs, bool& cold,
+                                             int& flags, FlatState& fr, double& u_phi, double& u_v, double* K) {
+  flatness(Y, a.wx, a.wy, tau_v, fr);
+  double ex = clip(X[0] - fr.x, -g.err_sat[0], g.err_sat[0]);
+  double ey = clip(X[1] - fr.y, -g.err_sat[1], g.err_sat[1]);
+  double ep = clip(wrap_pi(X[2] - fr.psi), -g.err_sat[2], g.err_sat[2]);
+  // cont_jac at the reference state: cos^2(atan z) = 1/(1+z^2), tan(atan z) = z
+  const double z2 = fr.z * fr.z;
+  const double b1 = kG / fr.va * ((1.0 + z2) / (2.0 + z2));
+  const double b2 = kG / (fr.va * fr.va) * fr.z;
+  double K0[6];
+  int it = care_gain(cc, fr.va, b1, b2, cs, cold, K0);
+  if (it < 0 && !cold) it = care_gain(cc, fr.va, b1, b2, cs, true, K0);   // warm start failed: retry cold once
+  if (it < 0) { flags |= 2; cold = true; } else cold = false;
+  // error in the path frame, feedback, saturation (:85-88)
+  const double e1 = fr.cpsi * ex + fr.spsi * ey, e2 = fr.cpsi * ey - fr.spsi * ex;
+  u_phi = clip(fr.u_phi - (K0[0] * e1 + K0[1] * e2 + K0[2] * ep), g.u_lo[0], g.u_hi[0]);
+  u_v = clip(fr.u_v - (K0[3] * e1 + K0[4] * e2 + K0[5] * ep), g.u_lo[1], g.u_hi[1]);
+  if (WANT_K) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      K[3 * m + 0] = K0[3 * m] * fr.cpsi - K0[3 * m + 1] * fr.spsi;
+      K[3 * m + 1] = K0[3 * m] * fr.spsi + K0[3 * m + 1] * fr.cpsi;
+      K[3 * m + 2] = K0[3 * m + 2];
+    }
+  }
+}
+
+// CircleTraj.get + GVFcontroller.get, d2d/guidance.py:137-146,155-181 (E = [[0,1],[-1,0]], H = 2I)
+__device__ __forceinline__ void gvf_control(double px, double py, double psi, double v, double cx, double cy,
+                                            double r, double ke, double kd, double& U, double& U1, double& U2) {
+  const double dx = px - cx, dy = py - cy;
+  const double e = (dx * dx + dy * dy) - r * r;
+  const double nx = 2.0 * dx, ny = 2.0 * dy;
+  double s, c;
+  sincos(psi, &s, &c);
+  const double pdx = v * c, pdy = v * s;                 // p_dot
+  const double tx = ny, ty = -nx;                        // tau = E n
+  const double qx = tx - ke * e * nx, qy = ty - ke * e * ny;   // pd_dot
+  const double nrm = sqrt(qx * qx + qy * qy);
+  const double qnx = qx / nrm, qny = qy / nrm;           // pd_dot_n
+  const double ox = qny, oy = -qnx;                      // E pd_dot_n
+  // w = (E - ke e I) H p_dot - ke (n p_dot^T) n
+  const double hx = 2.0 * pdx, hy = 2.0 * pdy;
+  const double kee = ke * e;
+  const double wx_ = (-kee * hx + hy) - ke * (nx * pdx) * nx - ke * (nx * pdy) * ny;
+  const double wy_ = (-hx - kee * hy) - ke * (ny * pdx) * nx - ke * (ny * pdy) * ny;
+  // U1 = -(m w) . (E pd_dot_n / |pd_dot|),  m = o o^T
+  const double ow = ox * wx_ + oy * wy_;
+  U1 = -(ox * ow * (ox / nrm) + oy * ow * (oy / nrm));
+  U2 = kd * (c * ox + s * oy);
+  U = U1 + U2;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double val) {   // val >= 0
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(__double_as_longlong(val)));
+}
+
+}  // namespace d2dx

@@ -1,0 +1,130 @@
+"""Guidance laws -- the `d2d.guidance` call surface (d2d/guidance.py:10-181), evaluated by the engine.
+
+Single calls (`DFFFController.get`, `DCFController.get`, `GVFcontroller.get`, ...) keep the reference's
+signatures and return types; each is one kernel launch on a batch of size 1 (or n).  Closed-loop simulations
+should use `d2d_b200.simulation`, which fuses controller and integrator in one rollout kernel."""
+import numpy as np
+
+from . import trajectory as ddt
+from .dynamic import Aircraft
+from .engine import get_engine
+
+
+def norm_mpi_pi(v):
+    """Wrap to [-pi, pi) with floored modulo (d2d/guidance.py:10).  Host-side convenience only; the kernels
+    carry their own bit-identical wrap."""
+    return (v + np.pi) % (2 * np.pi) - np.pi
+
+
+class WindField:
+    """Constant wind (d2d/guidance.py:12-19)."""
+
+    def __init__(self, w=[0., 0.]):
+        self.w = w
+
+    def sample(self, t, loc):
+        return self.w
+
+    def summarize(self):
+        return f"{self.w} m/s"
+
+
+class DiffFlatness:
+    """Flat output -> state and input (d2d/guidance.py:22-47).  Called without an instance, as the reference does."""
+
+    def state_and_input_from_output(Ys, W, ac):
+        eng = get_engine()
+        Ys = np.asarray(Ys, dtype=np.float64)
+        single = Ys.ndim == 2
+        Yb = Ys.reshape(-1, 4, 2)
+        n = len(Yb)
+        Yd = eng.to_device(np.ascontiguousarray(Yb.reshape(n, 8).T))
+        Wd = eng.to_device(np.ascontiguousarray(np.broadcast_to(np.asarray(W, dtype=np.float64).reshape(-1, 2), (n, 2)).T))
+        acd = eng.to_device(np.ascontiguousarray(np.broadcast_to(np.array([[ac.tau_phi], [ac.tau_v]]), (2, n))))
+        Xr, Ur, Xd = (a.cpu().numpy().T for a in eng.flatness(Yd, Wd, acd))
+        return (Xr[0], Ur[0], Xd[0]) if single else (Xr, Ur, Xd)
+
+
+class DFFFController:
+    """Differential-flatness feed-forward + LQR feedback (d2d/guidance.py:52-91).  `get(X, t)` returns the
+    saturated input U and appends the reference state and the gain to `Xref` / `K` like the reference."""
+
+    def __init__(self, traj, ac, wind):
+        self.traj, self.ac, self.wind = traj, ac, wind
+        self.dt = 0.01
+        self.time = np.arange(0, traj.duration, self.dt)
+        self.carrot, self.ref_pos = [0, 0], [0, 0]
+        self.Xref, self.K = [], []
+        self._table = None
+        self._care = None
+
+    def get(self, X, t):
+        eng = get_engine()
+        if self._table is None:
+            self._table = eng.table(ddt.pack([self.traj]))
+            self._care = eng.zeros(3, 1)
+        W = np.asarray(self.wind.sample(t, None), dtype=np.float64).reshape(2, 1)
+        acd = eng.to_device(np.array([[self.ac.tau_phi], [self.ac.tau_v]]))
+        Xd = eng.to_device(np.asarray(X, dtype=np.float64).reshape(5, 1))
+        U, Xr, K = eng.dfff_control(self._table, Xd, t, eng.to_device(W), acd, care_state=self._care)
+        self.Xref.append(Xr.cpu().numpy()[:, 0])
+        K5 = np.zeros((2, 5))
+        K5[:, :3] = K.cpu().numpy()[:, 0].reshape(2, 3)
+        self.K.append(K5)
+        return U.cpu().numpy()[:, 0]
+
+
+class DCFController:
+    """Distributed circular-formation controller (d2d/guidance.py:99-126)."""
+
+    def get(self, n_ac, B, c, p, z_des, kr):
+        eng = get_engine()
+        z_des = np.asarray(z_des, dtype=np.float64)
+        B = np.asarray(B, dtype=np.float64).reshape(n_ac, -1)
+        c = np.asarray(c, dtype=np.float64)
+        if c.shape != (n_ac, 2):
+            raise ValueError(f"operands could not be broadcast together: p is (2,{n_ac}), c.T is {c.T.shape} "
+                             "(c must be (n_ac, 2), cf. d2d/guidance.py:106)")
+        pd = eng.to_device(np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(2, n_ac)))
+        cd = eng.to_device(np.ascontiguousarray(c.T))
+        Ur, e = eng.dcf(B, z_des.reshape(-1), kr, pd, cd)
+        return Ur.cpu().numpy().reshape(n_ac, 1), e.cpu().numpy().reshape(-1, 1)
+
+
+class CircleTraj:
+    """Implicit circle e = |p - c|^2 - r^2 (d2d/guidance.py:133-146).  Pure parameter arithmetic on three
+    scalars; kept on the host because its outputs only feed `GVFcontroller.get`, which recomputes them on the
+    device from (X, c, r)."""
+
+    def __init__(self, c=np.array([0, 0])):
+        self.c = c
+
+    def get(self, X, r=1):
+        px, py = X[0], X[1]
+        e = np.asarray(((px - self.c[0]) ** 2 + (py - self.c[1]) ** 2) - r ** 2)
+        n = np.asarray([2 * (px - self.c[0]), 2 * (py - self.c[1])])
+        H = np.asarray([[2, 0], [0, 2]])
+        self._last_r = r
+        return e, n, H
+
+
+class GVFcontroller:
+    """Guidance vector field heading controller (d2d/guidance.py:148-181)."""
+
+    def __init__(self, traj, ac, wind):
+        self.traj, self.ac, self.wind = traj, ac, wind
+
+    def get(self, X, ke, kd, e, n, H):
+        # (e, n) define the circle for this state: c = p - n/2, r^2 = |n/2|^2 - e
+        eng = get_engine()
+        X = np.asarray(X, dtype=np.float64).reshape(5)
+        n = np.asarray(n, dtype=np.float64).reshape(2)
+        c = X[:2] - n / 2
+        if self.traj is not None and hasattr(self.traj, "c"):
+            c = np.asarray(self.traj.c, dtype=np.float64).reshape(2)
+        r = np.sqrt(float(np.sum(np.square(n / 2)) - float(np.asarray(e).reshape(-1)[0])))
+        if self.traj is not None and hasattr(self.traj, "_last_r"):
+            r = float(np.asarray(self.traj._last_r).reshape(-1)[0])
+        out = eng.gvf(eng.to_device(X.reshape(5, 1)), eng.to_device(c.reshape(2, 1)), eng.to_device(np.array([r])), ke, kd)
+        U, U1, U2 = out.cpu().numpy()[:, 0]
+        return U, U1, U2

@@ -1,0 +1,118 @@
+"""Named trajectories -- the `d2d.trajectory_factory` registry (d2d/trajectory_factory.py) for the
+trajectory families the engine evaluates.  Spline / tabulated trajectories (TrajSpline, TrajSiSpline,
+TrajTabulated) are outside the hot path and are not provided."""
+import numpy as np
+
+from . import _lib
+from . import trajectory as ddt
+
+trajectories = {}
+
+
+def register(T):
+    trajectories[T.name] = (T.desc, T)
+    return T
+
+
+def list_available():
+    return [f"{k}: {v[0]}" for k, v in sorted(trajectories.items())]
+
+
+@register
+class TrajCircle(ddt.TrajectoryCircle):                      # d2d/trajectory_factory.py:20-25
+    name, desc = "circle", "30m radius (30,30) centered circle"
+    extends = (-10, 70, -10, 70)
+
+    def __init__(self):
+        super().__init__(c=[30., 30.], r=30., v=10., t0=0., alpha0=0, dalpha=2 * np.pi)
+
+
+@register
+class TrajTwoLines(ddt.CompositeTraj):                       # :29-37
+    name, desc = "two_lines", "example of composite trajectory"
+    extends = (-20, 120, -20, 60)
+
+    def __init__(self):
+        first = ddt.TrajectoryLine([0, 0], [50, 50], v=10., t0=0.)
+        super().__init__([first, ddt.TrajectoryLine([50, 50], [100, 0], v=10., t0=first.duration)])
+
+
+@register
+class TrajSquare(ddt.CompositeTraj):                         # :40-50
+    name, desc = "square", "example of composite trajectory"
+    extends = (-10, 60, -10, 60)
+
+    def __init__(self):
+        corners = [[0, 0], [50, 0], [50, 50], [0, 50]]
+        sides, t0 = [], 0.
+        for k in range(4):
+            sides.append(ddt.TrajectoryLine(corners[k], corners[(k + 1) % 4], v=10., t0=t0))
+            t0 = t0 + sides[-1].duration
+        super().__init__(sides)
+
+
+@register
+class TrajLineWithIntro(ddt.CompositeTraj):                  # :53-61
+    name, desc = "line_with_intro", "line with circle_intro"
+
+    def __init__(self, Y0=[0, 0], Y1=[0, 50], Y2=[100, 50], r=-25.):
+        arc = ddt.TrajectoryCircle(c=(np.asarray(Y0) + Y1) / 2, r=r, v=10., alpha0=np.pi / 2, dalpha=np.pi)
+        super().__init__([arc, ddt.TrajectoryLine(Y1, Y2, v=10., t0=arc.duration)])
+        self.extends = (-50, 130, -30, 130)
+
+
+class TrajWithIntro(ddt.CompositeTraj):                      # :65-87 (not registered there either)
+    name, desc = "traj_with_intro", "traj with circle_intro"
+
+    def __init__(self, Y0, traj, v=10, duration=8.):
+        start = traj.get(0)[0]
+        gap = np.linalg.norm(start - Y0)
+        super().__init__([ddt.TrajectoryLine(Y0, start, v=gap / duration), traj])
+
+
+@register
+class TrajMinSnapDemo(ddt.MinSnapPoly):                      # :110-117
+    name, desc = "demo_minsnap", "demo_minsnap"
+    extends = (-10, 210, -10, 210)
+
+    def __init__(self):
+        super().__init__([[0, 10, 0, 0], [0, 0, 0, 0]], [[200, 0, 0, 0], [200, 10, 0, 0]], duration=33.65)
+
+
+@register
+class TrajSlalom(ddt.Trajectory):                            # :121-145 (a = 10, om = 1 fixed at :138)
+    name, desc = "slalom", "slalom"
+    extends = (-10, 100, -10, 50)
+
+    def __init__(self, p1=[0, 20], p2=[100, 20], v=10., t0=0., phi=0.):
+        self.p1, self.p2, self.v, self.t0, self.phi = np.asarray(p1), np.asarray(p2), v, t0, phi
+        dep = self.p2 - self.p1
+        self.length = np.linalg.norm(dep)
+        self.un = dep / self.length
+        self.duration = self.length / self.v
+
+    def segments(self):
+        uv = self.un * self.v
+        p = np.zeros(_lib.SEG_NPAR)
+        p[0], p[1], p[2], p[3], p[4], p[5] = self.t0, self.p1[0], self.p1[1], uv[0], uv[1], self.phi
+        return [(_lib.SEG_SLALOM, p)]
+
+
+@register
+class TrajSiDemo(ddt.SpaceIndexedTraj):                      # :177-185
+    name, desc = "sidemo", "space indexed trajectory demo"
+    extends = (-10, 100, -10, 50)
+
+    def __init__(self, p1=[0, 20], p2=[100, 20], duration=10., t0=0.):
+        dynamic = ddt.PolynomialOne([0, 0.05, 0, 0], [1, 0.05, 0, 0], duration=duration)
+        super().__init__(ddt.TrajectoryLine([0, 20], [100, 20], v=100), dynamic)
+
+
+def print_available():
+    print("Available trajectories:")
+    for i, n in enumerate(list_available()):
+        print(f"{i} -> {n}")
+
+
+def get(traj_name, *args):
+    return trajectories[traj_name][1](*args), trajectories[traj_name][0]

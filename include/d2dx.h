@@ -1,0 +1,257 @@
+/* d2dx -- C ABI of the B200-native d2d trajectory-evaluation engine.
+ *
+ * The reference (rajashree-srikanth/drone-sim-python) is pure Python and has no FFI of its own: the
+ * drop-in boundary is the duck-typed `d2d` call surface.  Every entry point
+ * below names the reference interface it replaces (file:line relative to the reference's `src/`).
+ * A ctypes binding of exactly these symbols is what a maintainer adds on the reference side
+ * (INTEGRATION.md); the package `d2d_b200` ships that binding together with `d2d`-compatible classes.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every `double*`, `int32_t*`, `int64_t*` is a DEVICE pointer owned by the caller unless the
+ *     parameter is documented as "host";
+ *   - arrays are structure-of-arrays with the batch index fastest: `X[5][B]` means element
+ *     (state k, scenario b) lives at `X[k*B + b]`;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream),
+ *     allocates nothing and keeps no hidden state;
+ *   - return value 0 = OK, otherwise a D2DX_E* code with text in d2dx_last_error() (thread-local);
+ *   - all arithmetic is IEEE fp64.
+ */
+#ifndef D2DX_H
+#define D2DX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2DX_VERSION 100
+
+enum { D2DX_OK = 0, D2DX_EINVAL = 1, D2DX_ECUDA = 2, D2DX_EUNSUPPORTED = 3 };
+
+typedef struct d2dx_handle d2dx_handle;
+
+/* -------- life cycle -------- */
+int d2dx_version(void);
+const char* d2dx_last_error(void);
+/* binds a handle to CUDA device `device` (no allocation beyond a few bytes of scratch) */
+int d2dx_create(int device, d2dx_handle** out);
+int d2dx_destroy(d2dx_handle* h);
+/* properties: what[0]=SM count, [1]=max resident threads of the DFFF rollout kernel per SM,
+ * [2]=same for the formation kernel, [3]=same for the collocation kernel (host int array[4]) */
+int d2dx_device_info(d2dx_handle* h, int32_t* what_host4);
+
+/* -------- trajectory table --------
+ * One trajectory per aircraft-scenario, made of >= 1 segments.
+ * Replaces the Trajectory class family: TrajectoryLine d2d/trajectory.py:125-141, TrajectoryCircle
+ * :143-160, MinSnapPoly/PolynomialOne :47-82,166-187, CompositeTraj :190-208, SpaceIndexedTraj
+ * :220-241 (line geometry + polynomial dynamics, as TrajSiDemo d2d/trajectory_factory.py:177-185),
+ * TrajSlalom d2d/trajectory_factory.py:121-145. */
+enum {
+  D2DX_SEG_LINE = 0,    /* par: 0 t0 | 1 p1x 2 p1y | 3 (un*v)x 4 (un*v)y                         */
+  D2DX_SEG_CIRCLE = 1,  /* par: 0 t0 | 1 cx 2 cy | 3 r | 4 omega=v/r | 5 alpha0                   */
+  D2DX_SEG_SLALOM = 2,  /* par: 0 t0 | 1 p1x 2 p1y | 3 (un*v)x 4 (un*v)y | 5 phase                */
+  D2DX_SEG_POLY = 3,    /* par: 0 t0 | 1..8 x coefs[0][0..7] | 9..16 y coefs[0][0..7]             */
+  D2DX_SEG_SI_LINE = 4  /* par: 0 t0(unused) | 1 p1x 2 p1y 3 (un*v)x 4 (un*v)y (geometry, t0=0)
+                                | 5..12 lambda coefs[0][0..7]                                    */
+};
+#define D2DX_SEG_NPAR 17
+
+typedef struct {
+  int32_t n_traj;            /* = B                                                              */
+  int32_t n_seg;             /* total number of segments S                                       */
+  const int32_t* first_seg;  /* [B]  index of the trajectory's first segment                     */
+  const int32_t* n_segs;     /* [B]  number of segments (>= 1)                                   */
+  const double* traj_t0;     /* [B]  CompositeTraj.t0                                            */
+  const double* traj_dur;    /* [B]  CompositeTraj.duration (np.sum of step durations);
+                                     <= 0 marks a plain (non-composite) trajectory: no fmod      */
+  const int32_t* seg_type;   /* [S]                                                              */
+  const double* seg_end;     /* [S]  CompositeTraj.steps_end (np.cumsum)                         */
+  const double* seg_par;     /* [D2DX_SEG_NPAR][S]                                               */
+  int32_t uniform_type;      /* >= 0: every trajectory is ONE plain segment of this type and
+                                first_seg[b] == b (selects a specialised kernel); -1: mixed    */
+} d2dx_traj_table;
+
+/* Trajectory.get(t) for every trajectory and every t: Y[nT][8][B], row 2*k+c = k-th derivative of
+ * component c (d2d/trajectory.py:88-122).  `time` is a device array [nT]. */
+int d2dx_traj_eval(d2dx_handle* h, const d2dx_traj_table* tt, int32_t nT, const double* time,
+                   double* Y, void* stream);
+
+/* -------- single calls of the d2d model (batched over n) -------- */
+/* Aircraft.cont_dyn, d2d/dynamic.py:14-23.  X[5][n], U[2][n], W[2][n], ac[2][n]=(tau_phi,tau_v) */
+int d2dx_cont_dyn(d2dx_handle* h, int32_t n, const double* X, const double* U, const double* W,
+                  const double* ac, double* Xdot, void* stream);
+/* Aircraft.disc_dyn, d2d/dynamic.py:25-28, with fixed-step RK4 (nsub sub-steps, ZOH) for LSODA */
+int d2dx_disc_dyn(d2dx_handle* h, int32_t n, const double* X, const double* U, const double* W,
+                  const double* ac, double dt, int32_t nsub, double* Xnext, void* stream);
+/* Aircraft.cont_jac, d2d/dynamic.py:32-43.  A[25][n] (row-major 5x5), Bm[10][n] (row-major 5x2) */
+int d2dx_cont_jac(d2dx_handle* h, int32_t n, const double* Xr, const double* ac, double* A,
+                  double* Bm, void* stream);
+/* DiffFlatness.state_and_input_from_output, d2d/guidance.py:23-47.  Ys[8][n] as in d2dx_traj_eval */
+int d2dx_flatness(d2dx_handle* h, int32_t n, const double* Ys, const double* W, const double* ac,
+                  double* Xr, double* Ur, double* Xrdot, void* stream);
+
+/* controller constants of DFFFController.get, d2d/guidance.py:69,79,87-88 */
+typedef struct {
+  double q_pos, q_psi;       /* Q = diag(q_pos, q_pos, q_psi)   reference: 1, 0.1                */
+  double r_phi, r_v;         /* R = diag(r_phi, r_v)            reference: 8, 1                  */
+  double err_sat[5];         /* reference: 20, 20, pi/3, pi/4, 1                                 */
+  double u_lo[2], u_hi[2];   /* reference: (-45deg, 4), (45deg, 20)                              */
+} d2dx_dfff_gains;
+int d2dx_dfff_default_gains(d2dx_dfff_gains* g_host);
+
+/* DFFFController.get(X, t), d2d/guidance.py:62-91, for B aircraft at one time `t`.
+ * Outputs U[2][B]; optional Xr[5][B], K[6][B] (row-major 2x3 = K[:, :3]; K[:, 3:] is zero).
+ * care_state[3][B] (optional, in/out) warm-starts the Riccati solve. */
+int d2dx_dfff_control(d2dx_handle* h, const d2dx_traj_table* tt, const double* X, double t,
+                      const double* W, const double* ac, const d2dx_dfff_gains* gains_host,
+                      double* U, double* Xr, double* K, double* care_state, void* stream);
+
+/* -------- closed-loop rollout, DFFF controller --------
+ * Replaces run_simulation, 05_test_simulation.py:21-34, for B aircraft-scenarios at once. */
+typedef struct {
+  int32_t B;
+  const double* X0;          /* [5][B]                                                           */
+  const double* wind;        /* [2][B]  WindField.sample, d2d/guidance.py:12-16 (constant field) */
+  const double* ac;          /* [2][B]  tau_phi, tau_v  (d2d/dynamic.py:11-12)                   */
+  d2dx_traj_table traj;
+  /* perturbation events `X[i] += perts[i]` (05_test_simulation.py:32), CSR by scenario, sorted by
+   * step inside a scenario; all NULL = none */
+  const int32_t* pert_begin; /* [B+1]                                                            */
+  const int32_t* pert_step;  /* [n_events] sample index i the perturbation is added to           */
+  const double* pert_dx;     /* [5][n_events]                                                    */
+  int32_t n_events;
+} d2dx_scenarios;
+
+typedef struct {
+  int32_t log_every;         /* sample i is logged at row i/log_every when i % log_every == 0    */
+  double* X_log;             /* [n_rows][5][B] or NULL                                           */
+  double* U_log;             /* [n_rows][2][B] or NULL                                           */
+  double* Xr_log;            /* [n_rows][5][B] or NULL   (DFFFController.Xref, guidance.py:66)   */
+  double* K_log;             /* [n_rows][6][B] or NULL   (DFFFController.K, guidance.py:83)      */
+  double* X_final;           /* [5][B]  state at sample i_end                                    */
+  double* sum_sq_err;        /* [B] or NULL  += sum_i |X[i,:2]-Xr[i,:2]|^2 over this call        */
+  double* max_err;           /* [B] or NULL  = max(previous, max_i |X[i,:2]-Xr[i,:2]|)           */
+  int32_t* flags;            /* [B] or NULL  |= 1 non-finite state seen, 2 Riccati not converged */
+  double* care_state;        /* [3][B] or NULL  Riccati warm start carried between calls         */
+  double* pop_stats;         /* [2] or NULL  += sum over scenarios of sum_sq_err; max of max_err */
+} d2dx_rollout_out;
+
+/* Advances every scenario from sample i_begin to sample i_end of `time` (device array [T], the
+ * reference's np.arange grid): for i in (i_begin, i_end]: U[i-1]=ctl(X[i-1],time[i-1]);
+ * X[i]=rk4(X[i-1],U[i-1],dt=time[i]-time[i-1]); X[i]+=perts[i].  X0 is the state at i_begin.  With
+ * final_control != 0 the extra U[i_end]=ctl(X[i_end],time[i_end]) of 05_test_simulation.py:33 is made. */
+int d2dx_rollout_dfff(d2dx_handle* h, const d2dx_scenarios* s, const double* time, int32_t i_begin,
+                      int32_t i_end, int32_t nsub, int32_t final_control,
+                      const d2dx_dfff_gains* gains_host, const d2dx_rollout_out* out, void* stream);
+
+/* -------- circular formation (DCF + GVF) -------- */
+/* DCFController.get, d2d/guidance.py:103-126, for F formations of n_ac aircraft.
+ * p[2][F*n_ac], c[2][F*n_ac] (aircraft f*n_ac+j), Binc[n_ac][n_e] (host, row-major, shared by all
+ * formations), z_des[n_e] (host).  Outputs Ur[F*n_ac], e_deg[F*n_e] (degrees). */
+int d2dx_dcf(d2dx_handle* h, int32_t F, int32_t n_ac, int32_t n_e, const double* Binc_host,
+             const double* z_des_host, double kr, const double* p, const double* c, double* Ur,
+             double* e_deg, void* stream);
+/* CircleTraj.get + GVFcontroller.get, d2d/guidance.py:137-146,155-181: X[5][n], c[2][n], r[n] ->
+ * out[3][n] = (U, U1, U2) */
+int d2dx_gvf(d2dx_handle* h, int32_t n, const double* X, const double* c, const double* r, double ke,
+             double kd, double* out, void* stream);
+
+typedef struct {
+  int32_t F, n_ac, n_e;
+  const double* X0;          /* [5][F*n_ac]                                                      */
+  const double* c;           /* [2][F*n_ac]  circle centre of each aircraft                      */
+  const double* r;           /* [F*n_ac]     nominal radius R                                    */
+  const double* ac;          /* [2][F*n_ac]  tau_phi, tau_v                                      */
+  const double* Binc_host;   /* host [n_ac][n_e] incidence matrix (08_CircularFormation_Full.py:49-60) */
+  const double* z_des_host;  /* host [n_e]                                                       */
+  double ke, kd, kr, v_c;    /* 08_CircularFormation_Full.py:39-41,90                            */
+} d2dx_formations;
+
+typedef struct {
+  int32_t log_every;
+  double* X_log;             /* [n_rows][5][F*n_ac] or NULL                                      */
+  double* U_log;             /* [n_rows][F*n_ac] or NULL   roll set-point arctan(U/9.81)         */
+  double* Rr_log;            /* [n_rows][F*n_ac] or NULL   commanded radius (row i holds step i's) */
+  double* eth_log;           /* [n_rows][F*n_e] or NULL    phase errors in degrees               */
+  double* X_final;           /* [5][F*n_ac]                                                      */
+  int32_t* flags;            /* [F*n_ac] or NULL                                                 */
+} d2dx_formation_out;
+
+/* Loop of CircularFormationGVF, 08_CircularFormation_Full.py:73-94 (c per aircraft as in
+ * 09_CircularFormation_diffcentre.py:33,87): samples i_begin..i_end of a uniform grid of step dt. */
+int d2dx_rollout_formation(d2dx_handle* h, const d2dx_formations* f, double dt, int32_t i_begin,
+                           int32_t i_end, int32_t nsub, const d2dx_formation_out* out, void* stream);
+
+/* -------- direct collocation: residual, Jacobian, cost, gradient --------
+ * Replaces what IPOPT calls back through opty.direct_collocation.Problem (06_optyplan.py:62-71,
+ * 07_multioptyplan.py:69-78): constraints(free), jacobian(free), obj(free), obj_grad(free), with the
+ * EoM of d2d/opty_utils.py:38-50 and the cost classes of d2d/opty_utils.py:55-165 and
+ * d2d/multiopty_utils.py:29-174. */
+enum { D2DX_JAC_COMPACT = 0, D2DX_JAC_OPTY_DENSE = 1 };
+enum { D2DX_EVAL_RESIDUAL = 1, D2DX_EVAL_JAC = 2, D2DX_EVAL_COST = 4, D2DX_EVAL_GRAD = 8 };
+#define D2DX_MAX_OBSTACLES 8
+
+typedef struct {
+  int32_t n_ac, N;           /* aircraft, collocation nodes                                      */
+  double h;                  /* node interval                                                    */
+  double wind[2];            /* constant wind of the planner (`+ w` in the EoM, opty_utils.py:42-43) */
+  /* input block order inside `free`: aircraft a's phi block is input block perm_phi[a], its v block
+   * is perm_v[a] (device int32 [n_ac] each, or NULL = the planner's numeric order,
+   * 07_multioptyplan.py:45-47).  opty itself sorts by name. */
+  const int32_t* perm_phi;
+  const int32_t* perm_v;
+  /* instance constraints free[var*N+node]-value (06_optyplan.py:46-49): device arrays [n_inst] */
+  int32_t n_inst;
+  const int32_t* inst_var;
+  const int32_t* inst_node;
+  const double* inst_val;
+  /* cost = obj_scale * ( (kvel*sum (v-vsp)^2 + kbank*sum phi^2) / (N*in_div)
+   *                      + kobs/N * sum_obstacles sum_i es + kcol/N * sum_pairs sum_i es ) */
+  double obj_scale, vsp, kvel, kbank;
+  int32_t in_div;            /* 1 single-aircraft classes, n_ac multi-aircraft classes           */
+  double kobs;               /* NaN or 0 disables (multiopty_utils.py:166)                       */
+  int32_t obs_kind, n_obs;   /* kind 0: clip(exp(r^2-d^2),0,1e3); kind 1: exp(-(2/r)^2 d^2)      */
+  double obs[D2DX_MAX_OBSTACLES][3];  /* cx, cy, r  -- applied to aircraft 0 (multiopty_utils.py:74) */
+  double kcol, rcol, kcol_k; /* CostCollision (multiopty_utils.py:120-153); NaN or 0 disables    */
+  int32_t col_all_pairs;     /* 0: aircraft (0,1) only as the reference; 1: all pairs            */
+  int32_t exact_grad;        /* 0: reference gradients (omit (k/r)^2); 1: exact      */
+} d2dx_colloc_problem;
+
+/* sizes: n_free=5*n_ac*N, n_con=3*n_ac*(N-1)+n_inst,
+ * nnz: compact 12*n_ac*(N-1)+n_inst, opty-dense (N-1)*3n_ac*8n_ac+n_inst  (host int64[3]) */
+int d2dx_colloc_sizes(const d2dx_colloc_problem* p_host, int32_t layout, int64_t* sizes_host3);
+/* COO structure of the Jacobian values (device int64 rows[nnz], cols[nnz]) */
+int d2dx_colloc_structure(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t layout,
+                          int64_t* rows, int64_t* cols, void* stream);
+/* one-time initialisation of an opty-dense value buffer (structural zeros + instance ones) for
+ * n_prob problems; d2dx_colloc_eval then only rewrites the non-zeros */
+int d2dx_colloc_init_dense(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t n_prob,
+                           double* jac, void* stream);
+/* Evaluates n_prob problems sharing one description: free[n_prob][n_free] ->
+ * residual[n_prob][n_con], jac[n_prob][nnz], cost[n_prob], grad[n_prob][n_free] (any may be NULL if
+ * its flag is clear).  scratch: device doubles, at least d2dx_colloc_scratch_size(...) elements. */
+int64_t d2dx_colloc_scratch_size(const d2dx_colloc_problem* p_host, int32_t n_prob);
+int d2dx_colloc_eval(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t n_prob,
+                     const double* free_, int32_t layout, uint32_t what, double* residual,
+                     double* jac, double* cost, double* grad, double* scratch, void* stream);
+/* Aircraft-sharded evaluation of ONE problem.  `p_local_host` describes THIS rank's shard as a
+ * problem of n_ac = number of owned aircraft (free_local, residual, jac (compact layout), grad all use the
+ * shard-local layout; in_div must be the TOTAL aircraft count).  The owned aircraft are global aircraft
+ * [a_lo, a_lo + n_ac) of n_ac_total; pos_all[n_ac_total][2][N] holds every aircraft's x,y -- the
+ * all-gathered positions, each rank contributing its contiguous [n_own][2][N] chunk.  cost[0] receives this
+ * rank's share (own input terms, obstacles if it owns aircraft 0, each pair counted once at the owner of
+ * its lower-index aircraft); the caller all-reduces it. */
+int d2dx_colloc_eval_shard(d2dx_handle* h, const d2dx_colloc_problem* p_local_host, int32_t n_ac_total,
+                           int32_t a_lo, const double* free_local, const double* pos_all, uint32_t what,
+                           double* residual, double* jac, double* cost, double* grad, double* scratch,
+                           void* stream);
+/* packs the x,y slices of a (shard-local) free vector into pos[n_ac][2][N], the all-gather send buffer */
+int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const double* free_local,
+                               double* pos, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2DX_H */

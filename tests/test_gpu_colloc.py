@@ -1,0 +1,175 @@
+"""Collocation kernel (through the C ABI) vs golden vectors derived from the reference's sympy EoM and cost
+classes.  Tolerance: north_star's 1e-10 relative on residuals and Jacobian entries."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _inst(g, tag):
+    return [(int(k), int(n), v) for (k, n, v) in g[f"{tag}/inst"]]
+
+
+@pytest.mark.parametrize("tag", ["c3", "c3w"])
+def test_c3_single_aircraft(golden, tag):
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    g = golden["colloc"]
+    N, h = 1001, 0.02
+    free, inst = g["c3/free"], _inst(g, "c3")
+    for layout in ("compact", "dense"):
+        prob = CollocationProblem(1, N, h, wind=g[f"{tag}/wind"], inst=inst, cost=CostSpec(vsp=12., kvel=1.), layout=layout)
+        assert prob.num_free == 5 * N and prob.num_constraints == 3 * (N - 1) + 6
+        res, jac, cost, grad = prob.evaluate(free)
+        np.testing.assert_allclose(res, g[f"{tag}/residual"], rtol=RTOL, atol=1e-11)
+        rows, cols = prob.jacobianstructure()
+        if layout == "dense":
+            np.testing.assert_allclose(jac[:-6], g[f"{tag}/jac_dense"].reshape(-1), rtol=RTOL, atol=0)
+            np.testing.assert_array_equal(rows[:-6], g["c3/rows"].reshape(-1))
+            np.testing.assert_array_equal(cols[:-6], g["c3/cols"].reshape(-1))
+        else:
+            D = np.zeros((3 * (N - 1) + 6, 5 * N)); D[rows, cols] = jac
+            D2 = np.zeros_like(D); np.add.at(D2, (g["c3/rows"].reshape(-1), g["c3/cols"].reshape(-1)), g[f"{tag}/jac_dense"].reshape(-1))
+            np.testing.assert_allclose(D[:-6], D2[:-6], rtol=RTOL, atol=0)
+        np.testing.assert_array_equal(jac[-6:], np.ones(6))
+        assert list(rows[-6:]) == list(range(3 * (N - 1), 3 * (N - 1) + 6))
+        assert list(cols[-6:]) == [0, N, 2 * N, N - 1, 2 * N - 1, 3 * N - 1]
+        np.testing.assert_allclose(cost, g["cost1/airvel/noisy/cost"], rtol=RTOL)
+        np.testing.assert_allclose(grad, g["cost1/airvel/noisy/grad"], rtol=RTOL, atol=1e-300)
+    # the cached IPOPT solution of the reference satisfies the constraints
+    prob = CollocationProblem(1, N, h, inst=inst)
+    assert np.abs(prob.con(g["c3/sol"])).max() < 1e-6
+
+
+SINGLE = {
+    "airvel": dict(vsp=12., kvel=1.), "bank": dict(kbank=1.), "input": dict(vsp=12., kvel=1., kbank=50.),
+    "obs0": dict(kobs=1., obstacles=[(30, 0, 15.)], obs_kind=0), "obs1": dict(kobs=1., obstacles=[(5, 15, 10.)], obs_kind=1),
+    "composit": dict(vsp=15., kvel=.5, kbank=1., kobs=.5, obstacles=[(5, 15, 10)], obs_kind=0),
+    "composit1": dict(vsp=12., kvel=.7, kbank=1.5, kobs=2., obstacles=[(5, 15, 10), (-3., 20., 6.)], obs_kind=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SINGLE))
+def test_single_aircraft_costs(golden, name):
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    g = golden["colloc"]
+    prob = CollocationProblem(1, 1001, 0.02, cost=CostSpec(**SINGLE[name]))
+    for tag, free in (("sol", g["c3/sol"]), ("noisy", g["c3/free"])):
+        np.testing.assert_allclose(prob.obj(free), g[f"cost1/{name}/{tag}/cost"], rtol=RTOL)
+        np.testing.assert_allclose(prob.obj_grad(free), g[f"cost1/{name}/{tag}/grad"], rtol=RTOL, atol=1e-300)
+
+
+MULTI = {
+    "input": dict(vsp=12., kvel=70., kbank=1.), "airvel": dict(vsp=12., kvel=1.), "bank": dict(kbank=1.),
+    "obs0": dict(kobs=1., obstacles=[(60., 5., 12.)], obs_kind=0), "obs1": dict(kobs=1., obstacles=[(60., 5., 12.)], obs_kind=1),
+    "collision": dict(kcol=1., rcol=10.),
+    "composit": dict(vsp=12., kvel=70., kbank=1., kobs=0.5, kcol=10., obstacles=[(60., 5., 12.), (-20., 30., 8.)], obs_kind=1, rcol=10.),
+    "composit_nocol": dict(vsp=12., kvel=2., kbank=1.),
+}
+
+
+@pytest.mark.parametrize("tag,n_ac,N,h", [("m3", 3, 20, 0.1), ("c4", 16, 500, 0.02)])
+def test_multi_aircraft(golden, tag, n_ac, N, h):
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    g = golden["colloc"]
+    free, inst = g[f"{tag}/free"], _inst(g, tag)
+    prob = CollocationProblem(n_ac, N, h, wind=g[f"{tag}/wind"], inst=inst, cost=CostSpec(**MULTI["composit"]))
+    res, jac, cost, grad = prob.evaluate(free)
+    np.testing.assert_allclose(res, g[f"{tag}/residual"], rtol=RTOL, atol=1e-10)
+    rows, cols = prob.jacobianstructure()
+    n, q = 3 * n_ac, 2 * n_ac
+    D = {}
+    # golden non-zeros: (N-1, nnz/node) at (eq, dense col) -> scatter both into dicts keyed by (row, col)
+    ee, cc = g[f"{tag}/nz_eq"], g[f"{tag}/nz_col"]
+    i = np.arange(N - 1)
+    ref = {}
+    for k, (e, c) in enumerate(zip(ee, cc)):
+        if c < n: col = c * N + i + 1
+        elif c < 2 * n: col = (c - n) * N + i
+        else: col = (n + (c - 2 * n)) * N + i + 1
+        for ii in (0, 1, N - 2):
+            ref[(e * (N - 1) + ii, int(col[ii]))] = g[f"{tag}/jac_nz"][ii, k]
+    got = {(int(r), int(c)): v for r, c, v in zip(rows, cols, jac)}
+    for key, v in ref.items():
+        assert abs(got[key] - v) <= RTOL * abs(v), key
+    # full compare through a dense scatter on the small case
+    if tag == "m3":
+        Dg = np.zeros((prob.num_constraints, prob.num_free)); Dg[rows, cols] = jac
+        pd = CollocationProblem(n_ac, N, h, wind=g[f"{tag}/wind"], inst=inst, layout="dense")
+        jd = pd.con_jac(free); rd, cd = pd.jacobianstructure()
+        np.testing.assert_allclose(jd[:-len(inst)], g["m3/jac_dense"].reshape(-1), rtol=RTOL, atol=0)
+        Dd = np.zeros_like(Dg); np.add.at(Dd, (rd, cd), jd)
+        np.testing.assert_array_equal(Dg, Dd)
+    np.testing.assert_allclose(cost, g[f"{tag}/cost/composit/cost"], rtol=RTOL)
+    np.testing.assert_allclose(grad, g[f"{tag}/cost/composit/grad"], rtol=RTOL, atol=1e-14)
+    for name, spec in MULTI.items():
+        p2 = CollocationProblem(n_ac, N, h, cost=CostSpec(**spec))
+        np.testing.assert_allclose(p2.obj(free), g[f"{tag}/cost/{name}/cost"], rtol=RTOL, err_msg=name)
+        gr, ref_g = p2.obj_grad(free), g[f"{tag}/cost/{name}/grad"]
+        if len(ref_g) != len(gr): gr = gr[::7]
+        np.testing.assert_allclose(gr, ref_g, rtol=RTOL, atol=1e-14, err_msg=name)
+
+
+def test_all_pairs_collision_and_batch_against_oracle():
+    """All-pairs generalisation and a batch of problems in one launch, vs the oracle."""
+    from oracle import d2d_oracle as orc
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    rng = np.random.default_rng(11)
+    n_ac, N, h, n_prob = 7, 150, 0.05, 9
+    free = rng.normal(0, 8., (n_prob, 5 * n_ac * N)); free[:, 4 * n_ac * N:] = 12 + rng.normal(0, 1, (n_prob, n_ac * N))
+    for exact in (False, True):
+        spec = dict(vsp=12., kvel=3., kbank=2., kcol=10., rcol=10., pairs="all", exact_grad=exact, kobs=1.5, obstacles=[(1., 2., 6.)], obs_kind=1)
+        prob = CollocationProblem(n_ac, N, h, wind=(1., 2.), cost=CostSpec(vsp=12., kvel=3., kbank=2., kcol=10., rcol=10., all_pairs=True,
+                                  exact_grad=exact, kobs=1.5, obstacles=[(1., 2., 6.)], obs_kind=1))
+        res, jac, cost, grad = prob.evaluate(free)
+        for p in range(n_prob):
+            np.testing.assert_allclose(res[p], orc.colloc_residual(free[p], N, n_ac, h, (1., 2.), []), rtol=RTOL, atol=1e-10)
+            np.testing.assert_allclose(jac[p], orc.colloc_jac_compact(free[p], N, n_ac, h).reshape(-1), rtol=RTOL)
+            co, go = orc.cost_and_grad(free[p], N, n_ac, spec, multi=True)
+            np.testing.assert_allclose(cost[p], co, rtol=RTOL)
+            np.testing.assert_allclose(grad[p], go, rtol=RTOL, atol=1e-13)
+    rows, cols = prob.jacobianstructure()
+    ro, co_ = orc.colloc_structure(N, n_ac, [], "compact")
+    np.testing.assert_array_equal(rows, ro); np.testing.assert_array_equal(cols, co_)
+
+
+def test_opty_name_sorted_input_order(golden):
+    """12 aircraft: opty orders phi10, phi11 before phi2; the permuted problem evaluated on the
+    permuted free vector equals the numeric-order problem."""
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    names = [str(s) for s in golden["colloc"]["sorted_inputs_12"]]
+    n_ac, N, h = 12, 40, 0.1
+    rng = np.random.default_rng(2)
+    free = rng.normal(0, 5., 5 * n_ac * N); free[4 * n_ac * N:] += 12
+    cs = CostSpec(vsp=12., kvel=1., kbank=1.)
+    a = CollocationProblem(n_ac, N, h, cost=cs)
+    b = CollocationProblem(n_ac, N, h, cost=cs, input_order="opty")
+    numeric = [f"phi{i}(t)" for i in range(n_ac)] + [f"v{i}(t)" for i in range(n_ac)]
+    fp = free.copy()
+    for k, nm in enumerate(names):
+        src = numeric.index(nm)
+        fp[(3 * n_ac + k) * N:(3 * n_ac + k + 1) * N] = free[(3 * n_ac + src) * N:(3 * n_ac + src + 1) * N]
+    ra, ja, ca, ga = a.evaluate(free)
+    rb, jb, cb, gb = b.evaluate(fp)
+    np.testing.assert_array_equal(ra, rb); np.testing.assert_array_equal(ja, jb); assert ca == cb
+    for k, nm in enumerate(names):
+        src = numeric.index(nm)
+        np.testing.assert_array_equal(gb[(3 * n_ac + k) * N:(3 * n_ac + k + 1) * N], ga[(3 * n_ac + src) * N:(3 * n_ac + src + 1) * N])
+
+
+def test_sharded_evaluation_single_gpu_emulation(golden):
+    """The aircraft-sharded entry point (C4 over 8 ranks, 2 aircraft each) emulated on one GPU: per-shard
+    outputs concatenated = the unsharded evaluation; shard costs sum to the total."""
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    from d2d_b200 import distributed
+    g = golden["colloc"]
+    n_ac, N, h = 16, 500, 0.02
+    free, inst = g["c4/free"], _inst(g, "c4")
+    cs = CostSpec(vsp=12., kvel=70., kbank=1., kcol=10., rcol=10., all_pairs=True, kobs=0.5, obstacles=[(60., 5., 12.)], obs_kind=1)
+    full = CollocationProblem(n_ac, N, h, inst=inst, cost=cs)
+    res, jac, cost, grad = full.evaluate(free)
+    parts = distributed.emulate_sharded_eval(n_ac, N, h, (0., 0.), inst, cs, free, world=8)
+    np.testing.assert_allclose(parts["residual"], res, rtol=0, atol=0)
+    np.testing.assert_allclose(parts["jac"], jac, rtol=0, atol=0)
+    np.testing.assert_allclose(parts["grad"], grad, rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(parts["cost"], cost, rtol=1e-13)

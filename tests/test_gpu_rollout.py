@@ -1,0 +1,223 @@
+"""CUDA path (through the C ABI) vs the golden vectors of the unmodified reference and vs the oracle.
+Tolerance: north_star's 1e-9 absolute on per-step states under the same fixed-step integrator and dt."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def d2d():
+    import d2d_b200
+    from d2d_b200 import simulation, trajectory, trajectory_factory, scenario, guidance, dynamic
+    d2d_b200.get_engine()
+    return d2d_b200
+
+
+def test_c1_against_reference_golden(d2d, golden):
+    from d2d_b200 import simulation, trajectory
+    g = golden["dfff_c1"]
+    res = simulation.rollout(g["time"], [trajectory.TrajectoryCircle(alpha0=3 * np.pi / 2)], g["wind"], g["X0"][None], log_ref=True)
+    assert res.flags[0] == 0
+    np.testing.assert_allclose(res.X[0], g["X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.U[0], g["U"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.Xref[0], g["Xref"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.K[0], g["K"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.X_final[0], g["X"][-1], rtol=0, atol=TOL)
+    # per-scenario reductions = what the log implies
+    d2 = np.sum(np.square(g["X"][:, :2] - g["Xref"][:, :2]), axis=1)
+    np.testing.assert_allclose(res.sum_sq_err[0], d2.sum(), rtol=1e-9)
+    np.testing.assert_allclose(res.max_err[0], np.sqrt(d2.max()), rtol=1e-9)
+    print("C1 max |dX| =", np.abs(res.X[0] - g["X"]).max(), " max |dK| =", np.abs(res.K[0] - g["K"]).max())
+
+
+def test_c1_drop_in_run_simulation(d2d, golden):
+    """The reference's own call sequence (05_test_simulation.py:37-53) on the mirrored classes."""
+    from d2d_b200 import dynamic, guidance, simulation, trajectory
+    g = golden["dfff_c1"]
+    traj = trajectory.TrajectoryCircle(alpha0=3 * np.pi / 2)
+    ac, wind = dynamic.Aircraft(), guidance.WindField([5, 0])
+    ctl = guidance.DFFFController(traj, ac, wind)
+    X, U, Yref = simulation.run_simulation(g["time"], ac, wind, ctl, g["X0"], np.zeros((len(g["time"]), 5)))
+    np.testing.assert_allclose(X, g["X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(U, g["U"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(Yref, g["Yref"], rtol=0, atol=1e-12)
+    assert len(ctl.Xref) == len(g["time"]) and np.asarray(ctl.K).shape == (len(g["time"]), 2, 5)
+
+
+def test_chunked_rollout_equals_single_launch(d2d, golden):
+    from d2d_b200 import simulation, trajectory
+    g = golden["dfff_c1"]
+    tr = [trajectory.TrajectoryCircle(alpha0=3 * np.pi / 2)]
+    a = simulation.rollout(g["time"], tr, g["wind"], g["X0"][None])
+    b = simulation.rollout(g["time"], tr, g["wind"], g["X0"][None], chunk_steps=137)
+    np.testing.assert_allclose(a.X, b.X, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(a.sum_sq_err, b.sum_sq_err, rtol=1e-13)
+    c = simulation.rollout(g["time"], tr, g["wind"], g["X0"][None], log_every=10)
+    np.testing.assert_array_equal(c.X[0], a.X[0][::10])
+
+
+SCENS = ["line", "line2", "square", "mucir", "mucir2", "patrol", "patrol_2", "patrol_3", "circForm"]
+
+
+@pytest.mark.parametrize("name", SCENS)
+def test_scenario_registry_against_reference_golden(d2d, golden, name):
+    """Every runnable scenario of d2d/scenario.py, all aircraft in one launch, full length."""
+    from d2d_b200 import scenario, simulation
+    g = golden["dfff_scenarios"]
+    scen, _ = scenario.get(name)
+    assert len(scen.time) == int(g[f"{name}/0/T"])
+    Xs, Us, Yrefs = simulation.test_simulation(scen)
+    for i in range(len(scen.trajs)):
+        np.testing.assert_allclose(Yrefs[i][::25], g[f"{name}/{i}/Yref"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(Xs[i][::5], g[f"{name}/{i}/X"], rtol=0, atol=TOL)
+        np.testing.assert_allclose(Us[i][::5], g[f"{name}/{i}/U"], rtol=0, atol=TOL)
+        np.testing.assert_allclose(Xs[i][-1], g[f"{name}/{i}/Xlast"], rtol=0, atol=TOL)
+        np.testing.assert_allclose(Us[i][-1], g[f"{name}/{i}/Ulast"], rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("name", ["minsnap", "sidemo", "slalom"])
+def test_extra_trajectories_against_reference_golden(d2d, golden, name):
+    from d2d_b200 import simulation, trajectory_factory as ddtf
+    g = golden["dfff_scenarios"]
+    traj = {"minsnap": ddtf.TrajMinSnapDemo, "sidemo": ddtf.TrajSiDemo, "slalom": ddtf.TrajSlalom}[name]()
+    time = np.arange(0., traj.duration, 0.01)
+    assert len(time) == int(g[f"{name}/0/T"])
+    np.testing.assert_allclose(traj.get_many(time[::25]), g[f"{name}/0/Yref"], rtol=0, atol=1e-11)
+    res = simulation.rollout(time, [traj], g[f"{name}/0/wind"], g[f"{name}/0/X0"][None], log_ref=True)
+    np.testing.assert_allclose(res.X[0][::5], g[f"{name}/0/X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.U[0][::5], g[f"{name}/0/U"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.K[0][::25], g[f"{name}/0/K"], rtol=0, atol=TOL)
+
+
+def test_single_calls_against_reference_golden(d2d, golden):
+    """Aircraft.cont_dyn / cont_jac, DiffFlatness, LQR gain, min-snap coefficients."""
+    from d2d_b200 import dynamic, guidance, trajectory_factory as ddtf
+    u = golden["units"]
+    ac = dynamic.Aircraft()
+    Xr, Ur, Xd = guidance.DiffFlatness.state_and_input_from_output(u["Ys"], u["Ws"], ac)
+    np.testing.assert_allclose(Xr, u["Xr"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(Ur, u["Ur"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(Xd, u["Xrdot"], rtol=1e-13, atol=1e-13)
+    A, B = ac.cont_jac(u["Xr"], u["Ur"], 0., None)
+    np.testing.assert_allclose(A, u["A"], rtol=1e-13, atol=1e-14)
+    assert B[0][3, 0] == 1 / ac.tau_phi and B[0][4, 1] == 1 / ac.tau_v
+    eng = d2d.get_engine()
+    Xdot = eng.cont_dyn(eng.to_device(u["Xs"].T.copy()), eng.to_device(u["Us"].T.copy()), eng.to_device(u["Ws"].T.copy()),
+                        eng.to_device(np.tile([[0.01], [1.]], (1, len(u["Xs"]))))).cpu().numpy().T
+    np.testing.assert_allclose(Xdot, u["Xdot"], rtol=1e-13, atol=1e-13)
+    one = ac.cont_dyn(u["Xs"][0], 0., u["Us"][0], guidance.WindField(list(u["Ws"][0])))
+    assert isinstance(one, list) and len(one) == 5
+    np.testing.assert_allclose(one, u["Xdot"][0], rtol=1e-13)
+    ms = ddtf.TrajMinSnapDemo()
+    np.testing.assert_array_equal(np.array([p.coefs for p in ms._polys]), u["minsnap_coefs"])
+    np.testing.assert_allclose(ms.get(10.0), u["minsnap_get10"], rtol=0, atol=1e-12)
+
+
+def test_lqr_gain_over_wide_range_against_oracle(d2d):
+    """The in-kernel Riccati solve vs scipy's CARE (through the oracle) far outside the flight envelope."""
+    from oracle import d2d_oracle as orc
+    from d2d_b200 import trajectory
+    eng = d2d.get_engine()
+    rng = np.random.default_rng(5)
+    n = 256
+    v = np.exp(rng.uniform(np.log(1.0), np.log(40.), n)); r = rng.uniform(8., 80., n) * rng.choice([-1, 1], n)
+    wind = rng.normal(0, 1.5, (n, 2))
+    batch = trajectory.CircleBatch(rng.uniform(-50, 50, n), rng.uniform(-50, 50, n), r, v, rng.uniform(0, 6.28, n))
+    tab = eng.table(batch.pack())
+    X = rng.normal(0, 1, (n, 5)); t = 1.234
+    acd = eng.to_device(np.tile([[0.01], [1.]], (1, n)))
+    U, Xr, K = eng.dfff_control(tab, eng.to_device(X.T.copy()), t, eng.to_device(wind.T.copy()), acd)
+    K = K.cpu().numpy().T.reshape(n, 2, 3); Xr = Xr.cpu().numpy().T
+    worst = 0.
+    for i in range(n):
+        tr = orc.Circle(c=[batch.cx[i], batch.cy[i]], r=r[i], v=v[i], alpha0=batch.alpha0[i])
+        _, Xro, Ko = orc.dfff_control(tr, X[i].copy(), t, wind[i])
+        np.testing.assert_allclose(Xr[i], Xro, rtol=1e-12, atol=1e-12)
+        worst = max(worst, np.abs(K[i] - Ko).max() / max(1., np.abs(Ko).max()))
+    assert worst < 1e-10, worst
+
+
+def test_monte_carlo_population_against_oracle(d2d):
+    """A seeded C5-style population (random circles, wind, initial states): 48 scenarios x 300 steps against the
+    Python oracle, every step."""
+    from oracle import d2d_oracle as orc
+    from d2d_b200 import simulation, trajectory
+    rng = np.random.default_rng(12345)
+    B, T = 48, 301
+    cx, cy = rng.uniform(-50, 50, B), rng.uniform(-50, 50, B)
+    r, v, a0 = rng.uniform(20, 60, B), rng.uniform(10, 15, B), rng.uniform(0, 2 * np.pi, B)
+    wind = rng.normal(0, 2.5, (B, 2))
+    time = np.arange(0, T * 0.01 - 1e-9, 0.01)
+    X0 = np.zeros((B, 5))
+    for b in range(B):
+        X0[b] = orc.flatness(orc.Circle([cx[b], cy[b]], r[b], v[b], alpha0=a0[b]).get(0.), wind[b])[0]
+    X0 += rng.normal(0, 1, (B, 5)) * np.array([5, 5, 0.2, 0.05, 0.5])
+    res = simulation.rollout(time, trajectory.CircleBatch(cx, cy, r, v, a0), wind, X0)
+    assert not res.flags.any()
+    worst = 0.
+    for b in range(B):
+        Xo, Uo, _, _, _ = orc.run_simulation(time, orc.Circle([cx[b], cy[b]], r[b], v[b], alpha0=a0[b]), wind[b], X0[b])
+        worst = max(worst, np.abs(res.X[b] - Xo).max(), np.abs(res.U[b] - Uo).max())
+    print("population worst |d| =", worst)
+    assert worst < TOL
+
+
+def test_formation_c2_against_reference_golden(d2d, golden):
+    from d2d_b200 import simulation
+    g = golden["formation"]
+    X, U, time, _, _, Rr, eth = simulation.CircularFormationGVF(np.array([0, 0]), 60, 6, 60)
+    assert len(time) == int(g["c2/T"])
+    np.testing.assert_allclose(X[::4], g["c2/X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(U[::4], g["c2/U"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(Rr[::4], g["c2/Rr"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(eth[::4], g["c2/eth"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(X[-1], g["c2/Xlast"], rtol=0, atol=TOL)
+
+
+def test_formation_script09_and_reference_csv(d2d, golden):
+    """Script 09's configuration (4 aircraft, own centres) and the reference's fixture src/states_over_time.csv."""
+    from d2d_b200 import simulation
+    g = golden["formation"]
+    c9 = np.array([[0, -20], [25, -40], [25, -80], [0, -100]], dtype=float)
+    X, U, time, _, _, Rr, eth = simulation.CircularFormationGVF(c9, 60, 4, 60, kd=25, z_des=np.zeros(3))
+    np.testing.assert_allclose(X[::4], g["s09/X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(Rr[::4], g["s09/Rr"], rtol=0, atol=1e-8)
+    X, *_ = simulation.CircularFormationGVF(c9, 60, 4, 200, kd=25, z_des=np.zeros(3), nsub=1, tau_phi=0.9667)
+    np.testing.assert_allclose(X[::20], g["csv_rk4_1/X"], rtol=0, atol=1e-8)
+    assert np.abs(X[::20] - g["csv/X"]).max() < 2e-3         # vs the LSODA-integrated CSV: integrator gap only
+
+
+def test_formation_batch_is_replicated_single(d2d):
+    """Many formations in one launch (5 per warp for n_ac = 6) give the single-formation answer."""
+    from d2d_b200 import simulation
+    n_ac, F = 6, 37
+    z = np.ones(n_ac - 1) * 2 * np.pi / n_ac
+    X1 = np.array([20, 30, -np.pi / 2, 0, 10.])
+    one = simulation.formation_rollout(np.zeros((1, n_ac, 2)), 60., n_ac, 200, 0.05, 4e-4, 15, 20, z, X1)
+    many = simulation.formation_rollout(np.zeros((F, n_ac, 2)), 60., n_ac, 200, 0.05, 4e-4, 15, 20, z, X1)
+    for f in range(F):
+        np.testing.assert_array_equal(many["X"][f], one["X"][0])
+
+
+def test_dcf_and_gvf_single_calls(d2d, golden):
+    from d2d_b200 import guidance, simulation
+    from oracle import d2d_oracle as orc
+    g = golden["formation"]
+    X = np.array([20, 30, -np.pi / 2, 0, 10.])
+    tr = guidance.CircleTraj(np.array([0, -20]))
+    e, n, H = tr.get(X, 60)
+    U, U1, U2 = guidance.GVFcontroller(tr, None, None).get(X, 4e-4, 25, e, n, H)
+    np.testing.assert_allclose([e, n[0], n[1], U, U1, U2], g["gvf_known"], rtol=1e-12)
+    rng = np.random.default_rng(3)
+    n_ac = 5
+    p, c = rng.normal(0, 40, (2, n_ac)), rng.normal(0, 5, (n_ac, 2))
+    B = simulation.chain_incidence(n_ac); z = np.ones(n_ac - 1) * 2 * np.pi / n_ac
+    Ur, e_deg = guidance.DCFController().get(n_ac, B, c, p, z, 20)
+    Uo, eo = orc.dcf(B, c, p, z, 20)
+    np.testing.assert_allclose(Ur[:, 0], Uo, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(e_deg[:, 0], eo, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        guidance.DCFController().get(n_ac, B, np.array([0., 0.]), p, z, 20)      # 1-D centre, cf. SURVEY D2
