@@ -1,0 +1,299 @@
+#!/usr/bin/env python3
+"""Headline benchmark: closed-loop aircraft-steps/s on the Monte-Carlo sweep (BASELINE.json configs[4], SURVEY 8d
+config C5): 10^6 aircraft-scenarios per GPU x 10^4 RK4 steps, dt = 0.01 s, random circles / wind / initial states,
+DFFF controller, log decimated x100.  One bench "step" = one full sweep.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA engine
+    python bench.py --impl reference ...                           # the CPU arm (C port of the oracle, all host threads)
+
+Prints ONE JSON line (contract in the task statement: value = device-resident throughput, e2e = through the public
+host-buffer API with H2D/D2H inside the timed region, roofline, cpu_baseline, clocks, gpu_launches)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time as _time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "drone-sim-python_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "closed-loop aircraft-steps/s"
+UNIT = "aircraft-steps/s"
+# Executed fp64 flop per aircraft-step of rollout_dfff_kernel<CIRCLE> (DADD + DMUL + 2 x DFMA thread-instructions
+# from the ncu capture under profiles/, divided by scenarios x steps); see DESIGN.md "Roofline accounting".
+FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "1090"))
+LOG_BYTES_PER_LOGGED_SAMPLE = 56          # 5 state + 2 input doubles
+
+
+def workload(B, seed):
+    """C5 population: circles c ~ U([-50,50]^2), r ~ U(20,60), v ~ U(10,15), alpha0 ~ U(0,2pi);
+    wind ~ N(0, 2.5^2) per axis, redrawn while |w| > 0.4 v; X0 = flat state(t=0) + N(0, diag(5,5,.2,.05,.5)^2)."""
+    rng = np.random.default_rng(seed)
+    cx, cy = rng.uniform(-50, 50, B), rng.uniform(-50, 50, B)
+    r, v, a0 = rng.uniform(20, 60, B), rng.uniform(10, 15, B), rng.uniform(0, 2 * np.pi, B)
+    wind = rng.normal(0, 2.5, (B, 2))
+    for _ in range(64):
+        bad = np.hypot(wind[:, 0], wind[:, 1]) > 0.4 * v
+        if not bad.any():
+            break
+        wind[bad] = rng.normal(0, 2.5, (int(bad.sum()), 2))
+    noise = rng.normal(0, 1, (B, 5)) * np.array([5, 5, 0.2, 0.05, 0.5])
+    return dict(cx=cx, cy=cy, r=r, v=v, a0=a0, wind=wind, noise=noise)
+
+
+def flat_state0(w):
+    """Flat state at t = 0 of every circle (closed form of d2d/guidance.py:23-47 on d2d/trajectory.py:153-160);
+    workload generation only -- both arms start from these X0."""
+    om = w["v"] / w["r"]
+    ca, sa = np.cos(w["a0"]), np.sin(w["a0"])
+    y0 = np.stack([w["cx"] + w["r"] * ca, w["cy"] + w["r"] * sa], 1)
+    y1 = np.stack([om * w["r"] * -sa, om * w["r"] * ca], 1)
+    y2 = np.stack([om ** 2 * w["r"] * -ca, om ** 2 * w["r"] * -sa], 1)
+    vax, vay = y1[:, 0] - w["wind"][:, 0], y1[:, 1] - w["wind"][:, 1]
+    va = np.sqrt(vax ** 2 + vay ** 2)
+    phi = np.arctan((y2[:, 1] * vax - y2[:, 0] * vay) / va / 9.81)
+    return np.stack([y0[:, 0], y0[:, 1], np.arctan2(vay, vax), phi, va], 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[6]) for r in self.rows if len(r) >= 7 and r[6].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows and self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def cpu_port_run(B, T_steps, seed, nthreads=0, reps=1):
+    """The oracle's C port on the host cores over a bounded sample of the same workload; returns (steps/s, cores, text)."""
+    from oracle import c_oracle as co
+    w = workload(B, seed)
+    X0 = flat_state0(w) + w["noise"]
+    ty, par = co.circle_par(w["cx"], w["cy"], w["r"], w["v"], w["a0"])
+    time = np.arange(T_steps + 1) * 0.01
+    cores = nthreads or co.max_threads()
+    best = 0.
+    for _ in range(reps):
+        t0 = _time.perf_counter()
+        out = co.rollout(time, ty, par, w["wind"], X0, want_log=False, nthreads=cores)
+        dt = _time.perf_counter() - t0
+        best = max(best, B * T_steps / dt)
+    return best, cores, f"first {B} scenarios x {T_steps} steps of the C5 population (seed {seed}), no log, {cores} threads", out
+
+
+def python_port_rate():
+    """The NumPy/SciPy oracle (the reference's own numerics: SciPy CARE every step) on one core, tiny sample."""
+    from oracle import d2d_oracle as orc
+    w = workload(2, 12345)
+    X0 = flat_state0(w) + w["noise"]
+    time = np.arange(151) * 0.01
+    t0 = _time.perf_counter()
+    for b in range(2):
+        orc.run_simulation(time, orc.Circle([w["cx"][b], w["cy"][b]], w["r"][b], w["v"][b], alpha0=w["a0"][b]), w["wind"][b], X0[b])
+    return 2 * 150 / (_time.perf_counter() - t0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="d2dx", choices=["d2dx", "reference"])
+    ap.add_argument("--scenarios", type=int, default=int(os.environ.get("D2DX_BENCH_B", 10 ** 6)), help="aircraft-scenarios per GPU")
+    ap.add_argument("--horizon", type=int, default=int(os.environ.get("D2DX_BENCH_T", 10 ** 4)), help="RK4 steps per scenario")
+    ap.add_argument("--log-every", type=int, default=100)
+    ap.add_argument("--chunks", type=int, default=10)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--seed", type=int, default=12345)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "C5 Monte-Carlo sweep: DFFF closed loop on random circles", "scenarios_per_gpu": args.scenarios,
+              "rk4_steps": args.horizon, "dt": 0.01, "nsub": 1, "log_every": args.log_every, "parallelism": f"scenario-sharded x{world}",
+              "l2_policy": "inputs exceed L2 (>= 176 MB of per-scenario state per sweep; compute-bound kernel)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample per step: ~1.5 s per thread-batch; the same population, first scenarios, first 1000 steps
+        from oracle import c_oracle as co
+        cores = co.max_threads()
+        Bc, Tc = 256 * cores, min(1000, args.horizon)
+        rates = []
+        for k in range(args.warmup + args.steps):
+            rate, cores, sample, _ = cpu_port_run(Bc, Tc, args.seed)
+            if k >= args.warmup:
+                rates.append(rate)
+        val = float(np.mean(rates))
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * Bc * Tc / val, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                 "note": "C port of the oracle (generic 3x3 CARE per step, pthreads); the reference itself is "
+                                         "single-threaded Python (366 steps/s/core measured in the survey)"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the engine arm")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from d2d_b200 import _lib, get_engine
+    from d2d_b200.distributed import reduce_population_stats
+    from d2d_b200.simulation import MonteCarloRollout
+
+    eng = get_engine()
+    B, T_steps = args.scenarios, args.horizon
+    time = np.arange(T_steps + 1) * 0.01               # = np.arange(0, (T+1)*0.01, 0.01) sample grid
+    w = workload(B, args.seed + rank)
+    X0 = flat_state0(w) + w["noise"]
+    host_log = not args.no_e2e
+    try:
+        mc = MonteCarloRollout(B, time, _lib.SEG_CIRCLE, nsub=1, log_every=args.log_every, n_chunks=args.chunks, host_log=host_log)
+    except RuntimeError as e:                           # pinned log buffers did not fit: keep the results, drop the host log
+        host_log = False
+        mc = MonteCarloRollout(B, time, _lib.SEG_CIRCLE, nsub=1, log_every=args.log_every, n_chunks=args.chunks, host_log=False)
+        config["host_log"] = f"disabled ({type(e).__name__})"
+    par = np.zeros((6, B))
+    par[1], par[2], par[3], par[4], par[5] = w["cx"], w["cy"], w["r"], w["v"] / w["r"], w["a0"]
+    mc.set_inputs(par, w["wind"], X0)
+    mc.upload()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(args.warmup):
+        mc.run_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        evs[k][0].record()
+        mc.run_device()
+        evs[k][1].record()
+    e1.record()
+    barrier()
+    launches = eng.launches - l0
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    pop = reduce_population_stats(mc.d_pop.clone())
+    flags_bad = int(mc.d_flags.ne(0).sum().item())
+    ms_per_step = ms_total / max(args.steps, 1)
+    total_steps = float(B) * T_steps * world
+    value = total_steps / (ms_per_step * 1e-3)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs])) / mc.launches_per_run     # avg duration of ONE launch
+
+    # ---- end-to-end through the host-buffer API (`e2e`) ----
+    e2e = None
+    if not args.no_e2e:
+        mc.run()                                         # warm the copy paths
+        barrier()
+        t0 = _time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(n_e2e):
+            out = mc.run()
+        c1.record()
+        barrier()
+        wall_ms = 1e3 * (_time.perf_counter() - t0)      # run() returns only after every copy has landed
+        ms_e2e = reduce_max(max(c0.elapsed_time(c1), wall_ms)) / n_e2e
+        e2e = {"value": total_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(mc.h2d_bytes), "d2h_bytes_per_step": int(mc.d2h_bytes),
+               "ms_per_step": ms_e2e, "host_log": host_log, "api": "d2d_b200.simulation.MonteCarloRollout.run (pinned host buffers in/out)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rollout_dfff_kernel<CIRCLE>) ----
+    peak_tf = eng.measure_fp64_peak()
+    steps_per_launch = float(B) * (T_steps / mc.launches_per_run)
+    ach_tf = steps_per_launch * FP64_FLOP_PER_STEP / (kernel_ms * 1e-3) / 1e12
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    log_bytes = steps_per_launch / args.log_every * LOG_BYTES_PER_LOGGED_SAMPLE
+    roofline = {"bound": "fp64", "kernel": "rollout_dfff_kernel<CIRCLE>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_tf, "peak_source": "DFMA probe kernel timed in this run (MEASURED_PEAKS.json has no fp64 figure); nominal 37.2",
+                "flop_per_aircraft_step": FP64_FLOP_PER_STEP, "kernel_ms": kernel_ms, "steps_per_launch": steps_per_launch,
+                "traffic": None,
+                "hbm": {"achieved_gbs": log_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak or 6650.0,
+                        "peak_source": "measured (MEASURED_PEAKS.json)" if hbm_peak else "fallback"}}
+    cpu = None
+    if not args.no_cpu:
+        from oracle import c_oracle as co
+        cores = co.max_threads()
+        rate, cores, sample, _ = cpu_port_run(512 * cores, min(1000, T_steps), args.seed)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "python_port_1core": python_port_rate()}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "checks": {"nonfinite_or_unconverged_scenarios": flags_bad, "population_rms_pos_err": float(np.sqrt(pop[0].item() / (B * world * (T_steps + 1)))),
+                       "population_max_pos_err": float(pop[1].item())}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

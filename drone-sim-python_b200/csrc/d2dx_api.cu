@@ -140,11 +140,35 @@ __global__ void __launch_bounds__(kThreads) dfff_control_kernel(const d2dx_traj_
   if (care_state) { care_state[b] = cs.C; care_state[B + b] = cs.S; care_state[2 * (size_t)B + b] = cold ? 0.0 : cs.al; }
 }
 
+// FP64 pipe probe: 16 independent DFMA chains per thread
+__global__ void dfma_burn_kernel(int iters, double* sink) {
+  double a[16];
+  const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-12 * (blockIdx.x + 1);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = k * 0.5;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 123.456) *sink = s;
+}
+
 }  // namespace d2dx
 
 using namespace d2dx;
 
 extern "C" {
+
+int d2dx_dfma_burn(d2dx_handle* h, int32_t blocks, int32_t threads, int32_t iters, double* sink, void* stream) {
+  D2DX_CHECK_ARG(h && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, "d2dx_dfma_burn: bad argument");
+  D2DX_CUDA(cudaSetDevice(h->device));
+  dfma_burn_kernel<<<blocks, threads, 0, as_stream(stream)>>>(iters, sink);
+  D2DX_LAUNCH_CHECK("dfma_burn_kernel");
+  return D2DX_OK;
+}
 
 int d2dx_version(void) { return D2DX_VERSION; }
 const char* d2dx_last_error(void) { return g_err; }

@@ -177,3 +177,113 @@ def CircularFormationGVF(c, r, n_ac, t_end, ke=0.0004, kd=15, kr=20, z_des=None,
     o = formation_rollout(c_[None], r, n_ac, len(time), t_step, ke, kd, kr, z_des, X1, nsub=nsub, tau_phi=tau_phi)
     zeros = np.zeros((len(time), n_ac))
     return o["X"][0], o["U"][0], time, zeros, zeros.copy(), o["Rr"][0], o["e_theta"][0]
+
+
+class MonteCarloRollout:
+    """Monte-Carlo sweep of B independent plain-circle (or min-snap) scenarios with
+    persistent pinned host buffers and device buffers.
+
+    `run()` is the host-facing call: asynchronous H2D of the inputs from pinned memory, the rollout in
+    `n_chunks` launches, and D2H of the decimated logs of chunk k on a copy stream while chunk k+1 computes;
+    it returns NumPy views of the pinned result buffers.  `run_device()` is the same sweep with the inputs
+    already resident in HBM and nothing copied back."""
+
+    def __init__(self, B, time, seg_type, nsub=1, log_every=100, n_chunks=10, log_u=True, host_log=True, engine=None):
+        from . import _lib
+        from .engine import PackedTrajectories
+        self.eng = eng = engine or get_engine()
+        self.B, self.nsub, self.log_every = int(B), int(nsub), int(log_every)
+        self.time = np.ascontiguousarray(time, dtype=np.float64)
+        self.T = len(self.time)
+        self.n_rows = (self.T - 1) // self.log_every + 1
+        self.seg_type = int(seg_type)
+        self.n_par_rows = {_lib.SEG_CIRCLE: 6, _lib.SEG_LINE: 5}.get(self.seg_type, _lib.SEG_NPAR)
+        pin = lambda *shape, dtype=torch.float64: torch.empty(*shape, dtype=dtype).pin_memory()
+        B = self.B
+        # pinned host inputs / outputs
+        self.h_X0, self.h_wind, self.h_ac, self.h_par = pin(5, B), pin(2, B), pin(2, B), pin(self.n_par_rows, B)
+        self.h_Xf, self.h_ss, self.h_mx, self.h_flags = pin(5, B), pin(B), pin(B), pin(B, dtype=torch.int32)
+        self.h_pop = pin(2)
+        self.host_log, self.log_u = host_log, log_u
+        self.h_Xlog = pin(self.n_rows, 5, B) if host_log else None
+        self.h_Ulog = pin(self.n_rows, 2, B) if (host_log and log_u) else None
+        # device buffers
+        self.d_X0, self.d_wind, self.d_ac = eng.empty(5, B), eng.empty(2, B), eng.empty(2, B)
+        par = eng.zeros(_lib.SEG_NPAR, B)
+        ar = np.arange(B, dtype=np.int32)
+        self.table = eng.table(PackedTrajectories(ar, np.ones(B, np.int32), np.zeros(B), np.zeros(B),
+                                                  np.full(B, self.seg_type, np.int32), np.zeros(B), np.zeros((_lib.SEG_NPAR, B)),
+                                                  self.seg_type))
+        self.d_par = self.table.t["seg_par"]
+        del par
+        self.d_time = eng.to_device(self.time)
+        self.d_Xlog = eng.empty(self.n_rows, 5, B)
+        self.d_Ulog = eng.empty(self.n_rows, 2, B) if log_u else None
+        self.d_Xf, self.d_Xa, self.d_Xb = eng.empty(5, B), eng.empty(5, B), eng.empty(5, B)
+        self.d_ss, self.d_mx, self.d_flags = eng.zeros(B), eng.zeros(B), eng.zeros(B, dtype=torch.int32)
+        self.d_care, self.d_pop = eng.zeros(3, B), eng.zeros(2)
+        # chunk boundaries aligned to the log stride
+        steps = self.T - 1
+        per = max(self.log_every, ((steps + n_chunks - 1) // n_chunks + self.log_every - 1) // self.log_every * self.log_every)
+        self.bounds = list(range(0, steps, per)) + [steps]
+        self.copy_stream = torch.cuda.Stream(device=eng.device)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.h_X0, self.h_wind, self.h_ac, self.h_par))
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.h_Xf, self.h_ss, self.h_mx, self.h_flags, self.h_pop)) + \
+            sum(t.numel() * t.element_size() for t in (self.h_Xlog, self.h_Ulog) if t is not None)
+        self.launches_per_run = len(self.bounds) - 1
+
+    def set_inputs(self, par_rows, wind, X0, tau_phi=0.01, tau_v=1.):
+        """par_rows (n_par_rows,B) segment parameters; wind (B,2); X0 (B,5).  Fills the pinned input buffers."""
+        self.h_par.numpy()[...] = par_rows
+        self.h_wind.numpy()[...] = np.asarray(wind, dtype=np.float64).T
+        self.h_X0.numpy()[...] = np.asarray(X0, dtype=np.float64).T
+        self.h_ac.numpy()[0], self.h_ac.numpy()[1] = tau_phi, tau_v
+
+    def upload(self):
+        self.d_X0.copy_(self.h_X0, non_blocking=True); self.d_wind.copy_(self.h_wind, non_blocking=True)
+        self.d_ac.copy_(self.h_ac, non_blocking=True); self.d_par[:self.n_par_rows].copy_(self.h_par, non_blocking=True)
+
+    def _sweep(self, copy_logs):
+        eng = self.eng
+        self.d_ss.zero_(); self.d_mx.zero_(); self.d_flags.zero_(); self.d_care.zero_(); self.d_pop.zero_()
+        cur = torch.cuda.current_stream(eng.device)
+        Xin, ping = self.d_X0, [self.d_Xa, self.d_Xb]
+        for k in range(len(self.bounds) - 1):
+            i, j = self.bounds[k], self.bounds[k + 1]
+            last = j == self.T - 1
+            Xout = self.d_Xf if last else ping[k % 2]
+            eng.rollout_dfff(self.table, Xin, self.d_wind, self.d_ac, self.d_time, i, j, nsub=self.nsub, final_control=last,
+                             log_every=self.log_every, X_log=self.d_Xlog, U_log=self.d_Ulog, X_final=Xout, sum_sq_err=self.d_ss,
+                             max_err=self.d_mx, flags=self.d_flags, care_state=self.d_care, pop_stats=self.d_pop)
+            Xin = Xout
+            if copy_logs and self.host_log:
+                r0 = (i + self.log_every - 1) // self.log_every
+                r1 = (j // self.log_every + 1) if last else (j + self.log_every - 1) // self.log_every
+                if r1 > r0:
+                    ev = torch.cuda.Event(); ev.record(cur)
+                    with torch.cuda.stream(self.copy_stream):
+                        self.copy_stream.wait_event(ev)
+                        self.h_Xlog[r0:r1].copy_(self.d_Xlog[r0:r1], non_blocking=True)
+                        if self.h_Ulog is not None:
+                            self.h_Ulog[r0:r1].copy_(self.d_Ulog[r0:r1], non_blocking=True)
+
+    def run_device(self):
+        """Inputs resident in HBM, results left in HBM (d_Xf, d_ss, d_mx, d_flags, d_Xlog, d_Ulog, d_pop)."""
+        self._sweep(copy_logs=False)
+
+    def run(self):
+        """Host buffers in, host buffers out; returns when everything has landed in pinned memory."""
+        self.upload()
+        self._sweep(copy_logs=True)
+        self.h_Xf.copy_(self.d_Xf, non_blocking=True); self.h_ss.copy_(self.d_ss, non_blocking=True)
+        self.h_mx.copy_(self.d_mx, non_blocking=True); self.h_flags.copy_(self.d_flags, non_blocking=True)
+        self.h_pop.copy_(self.d_pop, non_blocking=True)
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        self.copy_stream.synchronize()
+        out = {"X_final": self.h_Xf.numpy().T, "sum_sq_err": self.h_ss.numpy(), "max_err": self.h_mx.numpy(),
+               "flags": self.h_flags.numpy(), "pop_sum_sq_err": float(self.h_pop[0]), "pop_max_err": float(self.h_pop[1])}
+        if self.host_log:
+            out["X_log"] = self.h_Xlog.numpy()
+            if self.h_Ulog is not None:
+                out["U_log"] = self.h_Ulog.numpy()
+        return out

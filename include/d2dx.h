@@ -251,6 +251,11 @@ int d2dx_colloc_eval_shard(d2dx_handle* h, const d2dx_colloc_problem* p_local_ho
 int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const double* free_local,
                                double* pos, void* stream);
 
+/* -------- diagnostics -------- */
+/* FP64 roofline probe: every thread runs `iters` rounds of 16 independent DFMA chains (32*iters flop per
+ * thread); the caller times it with CUDA events.  sink: device double[1] (keeps the chains alive). */
+int d2dx_dfma_burn(d2dx_handle* h, int32_t blocks, int32_t threads, int32_t iters, double* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
