@@ -1,0 +1,157 @@
+"""Planner front-ends -- the `Planner` classes of 06_optyplan.py:25-145 (single aircraft) and
+07_multioptyplan.py:28-121 (aircraft set), with `self.prob` backed by the collocation kernel instead of
+opty's generated code.  `prob` exposes what IPOPT calls (`obj`, `obj_grad`, `con`, `con_jac`,
+`jacobianstructure`, `num_free`); the NLP solve itself (cyipopt / IPOPT) is outside the hot path."""
+import numpy as np
+
+from . import multiopty_utils as d2mou
+from . import opty_utils as d2ou
+from .collocation import CollocationProblem
+
+
+def _node_of(t, t0, h, N):
+    """opty attaches an instance constraint to the grid node nearest to its time."""
+    return int(min(max(round((t - t0) / h), 0), N - 1))
+
+
+class _PlannerBase:
+    def configure(self, tol=1e-8, max_iter=3000):
+        self.tol, self.max_iter = tol, max_iter
+
+    def run(self, initial_guess=None, **_):
+        raise NotImplementedError("the IPOPT solve (prob.solve) is not part of the engine; drive self.prob's callbacks "
+                                  "from your NLP solver (cyipopt.Problem accepts this object as problem_obj)")
+
+    def evaluate(self, free):
+        """residual, Jacobian values, cost, gradient at `free` in one fused launch."""
+        return self.prob.evaluate(free)
+
+
+class Planner(_PlannerBase):
+    """Single-aircraft planner (06_optyplan.py:25-145).  `exp` carries t0, t1, hz, p0, p1, wind, cost, obj_scale,
+    phi/v/x/y constraints, vref (d2d/optyplan_scenarios.py)."""
+
+    def __init__(self, exp, initialize=True, jac_layout="dense"):
+        self.exp, self.obj_scale = exp, exp.obj_scale
+        self.num_nodes, self.time_step, self.duration = d2ou.planner_timing(exp.t0, exp.t1, exp.hz)
+        self.wind, self.aircraft = exp.wind, d2ou.Aircraft()
+        N = self.num_nodes
+        self._slice_x, self._slice_y, self._slice_psi, self._slice_phi, self._slice_v = \
+            [slice(k * N, (k + 1) * N, 1) for k in range(5)]                        # :35-39
+        n0 = _node_of(exp.t0, exp.t0, self.time_step, N)
+        n1 = _node_of(exp.t1, exp.t0, self.time_step, N)
+        self._instance_constraints = [(k, n0, exp.p0[k]) for k in range(3)] + [(k, n1, exp.p1[k]) for k in range(3)]   # :46-49
+        self._bounds = {"phi": exp.phi_constraint, "v": exp.v_constraint}           # :53-57 (variable bounds for the NLP solver)
+        if exp.x_constraint is not None: self._bounds["x"] = exp.x_constraint
+        if exp.y_constraint is not None: self._bounds["y"] = exp.y_constraint
+        self.obstacles = getattr(exp, "obstacles", ())
+        if initialize:
+            w = exp.wind.sample_num(0., 0., 0.)
+            self.prob = CollocationProblem(1, N, self.time_step, wind=w, inst=self._instance_constraints,
+                                           cost=exp.cost.spec(), obj_scale=self.obj_scale, layout=jac_layout, multi=False)
+
+    def get_initial_guess(self, kind="tri", seed=None):                             # :79-115
+        N = self.num_nodes
+        guess = np.zeros(5 * N)
+        p0, p1 = np.array(self.exp.p0[:2], dtype=float), np.array(self.exp.p1[:2], dtype=float)
+        if kind == "rnd":
+            rng = np.random.default_rng(seed)
+            cx = self.exp.x_constraint or [-100, 100]
+            cy = self.exp.y_constraint or [-100, 100]
+            guess[self._slice_x] = rng.uniform(cx[0], cx[1], N)
+            guess[self._slice_y] = rng.uniform(cy[0], cy[1], N)
+            guess[self._slice_psi] = rng.uniform(-np.pi, np.pi, N)
+        elif kind == "tri":
+            x, y, psi, phi, v = d2ou.triangle(p0, p1, self.exp.vref, self.duration, N, go_left=-1.)
+            guess[self._slice_x], guess[self._slice_y], guess[self._slice_psi] = x, y, psi
+            guess[self._slice_phi], guess[self._slice_v] = phi, v
+        else:
+            guess[self._slice_x] = np.linspace(p0[0], p1[0], N)
+            guess[self._slice_y] = np.linspace(p0[1], p1[1], N)
+        return guess
+
+    def interpret_solution(self):                                                   # :127-133
+        self.sol_time = np.linspace(0.0, self.duration, num=self.num_nodes)
+        s = self.solution
+        self.sol_x, self.sol_y, self.sol_psi = s[self._slice_x], s[self._slice_y], s[self._slice_psi]
+        self.sol_phi, self.sol_v = s[self._slice_phi], s[self._slice_v]
+
+    def save_solution(self, filename):                                              # :135-139 (same .npz keys)
+        wind = np.array([self.wind.sample_num(_t, _x, _y) for _t, _x, _y in zip(self.sol_time, self.sol_x, self.sol_y)])
+        np.savez(filename, sol_time=self.sol_time, sol_x=self.sol_x, sol_y=self.sol_y, sol_psi=self.sol_psi,
+                 sol_phi=self.sol_phi, sol_v=self.sol_v, wind=wind)
+
+    def load_solution(self, filename):                                              # :141-145
+        d = np.load(filename)
+        self.sol_time, self.sol_x, self.sol_y, self.sol_psi, self.sol_phi, self.sol_v = \
+            [d[k] for k in ("sol_time", "sol_x", "sol_y", "sol_psi", "sol_phi", "sol_v")]
+        self.solution = np.concatenate([self.sol_x, self.sol_y, self.sol_psi, self.sol_phi, self.sol_v])
+
+
+class MultiPlanner(_PlannerBase):
+    """Aircraft-set planner (07_multioptyplan.py:28-121).  `scen` carries t0, t1, hz, p0s, p1s, wind, cost,
+    obj_scale, constraints, vref."""
+
+    def __init__(self, scen, initialize=True, jac_layout="compact", input_order="numeric"):
+        self.scen, self.obj_scale, self.wind = scen, scen.obj_scale, scen.wind
+        self.acs = d2mou.AircraftSet(n=len(scen.p0s))
+        self.num_nodes, self.time_step, self.duration = d2ou.planner_timing(scen.t0, scen.t1, scen.hz)
+        N, n = self.num_nodes, self.acs.nb_aicraft
+        self._slice_x = [slice((0 + 3 * i) * N, (1 + 3 * i) * N, 1) for i in range(n)]          # :41-47
+        self._slice_y = [slice((1 + 3 * i) * N, (2 + 3 * i) * N, 1) for i in range(n)]
+        self._slice_psi = [slice((2 + 3 * i) * N, (3 + 3 * i) * N, 1) for i in range(n)]
+        o = 3 * n * N
+        self._slice_phi = [slice(o + i * N, o + (i + 1) * N, 1) for i in range(n)]
+        o += n * N
+        self._slice_v = [slice(o + i * N, o + (i + 1) * N, 1) for i in range(n)]
+        n0 = _node_of(scen.t0, scen.t0, self.time_step, N)
+        n1 = _node_of(scen.t1, scen.t0, self.time_step, N)
+        self._instance_constraints = [(3 * i + k, n0, p[k]) for i, p in enumerate(scen.p0s) for k in range(3)] + \
+                                     [(3 * i + k, n1, p[k]) for i, p in enumerate(scen.p1s) for k in range(3)]   # :53-56
+        if initialize:
+            w = scen.wind.sample_num(0., 0., 0.)
+            self.prob = CollocationProblem(n, N, self.time_step, wind=w, inst=self._instance_constraints,
+                                           cost=scen.cost.spec(), obj_scale=self.obj_scale, layout=jac_layout,
+                                           input_order=input_order, multi=True)
+
+    def get_initial_guess(self, what="tri", seed=None):                             # :94-112
+        N, n = self.num_nodes, self.acs.nb_aicraft
+        guess = np.zeros(5 * n * N)
+        if what == "rnd":
+            rng = np.random.default_rng(seed)
+            for i in range(n):
+                guess[self._slice_x[i]] = rng.uniform(-100, 100, N)
+                guess[self._slice_y[i]] = rng.uniform(-100, 100, N)      # upstream draws y from the x range too (:99-102)
+                guess[self._slice_psi[i]] = rng.uniform(-np.pi, np.pi, N)
+                guess[self._slice_phi[i]] = rng.uniform(self.scen.phi_constraint[0], self.scen.phi_constraint[1], N)
+                guess[self._slice_v[i]] = rng.uniform(self.scen.v_constraint[0], self.scen.v_constraint[1], N)
+        else:
+            for i, (p0, p1) in enumerate(zip(self.scen.p0s, self.scen.p1s)):
+                x, y, psi, phi, v = d2ou.triangle(np.array(p0)[:2], np.array(p1)[:2], self.scen.vref, self.duration, N, go_left=-1.)
+                guess[self._slice_x[i]], guess[self._slice_y[i]], guess[self._slice_psi[i]] = x, y, psi
+                guess[self._slice_phi[i]], guess[self._slice_v[i]] = phi, v
+        return guess
+
+    def interpret_solution(self):                                                   # :115-121
+        s = self.solution
+        self.sol_time = np.linspace(0.0, self.duration, num=self.num_nodes)
+        self.sol_x, self.sol_y = [s[k] for k in self._slice_x], [s[k] for k in self._slice_y]
+        self.sol_psi, self.sol_v, self.sol_phi = [s[k] for k in self._slice_psi], [s[k] for k in self._slice_v], [s[k] for k in self._slice_phi]
+
+
+class exp_0:
+    """Single-aircraft experiment 0 (d2d/optyplan_scenarios.py:9-28); other experiments subclass and override."""
+    ncases = 1
+    tol, max_iter = 1e-5, 1500
+    vref = 12.
+    cost = d2ou.CostAirVel(vref)
+    obj_scale = 1.
+    wind = d2ou.WindField(w=[0., 0.])
+    obstacles = ()
+    t0, p0 = 0., (0., 0., 0., 0., 10.)
+    t1, p1 = 10., (0., 30., np.pi, 0., 10.)
+    x_constraint, y_constraint = None, None
+    phi_constraint = (-np.deg2rad(30.), np.deg2rad(30.))
+    v_constraint = (9., 14.)
+    hz = 10.
+    name, desc = "exp0", "Turn around - 12m/s objective"

@@ -173,3 +173,42 @@ def test_sharded_evaluation_single_gpu_emulation(golden):
     np.testing.assert_allclose(parts["jac"], jac, rtol=0, atol=0)
     np.testing.assert_allclose(parts["grad"], grad, rtol=1e-14, atol=1e-16)
     np.testing.assert_allclose(parts["cost"], cost, rtol=1e-13)
+
+
+def test_planner_front_ends_and_cost_classes(golden):
+    """The mirrored Planner / cost classes used the way the reference scripts use them (06_optyplan.py:177-204,
+    test/test_objective.py): known-answer costs of SURVEY appendix C, instance constraints, triangle guess."""
+    from d2d_b200 import multiopty_utils as d2mou, opty_utils as d2ou, planner
+    g = golden["colloc"]
+
+    class exp(planner.exp_0):
+        t1, hz = 20., 50.
+    p = planner.Planner(exp)
+    assert p.num_nodes == 1001 and p.prob.num_free == 5005 and p.prob.num_constraints == 3006
+    sol = g["c3/sol"]
+    assert abs(p.prob.obj(sol) - 8.089644746010487e-08) < 1e-18
+    assert np.abs(p.prob.con(sol)).max() < 1e-6                       # cached IPOPT solution is feasible
+    known = {"bank": (d2ou.CostBank(), 0.09602478183335866), "input": (d2ou.CostInput(12., 1., 50.), 4.801239172564381),
+             "obs0": (d2ou.CostObstacle((30, 0), 15., kind=0), 106.87281760768758),
+             "obs1": (d2ou.CostObstacle((5, 15), 10., kind=1), 5.801877126038269e-06),
+             "composit": (d2ou.CostComposit(((5, 15, 10),), vsp=15., kobs=.5, kvel=.5, kbank=1.), 4.596177031308985)}
+    for name, (c, val) in known.items():
+        np.testing.assert_allclose(c.cost(sol, p), val, rtol=1e-10, err_msg=name)
+        np.testing.assert_allclose(c.cost_grad(sol, p), g[f"cost1/{name}/sol/grad"], rtol=1e-10, atol=1e-300, err_msg=name)
+    guess = p.get_initial_guess("tri")
+    assert guess.shape == (5005,) and np.isfinite(p.prob.obj(guess))
+
+    class mscen:
+        t0, t1, hz = 0., 1.9, 10.
+        p0s = tuple(tuple(v) for v in g["m3/p0s"]); p1s = tuple(tuple(v) for v in g["m3/p1s"])
+        wind = d2ou.WindField([0.5, -1.0]); vref = 12.; obj_scale = 1.
+        cost = d2mou.CostComposit(kvel=70., kbank=1., kobs=0.5, kcol=10., vsp=12., obss=((60., 5., 12.), (-20., 30., 8.)), obs_kind=1, rcol=10.)
+    mp = planner.MultiPlanner(mscen)
+    assert mp.num_nodes == 20 and mp.acs.nb_aicraft == 3
+    free = g["m3/free"]
+    np.testing.assert_allclose(mp.prob.con(free), g["m3/residual"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(mp.prob.obj(free), g["m3/cost/composit/cost"], rtol=1e-10)
+    np.testing.assert_allclose(mscen.cost.cost_grad(free, mp), g["m3/cost/composit/grad"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(d2mou.CostCollision(r=10.).cost(free, mp), g["m3/cost/collision/cost"], rtol=1e-10)
+    with pytest.raises(NotImplementedError):
+        mp.run()
