@@ -221,3 +221,19 @@ def test_dcf_and_gvf_single_calls(d2d, golden):
     np.testing.assert_allclose(e_deg[:, 0], eo, rtol=1e-12, atol=1e-12)
     with pytest.raises(ValueError):
         guidance.DCFController().get(n_ac, B, np.array([0., 0.]), p, z, 20)      # 1-D centre, cf. SURVEY D2
+
+
+def test_integration_md_ctypes_stub_runs(d2d, golden):
+    """The reference-side ctypes stub printed in INTEGRATION.md, executed verbatim against libd2dx.so."""
+    import os, re
+    from d2d_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = [b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "run_simulation_gpu" in b][0]
+    code = code.replace('C.CDLL("libd2dx.so")', f'C.CDLL({_lib.LIB_PATH!r})')
+    ns = {}
+    exec(code, ns)
+    g = golden["dfff_c1"]
+    X, U = ns["run_simulation_gpu"](g["time"], (30., 30., 30., 10., 3 * np.pi / 2, 0.), g["wind"], g["X0"])
+    np.testing.assert_allclose(X, g["X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(U, g["U"], rtol=0, atol=TOL)
