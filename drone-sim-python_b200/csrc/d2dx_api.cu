@@ -127,9 +127,13 @@ __global__ void __launch_bounds__(kThreads) dfff_control_kernel(const d2dx_traj_
   double x[5];
   for (int k = 0; k < 5; ++k) x[k] = X[(size_t)k * B + b];
   const CareConst cc = care_const(g);
-  CareState cs = {0.0, 1.0, 1.0};
+  CareState cs = {0.0, 1.0, 1.0, 0.0, 0.0};
   bool cold = true;
-  if (care_state) { cs.C = care_state[b]; cs.S = care_state[B + b]; cs.al = care_state[2 * (size_t)B + b]; cold = !(cs.al > 0.0); }
+  if (care_state) {
+    cs.C = care_state[b]; cs.S = care_state[B + b]; cs.al = care_state[2 * (size_t)B + b];
+    cs.dth = care_state[3 * (size_t)B + b]; cs.dal = care_state[4 * (size_t)B + b];
+    cold = !(cs.al > 0.0);
+  }
   int flags = 0;
   FlatState fr;
   double u_phi, u_v, k6[6];
@@ -137,7 +141,10 @@ __global__ void __launch_bounds__(kThreads) dfff_control_kernel(const d2dx_traj_
   U[b] = u_phi; U[(size_t)B + b] = u_v;
   if (Xr) { Xr[b] = fr.x; Xr[(size_t)B + b] = fr.y; Xr[2 * (size_t)B + b] = fr.psi; Xr[3 * (size_t)B + b] = fr.phi; Xr[4 * (size_t)B + b] = fr.va; }
   if (K) for (int k = 0; k < 6; ++k) K[(size_t)k * B + b] = k6[k];
-  if (care_state) { care_state[b] = cs.C; care_state[B + b] = cs.S; care_state[2 * (size_t)B + b] = cold ? 0.0 : cs.al; }
+  if (care_state) {
+    care_state[b] = cs.C; care_state[B + b] = cs.S; care_state[2 * (size_t)B + b] = cold ? 0.0 : cs.al;
+    care_state[3 * (size_t)B + b] = cs.dth; care_state[4 * (size_t)B + b] = cs.dal;
+  }
 }
 
 // FP64 pipe probe: 16 independent DFMA chains per thread
@@ -156,11 +163,28 @@ __global__ void dfma_burn_kernel(int iters, double* sink) {
   if (s == 123.456) *sink = s;
 }
 
+__global__ void math_probe_kernel(int n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double s, c;
+  fm::sincos(x[i], s, c);
+  out[i] = s; out[(size_t)n + i] = c; out[2 * (size_t)n + i] = fm::atan2(y[i], x[i]); out[3 * (size_t)n + i] = fm::atan(x[i]);
+  out[4 * (size_t)n + i] = fm::div(y[i], x[i]); out[5 * (size_t)n + i] = fm::sqrt(fabs(x[i])); out[6 * (size_t)n + i] = fm::rsqrt(fabs(x[i]));
+}
+
 }  // namespace d2dx
 
 using namespace d2dx;
 
 extern "C" {
+
+int d2dx_math_probe(d2dx_handle* h, int32_t n, const double* x, const double* y, double* out, void* stream) {
+  D2DX_CHECK_ARG(h && n > 0 && x && y && out, "d2dx_math_probe: bad argument");
+  D2DX_CUDA(cudaSetDevice(h->device));
+  math_probe_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, x, y, out);
+  D2DX_LAUNCH_CHECK("math_probe_kernel");
+  return D2DX_OK;
+}
 
 int d2dx_dfma_burn(d2dx_handle* h, int32_t blocks, int32_t threads, int32_t iters, double* sink, void* stream) {
   D2DX_CHECK_ARG(h && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, "d2dx_dfma_burn: bad argument");

@@ -6,8 +6,33 @@
 #include <stdint.h>
 
 #include "../../include/d2dx.h"
+#include "d2dx_math.cuh"
 
 namespace d2dx {
+
+// elementary functions used on the hot path: the straight-line versions of d2dx_math.cuh, or (-DD2DX_USE_LIBM)
+// CUDA's libdevice for A/B comparison
+#ifdef D2DX_USE_LIBM
+__device__ __forceinline__ void sincos_b(double x, double& s, double& c) { ::sincos(x, &s, &c); }   // bounded argument
+__device__ __forceinline__ void sincos_any(double x, double& s, double& c) { ::sincos(x, &s, &c); }
+__device__ __forceinline__ double atan2_f(double y, double x) { return ::atan2(y, x); }
+__device__ __forceinline__ double atan_f(double v) { return ::atan(v); }
+__device__ __forceinline__ double sqrt_f(double v) { return ::sqrt(v); }
+__device__ __forceinline__ double rsqrt_f(double v) { return ::rsqrt(v); }
+__device__ __forceinline__ double rcp_f(double v) { return 1.0 / v; }
+__device__ __forceinline__ double div_f(double a, double b) { return a / b; }
+#else
+__device__ __forceinline__ void sincos_b(double x, double& s, double& c) { fm::sincos(x, s, c); }
+__device__ __forceinline__ void sincos_any(double x, double& s, double& c) {
+  if (fabs(x) < 1.0e5) fm::sincos(x, s, c); else ::sincos(x, &s, &c);      // libdevice's Payne-Hanek path for huge phases
+}
+__device__ __forceinline__ double atan2_f(double y, double x) { return fm::atan2(y, x); }
+__device__ __forceinline__ double atan_f(double v) { return fm::atan(v); }
+__device__ __forceinline__ double sqrt_f(double v) { return fm::sqrt(v); }
+__device__ __forceinline__ double rsqrt_f(double v) { return fm::rsqrt(v); }
+__device__ __forceinline__ double rcp_f(double v) { return fm::rcp(v); }
+__device__ __forceinline__ double div_f(double a, double b) { return fm::div(a, b); }
+#endif
 
 constexpr double kPi = 3.141592653589793;        // np.pi
 constexpr double kTwoPi = 6.283185307179586;     // 2*np.pi
@@ -66,7 +91,7 @@ __device__ __forceinline__ void segment_eval(int type, LD P, double t, FlatOut& 
       const double r = P(3), om = P(4);
       const double alpha = __dadd_rn(__dmul_rn(t - P(0), om), P(5));
       double sa, ca;
-      sincos(alpha, &sa, &ca);
+      sincos_any(alpha, sa, ca);
       const double w1 = __dmul_rn(om, r), w2 = __dmul_rn(__dmul_rn(om, om), r);
       Y.y0x = __dadd_rn(P(1), __dmul_rn(r, ca)); Y.y0y = __dadd_rn(P(2), __dmul_rn(r, sa));
       Y.y1x = -w1 * sa; Y.y1y = w1 * ca;
@@ -80,7 +105,7 @@ __device__ __forceinline__ void segment_eval(int type, LD P, double t, FlatOut& 
       Y.y0y = __dadd_rn(P(2), __dmul_rn(Y.y1y, dt));
       const double alpha = __dadd_rn(dt, P(5));
       double s, c;
-      sincos(alpha, &s, &c);
+      sincos_any(alpha, s, c);
       Y.y0y = __dadd_rn(Y.y0y, 10.0 * s);
       Y.y1y = __dadd_rn(Y.y1y, 10.0 * c);
       Y.y2y = -10.0 * s;
@@ -127,18 +152,19 @@ struct AcPar { double wx, wy, n_inv_tau_phi, n_inv_tau_v; };   // -1/tau as the 
 
 __device__ __forceinline__ void cont_dyn(const AcPar& a, double psi, double phi, double v, double phi_c,
                                          double v_c, double& dx, double& dy, double& dpsi, double& dphi, double& dv) {
-  double s, c;
-  sincos(psi, &s, &c);
+  double s, c, sp, cp;
+  sincos_b(psi, s, c);
+  sincos_b(phi, sp, cp);
   dx = v * c + a.wx;
   dy = v * s + a.wy;
-  dpsi = kG / v * tan(phi);
+  dpsi = kG * sp * rcp_f(v * cp);            // g / v * tan(phi)
   dphi = a.n_inv_tau_phi * (phi - phi_c);
   dv = a.n_inv_tau_v * (v - v_c);
 }
 
-// Fixed-step stand-in for Aircraft.disc_dyn (d2d/dynamic.py:25-28): nsub classical RK4 sub-steps with
-// the input held, then psi wrapped once (:27).
-__device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
+// Reference formulation of one control step (every stage with full-range sin / cos): used for the single-call
+// entry points' odd inputs and as the fallback of rk4_step when a stage leaves the fast path's validity range.
+static __device__ __noinline__ void rk4_step_generic(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
   const double h = dt / nsub, hh = 0.5 * h, h6 = h / 6.0;
   double x = X[0], y = X[1], psi = X[2], phi = X[3], v = X[4];
   for (int s = 0; s < nsub; ++s) {
@@ -156,20 +182,85 @@ __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c
   X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
 }
 
+#ifdef D2DX_USE_LIBM
+__device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
+  rk4_step_generic(a, X, phi_c, v_c, dt, nsub);
+}
+#else
+// g tan(phi) / v with one reciprocal through the Pade ratio of d2dx_math.cuh (|phi| <= 1.15, checked by the caller)
+__device__ __forceinline__ double turn_rate(double phi, double v) {
+  double tn, td;
+  fm::tan_ratio(phi, tn, td);
+  return kG * tn * rcp_f(v * td);
+}
+
+// heading of an RK4 stage by angle addition: sin / cos of psi0 + d from (s0, c0) = sin / cos psi0, |d| < 0.1
+__device__ __forceinline__ void stage_heading(double s0, double c0, double d, double& s, double& c) {
+  double sd, cd;
+  fm::sincos_small(d, sd, cd);
+  s = fma(c0, sd, s0 * cd);
+  c = fma(-s0, sd, c0 * cd);
+}
+
+// Fixed-step stand-in for Aircraft.disc_dyn (d2d/dynamic.py:25-28): nsub classical RK4 sub-steps of cont_dyn
+// (:14-23) with the input held, then psi wrapped once (:27).  Straight-line fast path: the four stage headings share
+// one full sincos (stages 2-4 by angle addition of the increment h psi_dot), tan(phi) is a Pade ratio folded into
+// the 1/v reciprocal.  Validity (|increment| < 0.1, |phi| <= 1.15) is accumulated in one flag; if it is ever violated
+// the control step is redone with rk4_step_generic.
+__device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
+  const double h = dt / nsub, hh = 0.5 * h, h6 = h / 6.0;
+  double x = X[0], y = X[1], psi = X[2], phi = X[3], v = X[4];
+  double worst_d = 0.0, worst_phi = 0.0;
+  for (int sub = 0; sub < nsub; ++sub) {
+    double s1, c1, s, c, d;
+    sincos_b(psi, s1, c1);
+    // stage 1
+    const double k1x = v * c1 + a.wx, k1y = v * s1 + a.wy, k1p = turn_rate(phi, v);
+    const double k1f = a.n_inv_tau_phi * (phi - phi_c), k1v = a.n_inv_tau_v * (v - v_c);
+    worst_phi = fmax(worst_phi, fabs(phi));
+    // stage 2
+    double ph = phi + hh * k1f, vv = v + hh * k1v;
+    d = hh * k1p; worst_d = fmax(worst_d, fabs(d)); worst_phi = fmax(worst_phi, fabs(ph));
+    stage_heading(s1, c1, d, s, c);
+    const double k2x = vv * c + a.wx, k2y = vv * s + a.wy, k2p = turn_rate(ph, vv);
+    const double k2f = a.n_inv_tau_phi * (ph - phi_c), k2v = a.n_inv_tau_v * (vv - v_c);
+    // stage 3
+    ph = phi + hh * k2f; vv = v + hh * k2v;
+    d = hh * k2p; worst_d = fmax(worst_d, fabs(d)); worst_phi = fmax(worst_phi, fabs(ph));
+    stage_heading(s1, c1, d, s, c);
+    const double k3x = vv * c + a.wx, k3y = vv * s + a.wy, k3p = turn_rate(ph, vv);
+    const double k3f = a.n_inv_tau_phi * (ph - phi_c), k3v = a.n_inv_tau_v * (vv - v_c);
+    // stage 4
+    ph = phi + h * k3f; vv = v + h * k3v;
+    d = h * k3p; worst_d = fmax(worst_d, fabs(d)); worst_phi = fmax(worst_phi, fabs(ph));
+    stage_heading(s1, c1, d, s, c);
+    const double k4x = vv * c + a.wx, k4y = vv * s + a.wy, k4p = turn_rate(ph, vv);
+    const double k4f = a.n_inv_tau_phi * (ph - phi_c), k4v = a.n_inv_tau_v * (vv - v_c);
+    x += h6 * (k1x + 2.0 * k2x + 2.0 * k3x + k4x);
+    y += h6 * (k1y + 2.0 * k2y + 2.0 * k3y + k4y);
+    psi += h6 * (k1p + 2.0 * k2p + 2.0 * k3p + k4p);
+    phi += h6 * (k1f + 2.0 * k2f + 2.0 * k3f + k4f);
+    v += h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
+  }
+  if (!(worst_d < 0.1 && worst_phi <= 1.15)) { rk4_step_generic(a, X, phi_c, v_c, dt, nsub); return; }   // also catches NaN
+  X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
+}
+#endif
+
 // DiffFlatness.state_and_input_from_output, d2d/guidance.py:23-47
-struct FlatState { double x, y, psi, phi, va, u_phi, u_v, vadot, psidot, z /* tan(phi) */, cpsi, spsi; };
+struct FlatState { double x, y, psi, phi, va, inv_va, u_phi, u_v, vadot, psidot, z /* tan(phi) */, cpsi, spsi; };
 
 __device__ __forceinline__ void flatness(const FlatOut& Y, double wx, double wy, double tau_v, FlatState& r) {
   const double vax = Y.y1x - wx, vay = Y.y1y - wy;
-  const double va2 = vax * vax + vay * vay, va = sqrt(va2);
-  const double inv_va = 1.0 / va;
-  r.x = Y.y0x; r.y = Y.y0y; r.va = va;
-  r.psi = atan2(vay, vax);
-  r.vadot = (vax * Y.y2x + vay * Y.y2y) / va;
+  const double va2 = vax * vax + vay * vay;
+  const double inv_va = rsqrt_f(va2), va = va2 * inv_va;
+  r.x = Y.y0x; r.y = Y.y0y; r.va = va; r.inv_va = inv_va;
+  r.psi = atan2_f(vay, vax);
+  r.vadot = (vax * Y.y2x + vay * Y.y2y) * inv_va;
   const double num = Y.y2y * vax - Y.y2x * vay;
-  r.psidot = num / va2;
-  r.z = num / va / kG;                    // argument of the arctan at :40, i.e. tan(phi_ref)
-  r.phi = atan(r.z);
+  r.psidot = num * inv_va * inv_va;
+  r.z = num * inv_va * (1.0 / kG);        // argument of the arctan at :40, i.e. tan(phi_ref)
+  r.phi = atan_f(r.z);
   r.u_phi = r.phi;                        // tau_phi * Xdot[phi] + phi with Xdot[phi] never filled (:42-43)
   r.u_v = tau_v * r.vadot + va;
   r.cpsi = vax * inv_va; r.spsi = vay * inv_va;   // cos / sin of arctan2(vay, vax)
@@ -190,47 +281,99 @@ __device__ __forceinline__ void flatness(const FlatOut& Y, double wx, double wy,
 // b2 = 0 solution C = 0, S = 1, al = sqrt(q3 + 2 v c1 sqrt(q))).  K' = [[C, S, al]/sqrt(r1) ; [S, -C, be]/sqrt(r2)]
 // (times sqrt(q) on the first two columns) and K1 = K' T.  Checked against scipy.linalg.solve_continuous_are
 // over v in [0.3, 60], |phi| < 1.4 to 3e-13 (tests/test_care_math.py).
-struct CareState { double C, S, al; };
+struct CareState { double C, S, al, dth, dal; };   // solution of the previous control step and its last change
 
 struct CareConst { double sq, q3, sr1, sr2, isr1, isr2; };
 
 __device__ __forceinline__ CareConst care_const(const d2dx_dfff_gains& g) {
   CareConst c;
-  c.sq = sqrt(g.q_pos); c.q3 = g.q_psi; c.sr1 = sqrt(g.r_phi); c.sr2 = sqrt(g.r_v);
+  c.sq = ::sqrt(g.q_pos); c.q3 = g.q_psi; c.sr1 = ::sqrt(g.r_phi); c.sr2 = ::sqrt(g.r_v);
   c.isr1 = 1.0 / c.sr1; c.isr2 = 1.0 / c.sr2;
   return c;
 }
 
-// returns the number of Newton iterations (-1: not converged); K0 is the 2x3 gain in the path frame
-__device__ __forceinline__ int care_gain(const CareConst& cc, double v, double b1, double b2, CareState& st,
-                                         bool cold, double* K0, int max_it = 40) {
-  const double c1 = cc.sr1 / b1, c2 = cc.sr2, ic2 = cc.isr2, e = b2 * c1;
-  const double c1q = c1 * cc.sq;
-  double C = st.C, S = st.S, al = st.al;
-  if (cold) { C = 0.0; S = 1.0; al = sqrt(cc.q3 + 2.0 * v * c1q); }
-  int it = 0;
+struct CareStep { double k1, ba, vc2, ve, k2, q3; };   // per-control-step constants of the two residuals
+
+// residuals F1, F2 at (C, S, al); also returns be
+__device__ __forceinline__ void care_residual(const CareStep& k, double C, double S, double al, double& be, double& F1, double& F2) {
+  be = fma(k.k1, C, k.ba * al);
+  F1 = fma(C, al, fma(S, be, fma(k.vc2, C, k.ve * S)));
+  F2 = fma(al, al, fma(be, be, -fma(k.k2, S, k.q3)));
+}
+
+// apply the update (dth, dal): rotate (C, S) by dth (first order + one Newton normalisation step), al += dal
+__device__ __forceinline__ void care_update(double& C, double& S, double& al, double dth, double dal) {
+  const double Cn = fma(-S, dth, C), Sn = fma(C, dth, S);
+  const double nrm = fma(-0.5, fma(Cn, Cn, Sn * Sn), 1.5);        // 1/sqrt(1 + dth^2) up to O(dth^4)
+  C = Cn * nrm; S = Sn * nrm; al += dal;
+}
+
+// Full Newton iteration loop (cold starts, trajectory corners, anything the two-step fast path did not finish).
+static __device__ __noinline__ bool care_newton_loop(const CareStep& k, double& C, double& S, double& al, int max_it) {
   bool conv = false;
-  for (; it < max_it && !conv; ++it) {
-    const double be = (c1q * C + e * al) * ic2;
-    const double dbt = -c1q * S * ic2, dba = e * ic2;
-    const double F1 = C * al + S * be + v * (c2 * C + e * S);
-    const double F2 = al * al + be * be - cc.q3 - 2.0 * v * c1q * S;
-    const double J11 = -S * al + C * be + S * dbt + v * (e * C - c2 * S), J12 = C + S * dba;
-    const double J21 = 2.0 * (be * dbt - v * c1q * C), J22 = 2.0 * (al + be * dba);
-    const double idet = 1.0 / (J11 * J22 - J12 * J21);
-    const double dth = (J12 * F2 - F1 * J22) * idet;
-    const double dal = (J21 * F1 - J11 * F2) * idet;
+  for (int it = 0; it < max_it && !conv; ++it) {
+    double be, F1, F2;
+    care_residual(k, C, S, al, be, F1, F2);
+    const double bt = -k.k1 * S;
+    const double J11 = fma(-S, al, fma(C, be, fma(S, bt, fma(k.ve, C, -k.vc2 * S)))), J12 = fma(S, k.ba, C);
+    const double J21 = 2.0 * fma(be, bt, -0.5 * k.k2 * C), J22 = 2.0 * fma(be, k.ba, al);
+    const double idet = rcp_f(fma(J11, J22, -J12 * J21));
+    const double dth = fma(J12, F2, -F1 * J22) * idet, dal = fma(J21, F1, -J11 * F2) * idet;
     const double Cn = C - S * dth, Sn = S + C * dth;
-    const double nrm = rsqrt(Cn * Cn + Sn * Sn);
-    C = Cn * nrm; S = Sn * nrm;
-    al += dal;
-    conv = fabs(dth) < 1e-9 && fabs(dal) < 1e-9 * fabs(al);
+    const double nrm = rsqrt_f(fma(Cn, Cn, Sn * Sn));               // exact normalisation: steps can be large here
+    C = Cn * nrm; S = Sn * nrm; al += dal;
+    conv = fabs(dth) < 3e-8 && fabs(dal) < 3e-8 * fabs(al);        // quadratic convergence: remaining error ~1e-15
+  }
+  return conv;
+}
+
+// Gain in the path frame.  Warm start = previous solution extrapolated by its last change (the reference moves
+// smoothly, so the start is already O(drift^2) close); then ONE Newton step and ONE chord step (same Jacobian) in
+// straight-line code, accepted when the chord step is below 3e-8 (=> error ~1e-15); otherwise the general loop.
+// Returns false when not even the loop converged.
+__device__ __forceinline__ bool care_gain(const CareConst& cc, double v, double b1, double b2, CareState& st, bool cold, double* K0) {
+  const double c1 = cc.sr1 * rcp_f(b1), e = b2 * c1, c1q = c1 * cc.sq;
+  CareStep k;
+  k.k1 = c1q * cc.isr2; k.ba = e * cc.isr2; k.vc2 = v * cc.sr2; k.ve = v * e; k.k2 = 2.0 * v * c1q; k.q3 = cc.q3;
+  double C = st.C, S = st.S, al = st.al;
+  bool ok;
+  if (cold) {
+    C = 0.0; S = 1.0; al = sqrt_f(cc.q3 + k.k2);                   // decoupled (b2 = 0) solution
+    ok = care_newton_loop(k, C, S, al, 60);
+    st.dth = 0.0; st.dal = 0.0;
+  } else {
+    const double C0 = C, S0 = S, al0 = al;
+    care_update(C, S, al, st.dth, st.dal);                         // extrapolate
+    double be, F1, F2;
+    care_residual(k, C, S, al, be, F1, F2);
+    const double bt = -k.k1 * S;
+    const double J11 = fma(-S, al, fma(C, be, fma(S, bt, fma(k.ve, C, -k.vc2 * S)))), J12 = fma(S, k.ba, C);
+    const double J21 = 2.0 * fma(be, bt, -0.5 * k.k2 * C), J22 = 2.0 * fma(be, k.ba, al);
+    const double idet = rcp_f(fma(J11, J22, -J12 * J21));
+    const double i11 = J22 * idet, i12 = -J12 * idet, i21 = -J21 * idet, i22 = J11 * idet;   // J^-1
+    double dth = -fma(i11, F1, i12 * F2), dal = -fma(i21, F1, i22 * F2);
+    care_update(C, S, al, dth, dal);                               // Newton step
+    care_residual(k, C, S, al, be, F1, F2);
+    dth = -fma(i11, F1, i12 * F2); dal = -fma(i21, F1, i22 * F2);
+    care_update(C, S, al, dth, dal);                               // chord step
+    // accept when the chord step is tiny AND the root is on the stabilising branch (S > 0, al > 0 there: kappa_2's
+    // first component and K_13 are positive for every v, b1 > 0)
+    ok = fabs(dth) < 3e-8 && fabs(dal) < 3e-8 * fabs(al) && S > 0.0 && al > 0.0;
+    if (!ok) {                                                     // corner of the reference, big jump: iterate from the
+      C = C0; S = S0; al = al0;                                    // previous solution, not from the failed extrapolation
+      ok = care_newton_loop(k, C, S, al, 40) && S > 0.0 && al > 0.0;
+    }
+    if (!ok) { C = 0.0; S = 1.0; al = sqrt_f(cc.q3 + k.k2); ok = care_newton_loop(k, C, S, al, 60); }   // restart cold once
+    // change over this control step (angle from the cross product of the unit vectors); only a small, smooth change
+    // is worth extrapolating
+    st.dth = fma(C0, S, -S0 * C); st.dal = al - al0;
+    if (!(fabs(st.dth) < 0.02 && fabs(st.dal) < 0.02 * al)) { st.dth = 0.0; st.dal = 0.0; }
   }
   st.C = C; st.S = S; st.al = al;
-  const double be = (c1q * C + e * al) * ic2;
+  const double be = fma(k.k1, C, k.ba * al);
   K0[0] = cc.sq * C * cc.isr1; K0[1] = cc.sq * S * cc.isr1; K0[2] = al * cc.isr1;
   K0[3] = cc.sq * S * cc.isr2; K0[4] = -cc.sq * C * cc.isr2; K0[5] = be * cc.isr2;
-  return conv ? it : -1;
+  return ok;
 }
 
 // DFFFController.get, d2d/guidance.py:62-91, given the flat output at t.  Returns U; fills the reference
@@ -245,12 +388,11 @@ __device__ __forceinline__ void dfff_control(const FlatOut& Y, const AcPar& a, d
   double ep = clip(wrap_pi(X[2] - fr.psi), -g.err_sat[2], g.err_sat[2]);
   // cont_jac at the reference state: cos^2(atan z) = 1/(1+z^2), tan(atan z) = z
   const double z2 = fr.z * fr.z;
-  const double b1 = kG / fr.va * ((1.0 + z2) / (2.0 + z2));
-  const double b2 = kG / (fr.va * fr.va) * fr.z;
+  const double b1 = kG * fr.inv_va * ((1.0 + z2) * rcp_f(2.0 + z2));
+  const double b2 = kG * fr.inv_va * fr.inv_va * fr.z;
   double K0[6];
-  int it = care_gain(cc, fr.va, b1, b2, cs, cold, K0);
-  if (it < 0 && !cold) it = care_gain(cc, fr.va, b1, b2, cs, true, K0);   // warm start failed: retry cold once
-  if (it < 0) { flags |= 2; cold = true; } else cold = false;
+  if (care_gain(cc, fr.va, b1, b2, cs, cold, K0)) cold = false;
+  else { flags |= 2; cold = true; }
   // error in the path frame, feedback, saturation (:85-88)
   const double e1 = fr.cpsi * ex + fr.spsi * ey, e2 = fr.cpsi * ey - fr.spsi * ex;
   u_phi = clip(fr.u_phi - (K0[0] * e1 + K0[1] * e2 + K0[2] * ep), g.u_lo[0], g.u_hi[0]);
@@ -272,12 +414,12 @@ __device__ __forceinline__ void gvf_control(double px, double py, double psi, do
   const double e = (dx * dx + dy * dy) - r * r;
   const double nx = 2.0 * dx, ny = 2.0 * dy;
   double s, c;
-  sincos(psi, &s, &c);
+  sincos_b(psi, s, c);
   const double pdx = v * c, pdy = v * s;                 // p_dot
   const double tx = ny, ty = -nx;                        // tau = E n
   const double qx = tx - ke * e * nx, qy = ty - ke * e * ny;   // pd_dot
-  const double nrm = sqrt(qx * qx + qy * qy);
-  const double qnx = qx / nrm, qny = qy / nrm;           // pd_dot_n
+  const double inrm = rsqrt_f(qx * qx + qy * qy);        // 1/|pd_dot|
+  const double qnx = qx * inrm, qny = qy * inrm;         // pd_dot_n
   const double ox = qny, oy = -qnx;                      // E pd_dot_n
   // w = (E - ke e I) H p_dot - ke (n p_dot^T) n
   const double hx = 2.0 * pdx, hy = 2.0 * pdy;
@@ -286,7 +428,7 @@ __device__ __forceinline__ void gvf_control(double px, double py, double psi, do
   const double wy_ = (-hx - kee * hy) - ke * (ny * pdx) * nx - ke * (ny * pdy) * ny;
   // U1 = -(m w) . (E pd_dot_n / |pd_dot|),  m = o o^T
   const double ow = ox * wx_ + oy * wy_;
-  U1 = -(ox * ow * (ox / nrm) + oy * ow * (oy / nrm));
+  U1 = -(ox * ow * (ox * inrm) + oy * ow * (oy * inrm));
   U2 = kd * (c * ox + s * oy);
   U = U1 + U2;
 }

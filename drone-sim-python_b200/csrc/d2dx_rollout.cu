@@ -7,6 +7,9 @@
 namespace d2dx {
 
 constexpr int kRolloutThreads = 128;
+#ifndef D2DX_ROLLOUT_MIN_BLOCKS
+#define D2DX_ROLLOUT_MIN_BLOCKS 4      // <= 128 registers per thread: 16 resident warps per SM
+#endif
 
 struct RolloutArgs {
   d2dx_scenarios s;
@@ -38,7 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 
 template <int UNIFORM, bool LOGGING>
-__global__ void __launch_bounds__(kRolloutThreads) rollout_dfff_kernel(const RolloutArgs a) {
+__global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) rollout_dfff_kernel(const RolloutArgs a) {
   __shared__ __align__(128) double spar[D2DX_SEG_NPAR][kRolloutThreads];
   __shared__ __align__(8) uint64_t bar;
   const int B = a.s.B;
@@ -82,10 +85,11 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_dfff_kernel(const Rol
   for (int k = 0; k < 5; ++k) X[k] = a.s.X0[(size_t)k * B + b];
 
   const CareConst cc = care_const(a.g);
-  CareState cs = {0.0, 1.0, 1.0};
+  CareState cs = {0.0, 1.0, 1.0, 0.0, 0.0};
   bool cold = true;
   if (a.o.care_state) {
     cs.C = a.o.care_state[b]; cs.S = a.o.care_state[B + b]; cs.al = a.o.care_state[2 * (size_t)B + b];
+    cs.dth = a.o.care_state[3 * (size_t)B + b]; cs.dal = a.o.care_state[4 * (size_t)B + b];
     cold = !(cs.al > 0.0);
   }
   int flags = 0;
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_dfff_kernel(const Rol
     if (a.o.care_state) {
       a.o.care_state[b] = cs.C; a.o.care_state[B + b] = cs.S;
       a.o.care_state[2 * (size_t)B + b] = cold ? 0.0 : cs.al;
+      a.o.care_state[3 * (size_t)B + b] = cs.dth; a.o.care_state[4 * (size_t)B + b] = cs.dal;
     }
   }
   if (a.o.pop_stats) {                 // population reductions: warp shuffles, one atomic per warp

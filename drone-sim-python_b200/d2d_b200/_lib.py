@@ -101,6 +101,7 @@ def _load():
         "d2dx_colloc_eval_shard": (C.c_int, [H, P(CollocProblem), i32, i32, c_dp, c_dp, u32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_colloc_pack_positions": (C.c_int, [H, i32, i32, c_dp, c_dp, c_dp]),
         "d2dx_dfma_burn": (C.c_int, [H, i32, i32, i32, c_dp, c_dp]),
+        "d2dx_math_probe": (C.c_int, [H, i32, c_dp, c_dp, c_dp, c_dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)        # AttributeError here = header and library out of sync

@@ -238,6 +238,13 @@ class Engine:
 
 
     # ---- diagnostics -------------------------------------------------------------------------------
+    def math_probe(self, x, y):
+        """Engine elementary functions on device arrays x, y -> [7][n] (sin, cos, atan2(y,x), atan x, y/x, sqrt|x|, rsqrt|x|)."""
+        n = x.numel(); out = self.empty(7, n)
+        check(lib.d2dx_math_probe(self.h, n, _ptr(x), _ptr(y), _ptr(out), self.stream_ptr()), "d2dx_math_probe")
+        self.launches += 1
+        return out
+
     def measure_fp64_peak(self, iters=20000, reps=5):
         """TFLOP/s of a pure DFMA kernel (16 independent chains per thread, 8 x 256 threads per SM), best of reps."""
         sink = self.zeros(1)

@@ -103,7 +103,7 @@ int d2dx_dfff_default_gains(d2dx_dfff_gains* g_host);
 
 /* DFFFController.get(X, t), d2d/guidance.py:62-91, for B aircraft at one time `t`.
  * Outputs U[2][B]; optional Xr[5][B], K[6][B] (row-major 2x3 = K[:, :3]; K[:, 3:] is zero).
- * care_state[3][B] (optional, in/out) warm-starts the Riccati solve. */
+ * care_state[5][B] (optional, in/out, zero-initialised) warm-starts the Riccati solve. */
 int d2dx_dfff_control(d2dx_handle* h, const d2dx_traj_table* tt, const double* X, double t,
                       const double* W, const double* ac, const d2dx_dfff_gains* gains_host,
                       double* U, double* Xr, double* K, double* care_state, void* stream);
@@ -134,7 +134,7 @@ typedef struct {
   double* sum_sq_err;        /* [B] or NULL  += sum_i |X[i,:2]-Xr[i,:2]|^2 over this call        */
   double* max_err;           /* [B] or NULL  = max(previous, max_i |X[i,:2]-Xr[i,:2]|)           */
   int32_t* flags;            /* [B] or NULL  |= 1 non-finite state seen, 2 Riccati not converged */
-  double* care_state;        /* [3][B] or NULL  Riccati warm start carried between calls         */
+  double* care_state;        /* [5][B] or NULL  Riccati warm start carried between calls (zeros = cold) */
   double* pop_stats;         /* [2] or NULL  += sum over scenarios of sum_sq_err; max of max_err */
 } d2dx_rollout_out;
 
@@ -255,6 +255,9 @@ int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const do
 /* FP64 roofline probe: every thread runs `iters` rounds of 16 independent DFMA chains (32*iters flop per
  * thread); the caller times it with CUDA events.  sink: device double[1] (keeps the chains alive). */
 int d2dx_dfma_burn(d2dx_handle* h, int32_t blocks, int32_t threads, int32_t iters, double* sink, void* stream);
+/* the engine's straight-line fp64 elementary functions on n argument pairs (x[n], y[n] device):
+ * out[7][n] = sin x, cos x, atan2(y, x), atan x, y / x, sqrt|x|, 1/sqrt|x|   (accuracy tests) */
+int d2dx_math_probe(d2dx_handle* h, int32_t n, const double* x, const double* y, double* out, void* stream);
 
 #ifdef __cplusplus
 }
