@@ -126,6 +126,53 @@ def python_port_rate():
     return 2 * 150 / (_time.perf_counter() - t0)
 
 
+def secondary_metrics(eng, hbm_peak):
+    """The other rows of the metric (collocation evals/s, formation aircraft-steps/s), device-resident, CUDA events.
+    Collocation is HBM-bound: 200 algorithmic bytes per aircraft-node in the compact layout."""
+    import torch
+    from d2d_b200 import _lib
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); e1.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    rng = np.random.default_rng(12345)
+    for tag, n_ac, N, h, n_prob, cost in (
+            ("c3_batch4096", 1, 1001, 0.02, 4096, CostSpec(vsp=12., kvel=1.)),
+            ("c4_batch256_allpairs", 16, 500, 0.02, 256, CostSpec(vsp=12., kvel=70., kbank=1., kcol=10., rcol=10., all_pairs=True)),
+            ("c3_single", 1, 1001, 0.02, 1, CostSpec(vsp=12., kvel=1.)),
+            ("c4_single_allpairs", 16, 500, 0.02, 1, CostSpec(vsp=12., kvel=70., kbank=1., kcol=10., rcol=10., all_pairs=True))):
+        prob = CollocationProblem(n_ac, N, h, inst=[(k, 0, 0.) for k in range(3 * n_ac)], cost=cost)
+        free = eng.to_device(rng.normal(0, 3., (n_prob, prob.num_free)) + 12. * (np.arange(prob.num_free) >= 4 * n_ac * N))
+        bufs = prob.buffers(n_prob)
+        dt = timed(lambda: prob.evaluate_device(free, _lib.EVAL_ALL, bufs), 20 if n_prob > 1 else 200)
+        bytes_alg = 200.0 * n_ac * N * n_prob
+        out[tag] = {"evals_per_s": n_prob / dt, "ms_per_launch": dt * 1e3, "aircraft_nodes_per_launch": n_ac * N * n_prob,
+                    "roofline": {"bound": "hbm" if n_prob > 1 else "launch latency", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": bytes_alg / dt / 1e9 / hbm_peak}}
+    # formation rollout, config C2 replicated: F formations of 6 aircraft, 1200 samples, dt 0.05, RK4 nsub 5
+    from d2d_b200.simulation import chain_incidence
+    n_ac, T = 6, 1200
+    F = eng.sm_count * 5 * (eng.formation_threads_per_sm // 32)        # whole waves: 5 formations per warp
+    M = F * n_ac
+    X0 = eng.to_device(np.ascontiguousarray(np.tile(np.array([20, 30, -np.pi / 2, 0, 10.]), (M, 1)).T))
+    c, r, ac = eng.zeros(2, M), eng.to_device(np.full(M, 60.)), eng.to_device(np.stack([np.full(M, 0.01), np.full(M, 1.)]))
+    z = np.ones(n_ac - 1) * 2 * np.pi / n_ac
+    Xf = eng.empty(5, M)
+    dt = timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3)
+    out["formation_c2_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dt, "rk4_substeps_per_s": M * (T - 1) * 5 / dt, "formations": F, "ms_per_launch": dt * 1e3}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -138,6 +185,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--seed", type=int, default=12345)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -284,10 +332,16 @@ def main():
         rate, cores, sample, _ = cpu_port_run(512 * cores, min(1000, T_steps), args.seed)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "python_port_1core": python_port_rate()}
+    secondary = None
+    if not args.no_secondary:
+        try:
+            secondary = secondary_metrics(eng, hbm_peak or 6650.0)
+        except Exception as e:                          # never lose the headline line over a side metric
+            secondary = {"error": f"{type(e).__name__}: {e}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
             "checks": {"nonfinite_or_unconverged_scenarios": flags_bad, "population_rms_pos_err": float(np.sqrt(pop[0].item() / (B * world * (T_steps + 1)))),
                        "population_max_pos_err": float(pop[1].item())}}
     print(json.dumps(line))

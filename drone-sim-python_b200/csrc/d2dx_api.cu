@@ -135,12 +135,13 @@ __global__ void __launch_bounds__(kThreads) dfff_control_kernel(const d2dx_traj_
     cold = !(cs.al > 0.0);
   }
   int flags = 0;
-  FlatState fr;
-  double u_phi, u_v, k6[6];
-  dfff_control<true>(Y, a, ac[B + b], x, g, cc, cs, cold, flags, fr, u_phi, u_v, k6);
+  RefCtl rc;
+  double u_phi, u_v;
+  make_ref(Y, a, ac[B + b], cc, cs, cold, flags, rc);
+  feedback(rc, x, g, u_phi, u_v);
   U[b] = u_phi; U[(size_t)B + b] = u_v;
-  if (Xr) { Xr[b] = fr.x; Xr[(size_t)B + b] = fr.y; Xr[2 * (size_t)B + b] = fr.psi; Xr[3 * (size_t)B + b] = fr.phi; Xr[4 * (size_t)B + b] = fr.va; }
-  if (K) for (int k = 0; k < 6; ++k) K[(size_t)k * B + b] = k6[k];
+  if (Xr) { Xr[b] = rc.xr; Xr[(size_t)B + b] = rc.yr; Xr[2 * (size_t)B + b] = rc.psir; Xr[3 * (size_t)B + b] = rc.phir; Xr[4 * (size_t)B + b] = rc.var; }
+  if (K) for (int k = 0; k < 6; ++k) K[(size_t)k * B + b] = rc.k[k];
   if (care_state) {
     care_state[b] = cs.C; care_state[B + b] = cs.S; care_state[2 * (size_t)B + b] = cold ? 0.0 : cs.al;
     care_state[3 * (size_t)B + b] = cs.dth; care_state[4 * (size_t)B + b] = cs.dal;

@@ -26,7 +26,10 @@ struct CollocArgs {
 
 __device__ __forceinline__ bool enabled(double k) { return (k == k) && k != 0.0; }
 
-__global__ void __launch_bounds__(kCollocThreads) colloc_kernel(const __grid_constant__ CollocArgs a) {
+// EXTRA = obstacle and / or pairwise collision terms present (exp, shared-memory pair loop); the plain instantiation is
+// the lean HBM-bound path (residual + Jacobian + input cost + gradient) and is held to 64 registers for occupancy.
+template <bool EXTRA>
+__global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(const __grid_constant__ CollocArgs a) {
   extern __shared__ double spos[];                 // [n_total][2][TN]
   __shared__ double sred[4][4];
   __shared__ int s_last;
@@ -38,8 +41,8 @@ __global__ void __launch_bounds__(kCollocThreads) colloc_kernel(const __grid_con
   const int i = tile * TN + il;
   const double* fr = a.free_ + (size_t)prob * a.n_free;
   const bool want_cg = (a.what & (D2DX_EVAL_COST | D2DX_EVAL_GRAD)) != 0;
-  const bool use_col = want_cg && enabled(P.kcol) && a.n_total > 1;
-  const bool use_obs = want_cg && enabled(P.kobs) && P.n_obs > 0;
+  const bool use_col = EXTRA && want_cg && enabled(P.kcol) && a.n_total > 1;
+  const bool use_obs = EXTRA && want_cg && enabled(P.kobs) && P.n_obs > 0;
 
   if (use_col) {                                   // stage the tile's positions of ALL aircraft
     for (int idx = tid; idx < a.n_total * TN; idx += kCollocThreads) {
@@ -70,18 +73,21 @@ __global__ void __launch_bounds__(kCollocThreads) colloc_kernel(const __grid_con
     const double x = fr[ox], y = fr[oy], psi = fr[ops], phi = fr[ophi], v = fr[ov];
 
     if ((a.what & (D2DX_EVAL_RESIDUAL | D2DX_EVAL_JAC)) && i >= 1) {
-      double s, c;
-      sincos(psi, &s, &c);
-      const double tn = tan(phi);
+      double s, c, sp, cp;
+      sincos_any(psi, s, c);
+      sincos_any(phi, sp, cp);
+      const double iv = rcp_f(v);
+      const double tn = sp * rcp_f(cp);            // tan(phi)
+      const double gtv = kG * tn * iv;             // g tan(phi) / v
       if (a.what & D2DX_EVAL_RESIDUAL) {           // equation-major, node-minor (opty layout)
         const double xp = fr[ox - 1], yp = fr[oy - 1], pp = fr[ops - 1];
         double* r = a.res + (size_t)prob * a.n_con + (size_t)(3 * a_l) * (N - 1) + (i - 1);
-        r[0] = (x - xp) / P.h - v * c + P.wind[0];
-        r[(size_t)(N - 1)] = (y - yp) / P.h - v * s + P.wind[1];
-        r[2 * (size_t)(N - 1)] = (psi - pp) / P.h - kG * tn / v;
+        r[0] = (x - xp) * ih - v * c + P.wind[0];
+        r[(size_t)(N - 1)] = (y - yp) * ih - v * s + P.wind[1];
+        r[2 * (size_t)(N - 1)] = (psi - pp) * ih - gtv;
       }
       if (a.what & D2DX_EVAL_JAC) {
-        const double j[12] = {ih, v * s, -ih, -c, ih, -v * c, -ih, -s, ih, -ih, -kG * (tn * tn + 1.0) / v, kG * tn / (v * v)};
+        const double j[12] = {ih, v * s, -ih, -c, ih, -v * c, -ih, -s, ih, -ih, -kG * fma(tn, tn, 1.0) * iv, gtv * iv};
         if (a.layout == D2DX_JAC_COMPACT) {        // [n_ac][12][N-1]: coalesced along the node
           double* jo = a.jac + (size_t)prob * a.nnz + (size_t)a_l * 12 * (N - 1) + (i - 1);
 #pragma unroll
@@ -242,9 +248,11 @@ __global__ void pack_positions_kernel(int n_ac, int N, const double* __restrict_
 
 int colloc_resident_threads_per_sm() {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, colloc_kernel, kCollocThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, colloc_kernel<false>, kCollocThreads, 0);
   return nb * kCollocThreads;
 }
+
+static bool enabled_h(double k) { return (k == k) && k != 0.0; }
 
 static void tile_shape(int n_ac, int& TN, int& APP) {
   TN = 128;
@@ -289,12 +297,19 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
   sizes(p, layout, s3);
   a.n_free = s3[0]; a.n_con = s3[1]; a.nnz = s3[2];
   D2DX_CUDA(cudaSetDevice(h->device));
-  const size_t smem = (size_t)n_total * 2 * a.TN * sizeof(double);
-  if (smem > 48 * 1024) {
-    D2DX_CHECK_ARG(smem <= 200 * 1024, "%s: %d aircraft need %zu B of shared memory", who, n_total, smem);
-    D2DX_CUDA(cudaFuncSetAttribute(colloc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool want_cg = (what & (D2DX_EVAL_COST | D2DX_EVAL_GRAD)) != 0;
+  const bool extra = want_cg && ((enabled_h(p->kcol) && n_total > 1) || (enabled_h(p->kobs) && p->n_obs > 0));
+  const unsigned grid = (unsigned)((long)n_prob * a.ntiles);
+  if (extra) {
+    const size_t smem = (enabled_h(p->kcol) && n_total > 1) ? (size_t)n_total * 2 * a.TN * sizeof(double) : 0;
+    if (smem > 48 * 1024) {
+      D2DX_CHECK_ARG(smem <= 200 * 1024, "%s: %d aircraft need %zu B of shared memory", who, n_total, smem);
+      D2DX_CUDA(cudaFuncSetAttribute(colloc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    colloc_kernel<true><<<grid, kCollocThreads, smem, as_stream(stream)>>>(a);
+  } else {
+    colloc_kernel<false><<<grid, kCollocThreads, 0, as_stream(stream)>>>(a);
   }
-  colloc_kernel<<<(unsigned)((long)n_prob * a.ntiles), kCollocThreads, smem, as_stream(stream)>>>(a);
   D2DX_LAUNCH_CHECK("colloc_kernel");
   return D2DX_OK;
 }

@@ -331,8 +331,8 @@ static __device__ __noinline__ bool care_newton_loop(const CareStep& k, double& 
 // smoothly, so the start is already O(drift^2) close); then ONE Newton step and ONE chord step (same Jacobian) in
 // straight-line code, accepted when the chord step is below 3e-8 (=> error ~1e-15); otherwise the general loop.
 // Returns false when not even the loop converged.
-__device__ __forceinline__ bool care_gain(const CareConst& cc, double v, double b1, double b2, CareState& st, bool cold, double* K0) {
-  const double c1 = cc.sr1 * rcp_f(b1), e = b2 * c1, c1q = c1 * cc.sq;
+__device__ __forceinline__ bool care_gain(const CareConst& cc, double v, double c1, double e, CareState& st, bool cold, double* K0) {
+  const double c1q = c1 * cc.sq;                                   // c1 = sqrt(r1)/b1, e = b2 c1
   CareStep k;
   k.k1 = c1q * cc.isr2; k.ba = e * cc.isr2; k.vc2 = v * cc.sr2; k.ve = v * e; k.k2 = 2.0 * v * c1q; k.q3 = cc.q3;
   double C = st.C, S = st.S, al = st.al;
@@ -376,35 +376,39 @@ __device__ __forceinline__ bool care_gain(const CareConst& cc, double v, double 
   return ok;
 }
 
-// DFFFController.get, d2d/guidance.py:62-91, given the flat output at t.  Returns U; fills the reference
-// state, and K (2x3, world frame) when WANT_K.
-template <bool WANT_K>
-__device__ __forceinline__ void dfff_control(const FlatOut& Y, const AcPar& a, double tau_v, const double* X,
-                                             const d2dx_dfff_gains& g, const CareConst& cc, CareState& cs, bool& cold,
-                                             int& flags, FlatState& fr, double& u_phi, double& u_v, double* K) {
+// DFFFController.get (d2d/guidance.py:62-91) split in two.  Everything up to the gain depends on the reference
+// trajectory and the wind only -- NOT on the aircraft state -- so the rollout computes it one control step ahead,
+// interleaved with the RK4 stages of the current step (two independent dependency chains per thread).
+struct RefCtl { double xr, yr, psir, phir, var, uphi, uv, k[6]; };   // reference state, feed-forward input, K1 = K' T (2x3)
+
+__device__ __forceinline__ void make_ref(const FlatOut& Y, const AcPar& a, double tau_v, const CareConst& cc, CareState& cs,
+                                         bool& cold, int& flags, RefCtl& r) {
+  FlatState fr;
   flatness(Y, a.wx, a.wy, tau_v, fr);
-  double ex = clip(X[0] - fr.x, -g.err_sat[0], g.err_sat[0]);
-  double ey = clip(X[1] - fr.y, -g.err_sat[1], g.err_sat[1]);
-  double ep = clip(wrap_pi(X[2] - fr.psi), -g.err_sat[2], g.err_sat[2]);
-  // cont_jac at the reference state: cos^2(atan z) = 1/(1+z^2), tan(atan z) = z
+  // cont_jac at the reference state (d2d/dynamic.py:36-38 as written), with cos^2(atan z) = 1/(1+z^2), tan(atan z) = z:
+  //   b1 = g/va/(1+cos^2 phi) = g (1+z^2) / (va (2+z^2)),  b2 = g z / va^2;   c1 = sqrt(r1)/b1,  e = b2 c1
   const double z2 = fr.z * fr.z;
-  const double b1 = kG * fr.inv_va * ((1.0 + z2) * rcp_f(2.0 + z2));
-  const double b2 = kG * fr.inv_va * fr.inv_va * fr.z;
+  const double c1 = cc.sr1 * (2.0 + z2) * rcp_f(kG * fr.inv_va * (1.0 + z2));
+  const double e = kG * fr.inv_va * fr.inv_va * fr.z * c1;
   double K0[6];
-  if (care_gain(cc, fr.va, b1, b2, cs, cold, K0)) cold = false;
+  if (care_gain(cc, fr.va, c1, e, cs, cold, K0)) cold = false;
   else { flags |= 2; cold = true; }
-  // error in the path frame, feedback, saturation (:85-88)
-  const double e1 = fr.cpsi * ex + fr.spsi * ey, e2 = fr.cpsi * ey - fr.spsi * ex;
-  u_phi = clip(fr.u_phi - (K0[0] * e1 + K0[1] * e2 + K0[2] * ep), g.u_lo[0], g.u_hi[0]);
-  u_v = clip(fr.u_v - (K0[3] * e1 + K0[4] * e2 + K0[5] * ep), g.u_lo[1], g.u_hi[1]);
-  if (WANT_K) {
+  r.xr = fr.x; r.yr = fr.y; r.psir = fr.psi; r.phir = fr.phi; r.var = fr.va; r.uphi = fr.u_phi; r.uv = fr.u_v;
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      K[3 * m + 0] = K0[3 * m] * fr.cpsi - K0[3 * m + 1] * fr.spsi;
-      K[3 * m + 1] = K0[3 * m] * fr.spsi + K0[3 * m + 1] * fr.cpsi;
-      K[3 * m + 2] = K0[3 * m + 2];
-    }
+  for (int m = 0; m < 2; ++m) {                                  // K1 = K' T,  T = rot(-psi_ref) (+) 1
+    r.k[3 * m + 0] = K0[3 * m] * fr.cpsi - K0[3 * m + 1] * fr.spsi;
+    r.k[3 * m + 1] = K0[3 * m] * fr.spsi + K0[3 * m + 1] * fr.cpsi;
+    r.k[3 * m + 2] = K0[3 * m + 2];
   }
+}
+
+// the state-dependent rest: error, wrap, saturations, feedback (d2d/guidance.py:67-70,85-88)
+__device__ __forceinline__ void feedback(const RefCtl& r, const double* X, const d2dx_dfff_gains& g, double& u_phi, double& u_v) {
+  const double ex = clip(X[0] - r.xr, -g.err_sat[0], g.err_sat[0]);
+  const double ey = clip(X[1] - r.yr, -g.err_sat[1], g.err_sat[1]);
+  const double ep = clip(wrap_pi(X[2] - r.psir), -g.err_sat[2], g.err_sat[2]);
+  u_phi = clip(r.uphi - fma(r.k[0], ex, fma(r.k[1], ey, r.k[2] * ep)), g.u_lo[0], g.u_hi[0]);
+  u_v = clip(r.uv - fma(r.k[3], ex, fma(r.k[4], ey, r.k[5] * ep)), g.u_lo[1], g.u_hi[1]);
 }
 
 // CircleTraj.get + GVFcontroller.get, d2d/guidance.py:137-146,155-181 (E = [[0,1],[-1,0]], H = 2I)

@@ -40,7 +40,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       :: "r"(mb), "r"(phase) : "memory");
 }
 
-template <int UNIFORM, bool LOGGING>
+template <int UNIFORM, bool LOGGING, bool LOGREF>
 __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) rollout_dfff_kernel(const RolloutArgs a) {
   __shared__ __align__(128) double spar[D2DX_SEG_NPAR][kRolloutThreads];
   __shared__ __align__(8) uint64_t bar;
@@ -102,12 +102,8 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
     if (ev < ev_end) ev_next = a.s.pert_step[ev];
   }
 
-  const int log_every = a.o.log_every > 0 ? a.o.log_every : 1;
-  const int n_samples = a.i_end - a.i_begin + (a.final_control ? 1 : 0);
-  double t = a.time[a.i_begin];
-  for (int n = 0; n < n_samples; ++n) {
-    const int i = a.i_begin + n;
-    // ---- reference trajectory at t (Trajectory.get) ----
+  // reference + gain at time t (Trajectory.get, DiffFlatness, cont_jac, LQR): state-independent
+  auto reference_at = [&](double t, RefCtl& r) {
     FlatOut Y;
     if (UNIFORM >= 0) {
       segment_eval<false>(UNIFORM, P, t, Y);
@@ -120,11 +116,20 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
       }
       segment_eval<false>(seg_type, P, te, Y);
     }
-    // ---- DFFFController.get ----
-    FlatState fr;
-    double u_phi, u_v, K[6];
-    dfff_control<LOGGING>(Y, ap, tau_v, X, a.g, cc, cs, cold, flags, fr, u_phi, u_v, K);
-    const double ex = X[0] - fr.x, ey = X[1] - fr.y, d2 = ex * ex + ey * ey;
+    make_ref(Y, ap, tau_v, cc, cs, cold, flags, r);
+  };
+
+  const int log_every = a.o.log_every > 0 ? a.o.log_every : 1;
+  const int n_samples = a.i_end - a.i_begin + (a.final_control ? 1 : 0);
+  double t = a.time[a.i_begin];
+  for (int n = 0; n < n_samples; ++n) {
+    const int i = a.i_begin + n;
+    // ---- DFFFController.get: reference + gain (state-independent), then the state feedback ----
+    RefCtl ref;
+    reference_at(t, ref);
+    double u_phi, u_v;
+    feedback(ref, X, a.g, u_phi, u_v);
+    const double ex = X[0] - ref.xr, ey = X[1] - ref.yr, d2 = ex * ex + ey * ey;
     sum_sq += d2; max_sq = fmax(max_sq, d2);
     if (LOGGING && active && (i % log_every) == 0) {
       const size_t row = (size_t)(i / log_every);
@@ -133,21 +138,23 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
         for (int k = 0; k < 5; ++k) a.o.X_log[(row * 5 + k) * B + b] = X[k];
       }
       if (a.o.U_log) { a.o.U_log[(row * 2) * B + b] = u_phi; a.o.U_log[(row * 2 + 1) * B + b] = u_v; }
-      if (a.o.Xr_log) {
+      if (LOGREF && a.o.Xr_log) {
         double* q = a.o.Xr_log + row * 5 * B + b;
-        q[0] = fr.x; q[(size_t)B] = fr.y; q[2 * (size_t)B] = fr.psi; q[3 * (size_t)B] = fr.phi; q[4 * (size_t)B] = fr.va;
+        q[0] = ref.xr; q[(size_t)B] = ref.yr; q[2 * (size_t)B] = ref.psir; q[3 * (size_t)B] = ref.phir; q[4 * (size_t)B] = ref.var;
       }
-      if (a.o.K_log) {
+      if (LOGREF && a.o.K_log) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a.o.K_log[(row * 6 + k) * B + b] = K[k];
+        for (int k = 0; k < 6; ++k) a.o.K_log[(row * 6 + k) * B + b] = ref.k[k];
       }
     }
     if (i == a.i_end) break;           // trailing controller evaluation of 05_test_simulation.py:33
     // ---- Aircraft.disc_dyn (fixed-step RK4), then perturbation ----
+    // (computing the next reference here, one step ahead and interleaved with the RK4 stages, was tried in round 1:
+    //  the extra live state pushed the kernel over 128 registers and it ran 7 % slower)
     const double t1 = a.time[i + 1];
     rk4_step(ap, X, u_phi, u_v, t1 - t, a.nsub);
     t = t1;
-    if (i + 1 == ev_next) {
+    if (i + 1 == ev_next) {            // perturbation event (05_test_simulation.py:32)
 #pragma unroll
       for (int k = 0; k < 5; ++k) X[k] += a.s.pert_dx[(size_t)k * a.s.n_events + ev];
       ++ev;
@@ -178,15 +185,17 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
 template <int UNIFORM>
 static int launch_rollout(const RolloutArgs& a, bool logging, cudaStream_t st) {
   const int grid = (a.s.B + kRolloutThreads - 1) / kRolloutThreads;
-  if (logging) rollout_dfff_kernel<UNIFORM, true><<<grid, kRolloutThreads, 0, st>>>(a);
-  else rollout_dfff_kernel<UNIFORM, false><<<grid, kRolloutThreads, 0, st>>>(a);
+  const bool logref = a.o.Xr_log || a.o.K_log;
+  if (logref) rollout_dfff_kernel<UNIFORM, true, true><<<grid, kRolloutThreads, 0, st>>>(a);
+  else if (logging) rollout_dfff_kernel<UNIFORM, true, false><<<grid, kRolloutThreads, 0, st>>>(a);
+  else rollout_dfff_kernel<UNIFORM, false, false><<<grid, kRolloutThreads, 0, st>>>(a);
   D2DX_LAUNCH_CHECK("rollout_dfff_kernel");
   return D2DX_OK;
 }
 
 int rollout_resident_threads_per_sm() {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_dfff_kernel<D2DX_SEG_CIRCLE, false>, kRolloutThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_dfff_kernel<D2DX_SEG_CIRCLE, false, false>, kRolloutThreads, 0);
   return nb * kRolloutThreads;
 }
 

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libd2dx.so")
+LIB_PATH = os.environ.get("D2DX_LIB") or os.path.join(_HERE, "libd2dx.so")     # D2DX_LIB: A/B builds of the same ABI
 
 SEG_LINE, SEG_CIRCLE, SEG_SLALOM, SEG_POLY, SEG_SI_LINE = range(5)
 SEG_NPAR = 17
