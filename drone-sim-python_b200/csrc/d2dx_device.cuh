@@ -210,29 +210,29 @@ __device__ __forceinline__ void stage_heading(double s0, double c0, double d, do
 __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
   const double h = dt / nsub, hh = 0.5 * h, h6 = h / 6.0;
   double x = X[0], y = X[1], psi = X[2], phi = X[3], v = X[4];
-  double worst_d = 0.0, worst_phi = 0.0;
+  bool fast_ok = true;                       // every stage increment < 0.1 rad and every bank angle <= 1.15 rad
   for (int sub = 0; sub < nsub; ++sub) {
     double s1, c1, s, c, d;
     sincos_b(psi, s1, c1);
     // stage 1
     const double k1x = v * c1 + a.wx, k1y = v * s1 + a.wy, k1p = turn_rate(phi, v);
     const double k1f = a.n_inv_tau_phi * (phi - phi_c), k1v = a.n_inv_tau_v * (v - v_c);
-    worst_phi = fmax(worst_phi, fabs(phi));
+    fast_ok = fast_ok && (fabs(phi) <= 1.15);
     // stage 2
     double ph = phi + hh * k1f, vv = v + hh * k1v;
-    d = hh * k1p; worst_d = fmax(worst_d, fabs(d)); worst_phi = fmax(worst_phi, fabs(ph));
+    d = hh * k1p; fast_ok = fast_ok && (fabs(d) < 0.1) && (fabs(ph) <= 1.15);
     stage_heading(s1, c1, d, s, c);
     const double k2x = vv * c + a.wx, k2y = vv * s + a.wy, k2p = turn_rate(ph, vv);
     const double k2f = a.n_inv_tau_phi * (ph - phi_c), k2v = a.n_inv_tau_v * (vv - v_c);
     // stage 3
     ph = phi + hh * k2f; vv = v + hh * k2v;
-    d = hh * k2p; worst_d = fmax(worst_d, fabs(d)); worst_phi = fmax(worst_phi, fabs(ph));
+    d = hh * k2p; fast_ok = fast_ok && (fabs(d) < 0.1) && (fabs(ph) <= 1.15);
     stage_heading(s1, c1, d, s, c);
     const double k3x = vv * c + a.wx, k3y = vv * s + a.wy, k3p = turn_rate(ph, vv);
     const double k3f = a.n_inv_tau_phi * (ph - phi_c), k3v = a.n_inv_tau_v * (vv - v_c);
     // stage 4
     ph = phi + h * k3f; vv = v + h * k3v;
-    d = h * k3p; worst_d = fmax(worst_d, fabs(d)); worst_phi = fmax(worst_phi, fabs(ph));
+    d = h * k3p; fast_ok = fast_ok && (fabs(d) < 0.1) && (fabs(ph) <= 1.15);
     stage_heading(s1, c1, d, s, c);
     const double k4x = vv * c + a.wx, k4y = vv * s + a.wy, k4p = turn_rate(ph, vv);
     const double k4f = a.n_inv_tau_phi * (ph - phi_c), k4v = a.n_inv_tau_v * (vv - v_c);
@@ -242,7 +242,7 @@ __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c
     phi += h6 * (k1f + 2.0 * k2f + 2.0 * k3f + k4f);
     v += h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
   }
-  if (!(worst_d < 0.1 && worst_phi <= 1.15)) { rk4_step_generic(a, X, phi_c, v_c, dt, nsub); return; }   // also catches NaN
+  if (!fast_ok) { rk4_step_generic(a, X, phi_c, v_c, dt, nsub); return; }   // NaN compares false: also caught
   X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
 }
 #endif

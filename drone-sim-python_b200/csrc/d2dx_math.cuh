@@ -49,15 +49,15 @@ static __constant__ __align__(16) double kTab[60] = {
     /*58*/ 0.0, 0.0,
 };
 
-// 1/b to ~1 ulp: MUFU.RCP64H seed + two Newton steps, no slow path (b normal, non-zero)
+// 1/b to ~1 ulp: MUFU.RCP64H seed (relative error e0 <= 2^-20), then y0 (1 + e0 + e0^2 + e0^3 + e0^4)-style
+// correction in three DFMA: e = 1 - b y0, t = e + e^2, y = y0 + y0 (t + e^2 t)  -> error e0^5.  No slow path
+// (b normal, non-zero).
 __device__ __forceinline__ double rcp(double b) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
-  double e = fma(-b, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-b, y, 1.0);
-  y = fma(y, fma(e, e, e), y);
-  return y;
+  const double e = fma(-b, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, fma(e * e, t, t), y);
 }
 
 // a/b with a final residual correction (<= 1 ulp)
@@ -71,12 +71,12 @@ __device__ __forceinline__ double div(double a, double b) {
 __device__ __forceinline__ double rsqrt(double a) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double h = 0.5 * a;                       // Newton: y <- y (1.5 - h y^2), twice
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  return y;
+  // e = 1 - a y^2;  1/sqrt(1 - e) = 1 + e/2 + 3 e^2/8 + 5 e^3/16 + 35 e^4/128 + ...   (seed error <= 2^-20 -> e^5 term negligible)
+  const double e = fma(-a * y, y, 1.0);
+  double p = fma(0.2734375, e, 0.3125);
+  p = fma(p, e, 0.375);
+  p = fma(p, e, 0.5);
+  return fma(y * e, p, y);
 }
 
 __device__ __forceinline__ double sqrt(double a) {
@@ -157,7 +157,24 @@ __device__ __forceinline__ double atan2(double y, double x) {
   return copysign(r, y);
 }
 
-__device__ __forceinline__ double atan(double v) { return atan2(v, 1.0); }
+// atan(v): the same reduction with x = 1 (thresholds are compile-time constants)
+__device__ __forceinline__ double atan(double v) {
+  const double ay = fabs(v);
+  const bool g0 = ay >= 0.4375, g1 = ay >= 0.6875, g2 = ay >= 1.1875, g3 = ay >= 2.4375;
+  const double cc = g2 ? 1.5 : (g1 ? 1.0 : (g0 ? 0.5 : 0.0));
+  double num = ay - cc, den = fma(cc, ay, 1.0);
+  if (g3) { num = -1.0; den = ay; }
+  const double hi = g3 ? kTab[38] : (g2 ? kTab[36] : (g1 ? kTab[34] : (g0 ? kTab[32] : 0.0)));
+  const double lo = g3 ? kTab[39] : (g2 ? kTab[37] : (g1 ? kTab[35] : (g0 ? kTab[33] : 0.0)));
+  const double t = div(num, den);
+  const double z = t * t;
+  double p = fma(kTab[20], z, kTab[21]);
+  p = fma(p, z, kTab[22]); p = fma(p, z, kTab[23]); p = fma(p, z, kTab[24]); p = fma(p, z, kTab[25]);
+  p = fma(p, z, kTab[26]); p = fma(p, z, kTab[27]); p = fma(p, z, kTab[28]); p = fma(p, z, kTab[29]);
+  p = fma(p, z, kTab[30]);
+  const double ts = t * (z * p);
+  return copysign(hi - ((ts - lo) - t), v);
+}
 
 }  // namespace fm
 }  // namespace d2dx
