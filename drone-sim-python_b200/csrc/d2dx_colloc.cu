@@ -30,7 +30,7 @@ __device__ __forceinline__ bool enabled(double k) { return (k == k) && k != 0.0;
 // the lean HBM-bound path (residual + Jacobian + input cost + gradient) and is held to 64 registers for occupancy.
 template <bool EXTRA>
 __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(const __grid_constant__ CollocArgs a) {
-  extern __shared__ double spos[];                 // [n_total][2][TN]
+  extern __shared__ double spos[];                 // [n_total][2][TN] positions (+ two gradient accumulators of the same shape)
   __shared__ double sred[4][4];
   __shared__ int s_last;
   const d2dx_colloc_problem& P = a.p;
@@ -43,6 +43,11 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
   const bool want_cg = (a.what & (D2DX_EVAL_COST | D2DX_EVAL_GRAD)) != 0;
   const bool use_col = EXTRA && want_cg && enabled(P.kcol) && a.n_total > 1;
   const bool use_obs = EXTRA && want_cg && enabled(P.kobs) && P.n_obs > 0;
+  // unsharded all-pairs mode: every unordered pair is evaluated ONCE (round k pairs aircraft a with a+k mod n) and its
+  // gradient is scattered to both members through shared-memory accumulators, rounds separated by block barriers
+  const bool sym_col = use_col && P.col_all_pairs && a.pos_all == nullptr;
+  double* sown = spos + (size_t)a.n_total * 2 * a.TN;      // written only by the thread that owns (aircraft, node)
+  double* sacc = sown + (size_t)a.n_total * 2 * a.TN;      // partner-side contributions
 
   if (use_col) {                                   // stage the tile's positions of ALL aircraft
     for (int idx = tid; idx < a.n_total * TN; idx += kCollocThreads) {
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
           if (P.obs_kind == 0) es = clip(exp(r * r - (dx * dx + dy * dy)), 0.0, 1e3);
           else {
             const double ux = dx / r * 2.0, uy = dy / r * 2.0;
-            es = exp(-(ux * ux + uy * uy));
+            es = fm::exp_neg(-(ux * ux + uy * uy));
             if (P.exact_grad) f = (2.0 / r) * (2.0 / r);
           }
           s_obs += es;
@@ -129,7 +134,10 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
           gy += P.kobs * (sN * -2.0 * dy * es) * f;
         }
       }
-      if (use_col) {                               // CostCollision (multiopty_utils.py:120-153), pairs via shared memory
+      if (sym_col) {                               // pair terms come in the rounds below; park the obstacle part
+        sown[(a_l * 2) * TN + il] = gx; sown[(a_l * 2 + 1) * TN + il] = gy;
+        sacc[(a_l * 2) * TN + il] = 0.0; sacc[(a_l * 2 + 1) * TN + il] = 0.0;
+      } else if (use_col) {                        // CostCollision (multiopty_utils.py:120-153), pairs via shared memory
         const double f = P.exact_grad ? col_kr * col_kr : 1.0;
         const int b_lo = P.col_all_pairs ? 0 : (g_glob == 0 ? 1 : (g_glob == 1 ? 0 : 0));
         const int b_hi = P.col_all_pairs ? a.n_total : (g_glob == 0 ? 2 : (g_glob == 1 ? 1 : 0));
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
           if (b == g_glob) continue;
           const double dx = x - spos[(b * 2) * TN + il], dy = y - spos[(b * 2 + 1) * TN + il];
           const double ux = dx / P.rcol * P.kcol_k, uy = dy / P.rcol * P.kcol_k;
-          const double es = exp(-(ux * ux + uy * uy));
+          const double es = fm::exp_neg(-(ux * ux + uy * uy));
           if (g_glob < b) s_col += es;
           gx += P.kcol * (sN * -2.0 * dx * es) * f;
           gy += P.kcol * (sN * -2.0 * dy * es) * f;
@@ -145,9 +153,41 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
       }
       if (a.what & D2DX_EVAL_GRAD) {
         double* go = a.grad + (size_t)prob * a.n_free;
-        go[ox] = gx; go[oy] = gy; go[ops] = 0.0;
+        if (!sym_col) { go[ox] = gx; go[oy] = gy; }
+        go[ops] = 0.0;
         go[ophi] = (P.kbank * 2.0 * phi) * norm_in;
         go[ov] = (P.kvel * 2.0 * dv) * norm_in;
+      }
+    }
+  }
+
+  if (EXTRA && sym_col) {                          // block-uniform condition: every thread takes part in the barriers
+    const int n = n_ac, half = n / 2;
+    const bool even = (n % 2) == 0;
+    const double f = P.exact_grad ? col_kr * col_kr : 1.0;
+    for (int k = 1; k <= half; ++k) {
+      __syncthreads();
+      if (i < N) {
+        for (int a_l = al; a_l < n; a_l += a.APP) {
+          if (even && k == half && a_l >= half) continue;         // the antipodal pair is visited from its lower member only
+          int b = a_l + k; if (b >= n) b -= n;
+          const double dx = spos[(a_l * 2) * TN + il] - spos[(b * 2) * TN + il];
+          const double dy = spos[(a_l * 2 + 1) * TN + il] - spos[(b * 2 + 1) * TN + il];
+          const double ux = dx / P.rcol * P.kcol_k, uy = dy / P.rcol * P.kcol_k;
+          const double es = fm::exp_neg(-(ux * ux + uy * uy));
+          s_col += es;
+          const double wx = P.kcol * (sN * -2.0 * dx * es) * f, wy = P.kcol * (sN * -2.0 * dy * es) * f;
+          sown[(a_l * 2) * TN + il] += wx; sown[(a_l * 2 + 1) * TN + il] += wy;
+          sacc[(b * 2) * TN + il] -= wx; sacc[(b * 2 + 1) * TN + il] -= wy;
+        }
+      }
+    }
+    __syncthreads();
+    if ((a.what & D2DX_EVAL_GRAD) && i < N) {
+      double* go = a.grad + (size_t)prob * a.n_free;
+      for (int a_l = al; a_l < n; a_l += a.APP) {
+        go[(size_t)(3 * a_l) * N + i] = sown[(a_l * 2) * TN + il] + sacc[(a_l * 2) * TN + il];
+        go[(size_t)(3 * a_l + 1) * N + i] = sown[(a_l * 2 + 1) * TN + il] + sacc[(a_l * 2 + 1) * TN + il];
       }
     }
   }
@@ -301,7 +341,9 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
   const bool extra = want_cg && ((enabled_h(p->kcol) && n_total > 1) || (enabled_h(p->kobs) && p->n_obs > 0));
   const unsigned grid = (unsigned)((long)n_prob * a.ntiles);
   if (extra) {
-    const size_t smem = (enabled_h(p->kcol) && n_total > 1) ? (size_t)n_total * 2 * a.TN * sizeof(double) : 0;
+    const bool col = enabled_h(p->kcol) && n_total > 1;
+    const bool sym = col && p->col_all_pairs && pos_all == nullptr;
+    const size_t smem = col ? (size_t)n_total * 2 * a.TN * sizeof(double) * (sym ? 3 : 1) : 0;
     if (smem > 48 * 1024) {
       D2DX_CHECK_ARG(smem <= 200 * 1024, "%s: %d aircraft need %zu B of shared memory", who, n_total, smem);
       D2DX_CUDA(cudaFuncSetAttribute(colloc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

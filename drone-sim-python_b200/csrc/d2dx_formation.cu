@@ -73,13 +73,13 @@ __global__ void __launch_bounds__(kFormThreads) rollout_formation_kernel(const _
 #pragma unroll
       for (int k = 0; k < 5; ++k) a.o.X_log[(row * 5 + k) * M + g] = X[k];
     }
-    const double theta = atan2(X[1] - cy, X[0] - cx);
+    const double theta = atan2_f(X[1] - cy, X[0] - cx);
     double e_edge;
     const double Ur = dcf_warp(sB, sz, a.n_ac, a.n_e, base, j, theta, a.kr, e_edge);
     const double Rr = Ur + R;                            // 08_CircularFormation_Full.py:76
     double U, U1, U2;
     gvf_control(X[0], X[1], X[2], X[4], cx, cy, Rr, a.ke, a.kd, U, U1, U2);
-    const double phi_c = atan(U / 9.81);                 // :85
+    const double phi_c = atan_f(U * (1.0 / 9.81));       // :85  arctan(U/9.81)
     if (log_now) {
       if (a.o.U_log) a.o.U_log[row * M + g] = phi_c;
       if (a.o.Rr_log) a.o.Rr_log[row * M + g] = Rr;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kFormThreads) dcf_kernel(const __grid_constant
   const long f = active ? f_raw : 0;
   const int base = lf * a.n_ac < 32 ? lf * a.n_ac : 0;
   const size_t M = (size_t)a.F * a.n_ac, g = (size_t)f * a.n_ac + j;
-  const double theta = atan2(a.p[M + g] - a.c[M + g], a.p[g] - a.c[g]);
+  const double theta = atan2_f(a.p[M + g] - a.c[M + g], a.p[g] - a.c[g]);
   double e_edge;
   const double Ur = dcf_warp(sB, sz, a.n_ac, a.n_e, base, j, theta, a.kr, e_edge);
   if (active) {

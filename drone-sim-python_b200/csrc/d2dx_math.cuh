@@ -133,6 +133,33 @@ __device__ __forceinline__ void sincos_small(double d, double& s, double& c) {
   c = fma(pc, u, 1.0);
 }
 
+// exp(y) for y <= 0 (Gaussian-type penalties): k = rint(y log2 e), r = y - k ln2 (two-term), degree-13 Taylor polynomial
+// on |r| <= ln2/2 (truncation 4e-18 relative), scaling through the exponent field; flushes to 0 below 2^-1000.
+__device__ __forceinline__ double exp_neg(double y) {
+  const double t = fma(y, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double j = t - 6755399441055744.0;
+  double r = fma(j, -6.93147180369123816490e-01, y);
+  r = fma(j, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;                 // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);               // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);              // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);              // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);             // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);               // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);              // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);             // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);              // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);             // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);             // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int hi = __double2hiint(p) + (k << 20);
+  const double v = __hiloint2double(hi, __double2loint(p));
+  return (k < -1000) ? 0.0 : v;
+}
+
 // atan(num/den) for den > 0 ... folded into atan2 below: one division in total.
 // atan2(y, x) (fdlibm's 4-interval reduction atan(t) = atan(c) + atan((t-c)/(1+ct)), c in {0, .5, 1, 1.5, inf}, with
 // t = |y|/|x| never formed: (t-c)/(1+ct) = (|y| - c|x|)/(|x| + c|y|)).  x = y = 0 returns 0 like np.arctan2.
