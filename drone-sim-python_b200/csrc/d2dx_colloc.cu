@@ -21,6 +21,8 @@ struct CollocArgs {
   int n_total, a_lo;          // shard context: owned aircraft are global [a_lo, a_lo + p.n_ac) of n_total
   const double* pos_all;      // [n_total][2][N] or NULL (positions come from free_)
   int TN, APP, ntiles;        // nodes per tile, aircraft per pass, tiles per problem
+  int ticket_mode;            // 1: the last warp of a problem (atomic ticket) finishes the cost in this kernel;
+                              // 0: per-warp partials only, colloc_cost_kernel finishes (large batches: no fence in the hot kernel)
   long n_free, n_con, nnz;
 };
 
@@ -31,8 +33,6 @@ __device__ __forceinline__ bool enabled(double k) { return (k == k) && k != 0.0;
 template <bool EXTRA>
 __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(const __grid_constant__ CollocArgs a) {
   extern __shared__ double spos[];                 // [n_total][2][TN] positions (+ two gradient accumulators of the same shape)
-  __shared__ double sred[4][4];
-  __shared__ int s_last;
   const d2dx_colloc_problem& P = a.p;
   const int N = P.N, n_ac = P.n_ac, TN = a.TN;
   const int tid = threadIdx.x;
@@ -201,28 +201,54 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
     }
   }
 
-  if (a.what & D2DX_EVAL_COST) {                   // deterministic two-level reduction, last block finishes
-    double v4[4] = {warp_sum(s_v), warp_sum(s_phi), warp_sum(s_obs), warp_sum(s_col)};
-    if ((tid & 31) == 0) for (int k = 0; k < 4; ++k) sred[tid >> 5][k] = v4[k];
-    __syncthreads();
-    if (tid == 0) {
-      double* part = a.scratch + ((size_t)prob * a.ntiles + tile) * 4;
-      for (int k = 0; k < 4; ++k) part[k] = sred[0][k] + sred[1][k] + sred[2][k] + sred[3][k];
-      __threadfence();
-      s_last = (atomicAdd(&a.tickets[prob % kMaxTickets], 1) == a.ntiles - 1);
+  if (a.what & D2DX_EVAL_COST) {                   // deterministic reduction: warp shuffles -> per-warp partials -> fixed-order sum
+    const double v4[4] = {warp_sum(s_v), warp_sum(s_phi), warp_sum(s_obs), warp_sum(s_col)};
+    const int nparts = a.ntiles * (kCollocThreads / 32);
+    const int lane = tid & 31;
+    double* part = a.scratch + ((size_t)prob * nparts + tile * (kCollocThreads / 32) + (tid >> 5)) * 4;
+    if (lane == 0) { part[0] = v4[0]; part[1] = v4[1]; part[2] = v4[2]; part[3] = v4[3]; }
+    if (a.ticket_mode) {
+      int last = 0;
+      if (lane == 0) {
+        __threadfence();
+        last = atomicAdd(&a.tickets[prob % kMaxTickets], 1) == nparts - 1;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        const double* all = a.scratch + (size_t)prob * nparts * 4;
+        double t4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int t = lane; t < nparts; t += 32)
+          for (int k = 0; k < 4; ++k) t4[k] += __ldcg(all + t * 4 + k);
+        for (int k = 0; k < 4; ++k) t4[k] = warp_sum(t4[k]);
+        if (lane == 0) {
+          double c = norm_in * (P.kvel * t4[0] + P.kbank * t4[1]);
+          if (use_obs) c += P.kobs * (sN * t4[2]);
+          if (use_col) c += P.kcol * (sN * t4[3]);
+          a.cost[prob] = c;
+          a.tickets[prob % kMaxTickets] = 0;
+        }
+      }
     }
-    __syncthreads();
-    if (s_last && tid == 0) {
-      __threadfence();
-      double t4[4] = {0.0, 0.0, 0.0, 0.0};
-      const double* part = a.scratch + (size_t)prob * a.ntiles * 4;
-      for (int t = 0; t < a.ntiles; ++t) for (int k = 0; k < 4; ++k) t4[k] += __ldcg(part + t * 4 + k);
-      double c = norm_in * (P.kvel * t4[0] + P.kbank * t4[1]);
-      if (use_obs) c += P.kobs * (sN * t4[2]);
-      if (use_col) c += P.kcol * (sN * t4[3]);
-      a.cost[prob] = c;
-      a.tickets[prob % kMaxTickets] = 0;
-    }
+  }
+}
+
+// second pass of the cost for large batches: one warp per problem sums the per-warp partials in a fixed order
+__global__ void __launch_bounds__(128) colloc_cost_kernel(int n_prob, int nparts, const double* __restrict__ scratch, double norm_in,
+                                                          double sN, double kvel, double kbank, double kobs, double kcol,
+                                                          int use_obs, int use_col, double* __restrict__ cost) {
+  const int prob = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (prob >= n_prob) return;
+  const double* all = scratch + (size_t)prob * nparts * 4;
+  double t4[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int t = lane; t < nparts; t += 32)
+    for (int k = 0; k < 4; ++k) t4[k] += all[t * 4 + k];
+  for (int k = 0; k < 4; ++k) t4[k] = warp_sum(t4[k]);
+  if (lane == 0) {
+    double c = norm_in * (kvel * t4[0] + kbank * t4[1]);
+    if (use_obs) c += kobs * (sN * t4[2]);
+    if (use_col) c += kcol * (sN * t4[3]);
+    cost[prob] = c;
   }
 }
 
@@ -337,6 +363,7 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
   sizes(p, layout, s3);
   a.n_free = s3[0]; a.n_con = s3[1]; a.nnz = s3[2];
   D2DX_CUDA(cudaSetDevice(h->device));
+  a.ticket_mode = n_prob < 64;                 // latency-sensitive single evaluations stay one launch
   const bool want_cg = (what & (D2DX_EVAL_COST | D2DX_EVAL_GRAD)) != 0;
   const bool extra = want_cg && ((enabled_h(p->kcol) && n_total > 1) || (enabled_h(p->kobs) && p->n_obs > 0));
   const unsigned grid = (unsigned)((long)n_prob * a.ntiles);
@@ -353,6 +380,13 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
     colloc_kernel<false><<<grid, kCollocThreads, 0, as_stream(stream)>>>(a);
   }
   D2DX_LAUNCH_CHECK("colloc_kernel");
+  if ((what & D2DX_EVAL_COST) && !a.ticket_mode) {
+    const double sN = p->obj_scale / p->N;
+    colloc_cost_kernel<<<(n_prob + 3) / 4, 128, 0, as_stream(stream)>>>(
+        n_prob, a.ntiles * (kCollocThreads / 32), scratch, sN / p->in_div, sN, p->kvel, p->kbank, p->kobs, p->kcol,
+        enabled_h(p->kobs) && p->n_obs > 0, enabled_h(p->kcol) && n_total > 1, cost);
+    D2DX_LAUNCH_CHECK("colloc_cost_kernel");
+  }
   return D2DX_OK;
 }
 
@@ -371,7 +405,7 @@ int64_t d2dx_colloc_scratch_size(const d2dx_colloc_problem* p, int32_t n_prob) {
   if (!p || n_prob < 1) return 0;
   int TN, APP;
   tile_shape(p->n_ac, TN, APP);
-  return (int64_t)n_prob * ((p->N + TN - 1) / TN) * 4;
+  return (int64_t)n_prob * ((p->N + TN - 1) / TN) * (kCollocThreads / 32) * 4;
 }
 
 int d2dx_colloc_structure(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t layout, int64_t* rows, int64_t* cols, void* stream) {
