@@ -156,7 +156,11 @@ def secondary_metrics(eng, hbm_peak):
         bufs = prob.buffers(n_prob)
         dt = timed(lambda: prob.evaluate_device(free, _lib.EVAL_ALL, bufs), 20 if n_prob > 1 else 200)
         bytes_alg = 200.0 * n_ac * N * n_prob
-        out[tag] = {"evals_per_s": n_prob / dt, "ms_per_launch": dt * 1e3, "aircraft_nodes_per_launch": n_ac * N * n_prob,
+        extra = {}
+        if n_prob == 1:                                  # the same launch replayed from a CUDA graph
+            replay, _ = prob.graph(free)
+            extra = {"graph_replay_evals_per_s": 1.0 / timed(replay, 200)}
+        out[tag] = {**extra, "evals_per_s": n_prob / dt, "ms_per_launch": dt * 1e3, "aircraft_nodes_per_launch": n_ac * N * n_prob,
                     "roofline": {"bound": "hbm" if n_prob > 1 else "launch latency", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_alg / dt / 1e9 / hbm_peak}}
     # formation rollout, config C2 replicated: F formations of 6 aircraft, 1200 samples, dt 0.05, RK4 nsub 5

@@ -79,6 +79,20 @@ class CollocationProblem:
         self.eng.colloc_eval(self.c, n_prob, free_dev, self.layout, what, b["res"], b["jac"], b["cost"], b["grad"], b["scratch"])
         return b
 
+    def graph(self, free_dev, what=_lib.EVAL_ALL):
+        """Captures one evaluation of `free_dev` (device tensor (n_prob, num_free), updated in place by the caller)
+        into a CUDA graph and returns (replay, outputs): `replay()` re-launches it with ~one driver call -- the
+        launch-latency-bound single-problem case of an NLP solver's callback loop."""
+        n_prob = free_dev.shape[0]
+        out = self.buffers(n_prob)
+        self.evaluate_device(free_dev, what, out)               # warm up (lazy module load) outside the capture
+        torch.cuda.synchronize(self.eng.device)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.eng.device)
+        with torch.cuda.graph(g, stream=side):
+            self.evaluate_device(free_dev, what, out)
+        return g.replay, out
+
     # ---- host level (what IPOPT calls) ----------------------------------------------------------------
     def _run(self, free, what, key):
         free = np.asarray(free, dtype=np.float64)

@@ -234,6 +234,26 @@ class MinSnapBatch:
     def __len__(self):
         return len(self.coefs0)
 
+    @classmethod
+    def from_boundaries(cls, Y0, Y1, duration, t0=0.):
+        """B min-snap trajectories of one common duration from boundary values Y0, Y1 of shape (B, 2, 4)
+        (position and three derivatives per component) -- the algebra of PolynomialOne (d2d/trajectory.py:53-68),
+        vectorised over the batch."""
+        Y0, Y1 = np.asarray(Y0, dtype=np.float64), np.asarray(Y1, dtype=np.float64)
+        nd = 4
+        M1 = np.diag([float(arr(i, i)) for i in range(nd)])
+        M3, M4 = np.zeros((nd, nd)), np.zeros((nd, nd))
+        for i in range(nd):
+            for j in range(nd):
+                if j >= i:
+                    M3[i, j] = arr(i, j) * duration ** (j - i)
+                M4[i, j] = arr(i, j + nd) * duration ** (j - i + nd)
+        lo = Y0 @ np.linalg.inv(M1).T
+        hi = (Y1 - lo @ M3.T) @ np.linalg.inv(M4).T
+        obj = cls(np.concatenate([lo, hi], axis=2), t0)
+        obj.duration = duration
+        return obj
+
     def pack(self):
         B = len(self)
         par = np.zeros((_lib.SEG_NPAR, B))

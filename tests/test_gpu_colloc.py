@@ -212,3 +212,18 @@ def test_planner_front_ends_and_cost_classes(golden):
     np.testing.assert_allclose(d2mou.CostCollision(r=10.).cost(free, mp), g["m3/cost/collision/cost"], rtol=1e-10)
     with pytest.raises(NotImplementedError):
         mp.run()
+
+
+def test_cuda_graph_replay_matches_direct_evaluation(golden):
+    import torch
+    from d2d_b200 import get_engine
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    g = golden["colloc"]
+    eng = get_engine()
+    prob = CollocationProblem(1, 1001, 0.02, inst=_inst(g, "c3"), cost=CostSpec(vsp=12., kvel=1.))
+    free = eng.to_device(g["c3/sol"][None].copy())
+    replay, out = prob.graph(free)
+    free.copy_(eng.to_device(g["c3/free"][None]))             # new iterate written in place, then one replay
+    replay(); torch.cuda.synchronize()
+    np.testing.assert_allclose(out["res"].cpu().numpy()[0], g["c3/residual"], rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(out["cost"].cpu().numpy()[0], g["cost1/airvel/noisy/cost"], rtol=RTOL)

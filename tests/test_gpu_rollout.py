@@ -258,3 +258,42 @@ def test_engine_elementary_functions_accuracy(d2d):
             ok = ulp <= 4
         assert ok.all(), (nm, float(ulp.max()), x[np.argmax(ulp)], y[np.argmax(ulp)])
         print(nm, "max ulp", float(ulp[ok].max()))
+
+
+def test_minsnap_population_against_c_oracle(d2d):
+    """C5's second population: randomised min-snap polynomials, POLY-specialised kernel, vs the C oracle."""
+    from oracle import c_oracle as co, d2d_oracle as orc
+    from d2d_b200 import simulation, trajectory
+    rng = np.random.default_rng(99)
+    B, dur = 300, 33.65
+    Y0 = np.zeros((B, 2, 4)); Y1 = np.zeros((B, 2, 4))
+    ang0, ang1 = rng.uniform(-0.5, 0.5, B), rng.uniform(1.0, 2.0, B)
+    Y0[:, 0, 0], Y0[:, 1, 0] = rng.uniform(-20, 20, B), rng.uniform(-20, 20, B)
+    Y0[:, 0, 1], Y0[:, 1, 1] = 10 * np.cos(ang0), 10 * np.sin(ang0)
+    Y1[:, 0, 0], Y1[:, 1, 0] = Y0[:, 0, 0] + rng.uniform(150, 250, B), Y0[:, 1, 0] + rng.uniform(150, 250, B)
+    Y1[:, 0, 1], Y1[:, 1, 1] = 10 * np.cos(ang1), 10 * np.sin(ang1)
+    batch = trajectory.MinSnapBatch.from_boundaries(Y0, Y1, dur)
+    # the vectorised coefficient solve agrees with the per-object one
+    one = trajectory.MinSnapPoly(Y0[0], Y1[0], dur)
+    np.testing.assert_allclose(batch.coefs0[0, 0], one._polys[0].coefs[0], rtol=1e-12, atol=1e-18)
+    wind = rng.normal(0, 1.5, (B, 2))
+    time = np.arange(0, 20., 0.01)
+    par = np.zeros((B, 17)); par[:, 1:9] = batch.coefs0[:, 0]; par[:, 9:17] = batch.coefs0[:, 1]
+    X0 = np.zeros((B, 5))
+    for b in range(B):
+        ms = orc.MinSnap(Y0[b], Y1[b], dur)
+        for c in range(2):
+            ms._polys[c].coefs[0] = batch.coefs0[b, c]
+            for d in range(1, 4):
+                for pw in range(8 - d):
+                    ms._polys[c].coefs[d, pw] = orc._arr(d, pw + d) * batch.coefs0[b, c, pw + d]
+        X0[b] = orc.flatness(ms.get(0.), wind[b])[0]
+    X0 += rng.normal(0, 1, (B, 5)) * np.array([3, 3, 0.1, 0.02, 0.3])
+    res = simulation.rollout(time, batch, wind, X0, log_every=10)
+    ref = co.rollout(time, np.full(B, co.T_POLY, np.int32), par, wind, X0, log_every=10)
+    assert ref["failed"] == 0 and not res.flags.any()
+    ok = ref["max_err"] < 10.
+    assert ok.sum() > 0.8 * B
+    err = np.abs(res.X[ok] - ref["X"][ok]).max()
+    print("min-snap population: max |dX| =", err, "over", int(ok.sum()), "scenarios")
+    assert err < TOL
