@@ -285,7 +285,7 @@ struct CareState { double C, S, al, dth, dal; };   // solution of the previous c
 
 struct CareConst { double sq, q3, sr1, sr2, isr1, isr2; };
 
-__device__ __forceinline__ CareConst care_const(const d2dx_dfff_gains& g) {
+__host__ __device__ __forceinline__ CareConst care_const(const d2dx_dfff_gains& g) {
   CareConst c;
   c.sq = ::sqrt(g.q_pos); c.q3 = g.q_psi; c.sr1 = ::sqrt(g.r_phi); c.sr2 = ::sqrt(g.r_v);
   c.isr1 = 1.0 / c.sr1; c.isr2 = 1.0 / c.sr2;

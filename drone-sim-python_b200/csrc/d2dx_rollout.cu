@@ -15,6 +15,7 @@ struct RolloutArgs {
   d2dx_scenarios s;
   d2dx_rollout_out o;
   d2dx_dfff_gains g;
+  CareConst cc;               // sqrt(Q), sqrt(R), ... computed on the host: read from the constant bank, not held in registers
   const double* time;
   int i_begin, i_end, nsub, final_control;
 };
@@ -42,7 +43,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 
 template <int UNIFORM, bool LOGGING, bool LOGREF>
 __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) rollout_dfff_kernel(const RolloutArgs a) {
-  __shared__ __align__(128) double spar[D2DX_SEG_NPAR][kRolloutThreads];
+  // rows 0..NPAR-1: trajectory parameters; rows NPAR..NPAR+4: wind x, wind y, -1/tau_phi, -1/tau_v, tau_v
+  __shared__ __align__(128) double spar[D2DX_SEG_NPAR + 5][kRolloutThreads];
   __shared__ __align__(8) uint64_t bar;
   const int B = a.s.B;
   const int tid = threadIdx.x;
@@ -76,15 +78,21 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
   }
   auto P = [&](int k) { return spar[k][tid]; };
 
-  const double tau_phi = a.s.ac[b], tau_v = a.s.ac[B + b];
-  AcPar ap;
-  ap.wx = a.s.wind[b]; ap.wy = a.s.wind[B + b];
-  ap.n_inv_tau_phi = -1.0 / tau_phi; ap.n_inv_tau_v = -1.0 / tau_v;
+  spar[D2DX_SEG_NPAR + 0][tid] = a.s.wind[b]; spar[D2DX_SEG_NPAR + 1][tid] = a.s.wind[B + b];
+  spar[D2DX_SEG_NPAR + 2][tid] = -1.0 / a.s.ac[b]; spar[D2DX_SEG_NPAR + 3][tid] = -1.0 / a.s.ac[B + b];
+  spar[D2DX_SEG_NPAR + 4][tid] = a.s.ac[B + b];
+  // re-read from shared memory at each use: five doubles less to keep in registers across the time loop
+  auto load_ac = [&]() {
+    AcPar ap;
+    ap.wx = spar[D2DX_SEG_NPAR + 0][tid]; ap.wy = spar[D2DX_SEG_NPAR + 1][tid];
+    ap.n_inv_tau_phi = spar[D2DX_SEG_NPAR + 2][tid]; ap.n_inv_tau_v = spar[D2DX_SEG_NPAR + 3][tid];
+    return ap;
+  };
   double X[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) X[k] = a.s.X0[(size_t)k * B + b];
 
-  const CareConst cc = care_const(a.g);
+  const CareConst& cc = a.cc;
   CareState cs = {0.0, 1.0, 1.0, 0.0, 0.0};
   bool cold = true;
   if (a.o.care_state) {
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
       }
       segment_eval<false>(seg_type, P, te, Y);
     }
-    make_ref(Y, ap, tau_v, cc, cs, cold, flags, r);
+    make_ref(Y, load_ac(), spar[D2DX_SEG_NPAR + 4][tid], cc, cs, cold, flags, r);
   };
 
   const int log_every = a.o.log_every > 0 ? a.o.log_every : 1;
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
     // (computing the next reference here, one step ahead and interleaved with the RK4 stages, was tried in round 1:
     //  the extra live state pushed the kernel over 128 registers and it ran 7 % slower)
     const double t1 = a.time[i + 1];
-    rk4_step(ap, X, u_phi, u_v, t1 - t, a.nsub);
+    rk4_step(load_ac(), X, u_phi, u_v, t1 - t, a.nsub);
     t = t1;
     if (i + 1 == ev_next) {            // perturbation event (05_test_simulation.py:32)
 #pragma unroll
@@ -216,6 +224,7 @@ extern "C" int d2dx_rollout_dfff(d2dx_handle* h, const d2dx_scenarios* s, const 
   a.s = *s; a.o = *out; a.time = time;
   a.i_begin = i_begin; a.i_end = i_end; a.nsub = nsub; a.final_control = final_control;
   if (gains_host) a.g = *gains_host; else d2dx_dfff_default_gains(&a.g);
+  a.cc = care_const(a.g);
   D2DX_CHECK_ARG(a.g.q_pos > 0 && a.g.q_psi > 0 && a.g.r_phi > 0 && a.g.r_v > 0, "d2dx_rollout_dfff: Q, R must be positive");
   D2DX_CUDA(cudaSetDevice(h->device));
   const bool logging = out->X_log || out->U_log || out->Xr_log || out->K_log;
