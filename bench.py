@@ -27,7 +27,7 @@ METRIC = "closed-loop aircraft-steps/s"
 UNIT = "aircraft-steps/s"
 # Executed fp64 flop per aircraft-step of rollout_dfff_kernel<CIRCLE> (DADD + DMUL + 2 x DFMA thread-instructions
 # from the ncu capture under profiles/, divided by scenarios x steps); see DESIGN.md "Roofline accounting".
-FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "749"))
+FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "746"))
 LOG_BYTES_PER_LOGGED_SAMPLE = 56          # 5 state + 2 input doubles
 
 

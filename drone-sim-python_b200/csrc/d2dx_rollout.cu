@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
     double u_phi, u_v;
     feedback(ref, X, a.g, u_phi, u_v);
     const double ex = X[0] - ref.xr, ey = X[1] - ref.yr, d2 = ex * ex + ey * ey;
-    sum_sq += d2; max_sq = fmax(max_sq, d2);
+    sum_sq += d2; max_sq = d2 > max_sq ? d2 : max_sq;
     if (LOGGING && active && (i % log_every) == 0) {
       const size_t row = (size_t)(i / log_every);
       if (a.o.X_log) {
