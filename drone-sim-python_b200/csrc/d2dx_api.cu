@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads) traj_eval_kernel(const d2dx_traj_tab
   const int seg = composite_locate(tt, b, time[it], te);
   auto P = [&](int k) { return tt.seg_par[(size_t)k * S + seg]; };
   FlatOut o;
-  segment_eval<true>(tt.seg_type[seg], P, te, o);
+  segment_eval<true>(tt.seg_type[seg], P, te, o, &tt);
   double* y = Y + (size_t)it * 8 * B + b;
   y[0] = o.y0x; y[(size_t)B] = o.y0y; y[2 * (size_t)B] = o.y1x; y[3 * (size_t)B] = o.y1y;
   y[4 * (size_t)B] = o.y2x; y[5 * (size_t)B] = o.y2y; y[6 * (size_t)B] = o.y3x; y[7 * (size_t)B] = o.y3y;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kThreads) dfff_control_kernel(const d2dx_traj_
   const int seg = composite_locate(tt, b, t, te);
   auto P = [&](int k) { return tt.seg_par[(size_t)k * S + seg]; };
   FlatOut Y;
-  segment_eval<false>(tt.seg_type[seg], P, te, Y);
+  segment_eval<false>(tt.seg_type[seg], P, te, Y, &tt);
   const AcPar a = load_ac(W, ac, B, b);
   double x[5];
   for (int k = 0; k < 5; ++k) x[k] = X[(size_t)k * B + b];

@@ -83,9 +83,18 @@ __device__ __forceinline__ double poly_row(LD c0, double t) {
 
 // One trajectory segment evaluated at time t.  `P(k)` returns parameter slot k (include/d2dx.h).
 template <bool WANT3, typename LD>
-__device__ __forceinline__ void segment_eval(int type, LD P, double t, FlatOut& Y) {
+__device__ __forceinline__ void segment_eval(int type, LD P, double t, FlatOut& Y, const d2dx_traj_table* tt = nullptr) {
   Y.y2x = Y.y2y = Y.y3x = Y.y3y = 0.0;
   switch (type) {
+    case D2DX_SEG_TABLE: {           // TrajTabulated.get, d2d/trajectory_factory.py:162-171
+      const int first = (int)P(1), n = (int)P(2);
+      const double* tm = tt->tab_time + first;
+      int lo = 0, hi = n;            // np.argmin(t > sol_time): first row with sol_time >= t, 0 when there is none
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (t > tm[mid]) lo = mid + 1; else hi = mid; }
+      const int idx = first + (lo < n ? lo : 0);
+      Y.y0x = tt->tab_x[idx]; Y.y0y = tt->tab_y[idx];
+      Y.y1x = tt->tab_vx[idx]; Y.y1y = tt->tab_vy[idx];
+    } break;
     case D2DX_SEG_LINE: {            // TrajectoryLine.get, d2d/trajectory.py:136-141
       const double dt = t - P(0);
       Y.y1x = P(3); Y.y1y = P(4);

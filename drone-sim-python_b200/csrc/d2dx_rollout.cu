@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
         cur_seg = seg; seg_type = tt.seg_type[seg];
         for (int k = 0; k < D2DX_SEG_NPAR; ++k) spar[k][tid] = tt.seg_par[(size_t)k * S + seg];
       }
-      segment_eval<false>(seg_type, P, te, Y);
+      segment_eval<false>(seg_type, P, te, Y, &tt);
     }
     make_ref(Y, load_ac(), spar[D2DX_SEG_NPAR + 4][tid], cc, cs, cold, flags, r);
   };

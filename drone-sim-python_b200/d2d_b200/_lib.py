@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("D2DX_LIB") or os.path.join(_HERE, "libd2dx.so")     # D2DX_LIB: A/B builds of the same ABI
 
-SEG_LINE, SEG_CIRCLE, SEG_SLALOM, SEG_POLY, SEG_SI_LINE = range(5)
+SEG_LINE, SEG_CIRCLE, SEG_SLALOM, SEG_POLY, SEG_SI_LINE, SEG_TABLE = range(6)
 SEG_NPAR = 17
 JAC_COMPACT, JAC_OPTY_DENSE = 0, 1
 EVAL_RESIDUAL, EVAL_JAC, EVAL_COST, EVAL_GRAD = 1, 2, 4, 8
@@ -21,7 +21,8 @@ c_dp = C.c_void_p      # device pointers travel as integers
 class TrajTable(C.Structure):
     _fields_ = [("n_traj", C.c_int32), ("n_seg", C.c_int32),
                 ("first_seg", c_dp), ("n_segs", c_dp), ("traj_t0", c_dp), ("traj_dur", c_dp),
-                ("seg_type", c_dp), ("seg_end", c_dp), ("seg_par", c_dp), ("uniform_type", C.c_int32)]
+                ("seg_type", c_dp), ("seg_end", c_dp), ("seg_par", c_dp), ("uniform_type", C.c_int32),
+                ("n_tab", C.c_int32), ("tab_time", c_dp), ("tab_x", c_dp), ("tab_y", c_dp), ("tab_vx", c_dp), ("tab_vy", c_dp)]
 
 
 class DfffGains(C.Structure):

@@ -19,7 +19,7 @@ def _ptr(t):
 class PackedTrajectories:
     """Host-side (NumPy) trajectory table in the layout of d2dx_traj_table."""
 
-    def __init__(self, first_seg, n_segs, traj_t0, traj_dur, seg_type, seg_end, seg_par, uniform_type=-1):
+    def __init__(self, first_seg, n_segs, traj_t0, traj_dur, seg_type, seg_end, seg_par, uniform_type=-1, tables=None):
         self.first_seg = np.ascontiguousarray(first_seg, np.int32)
         self.n_segs = np.ascontiguousarray(n_segs, np.int32)
         self.traj_t0 = np.ascontiguousarray(traj_t0, np.float64)
@@ -28,6 +28,8 @@ class PackedTrajectories:
         self.seg_end = np.ascontiguousarray(seg_end, np.float64)
         self.seg_par = np.ascontiguousarray(seg_par, np.float64)
         self.uniform_type = int(uniform_type)
+        # (5, n_tab) rows time, x, y, vx, vy of the D2DX_SEG_TABLE segments, or None
+        self.tables = None if tables is None else np.ascontiguousarray(tables, np.float64)
         assert self.seg_par.shape == (_lib.SEG_NPAR, len(self.seg_type))
 
     @property
@@ -51,6 +53,12 @@ class DeviceTable:
         self.c = _lib.TrajTable(packed.n_traj, packed.n_seg, *[_ptr(self.t[k]) for k in
                                 ("first_seg", "n_segs", "traj_t0", "traj_dur", "seg_type", "seg_end", "seg_par")],
                                 packed.uniform_type)
+        if packed.tables is not None:
+            self.tab = eng.to_device(packed.tables, non_blocking)
+            n = packed.tables.shape[1]
+            base, es = self.tab.data_ptr(), 8 * n
+            self.c.n_tab = n
+            self.c.tab_time, self.c.tab_x, self.c.tab_y, self.c.tab_vx, self.c.tab_vy = (base + k * es for k in range(5))
 
 
 class Engine:

@@ -270,8 +270,14 @@ def pack(trajs):
     if hasattr(trajs, "pack"):
         return trajs.pack()
     first, nseg, t0s, durs, types, ends, pars = [], [], [], [], [], [], []
+    tables, n_rows = [], 0
     for tr in trajs:
         segs = tr.segments()
+        for ty, p in segs:
+            if ty == _lib.SEG_TABLE:                     # p[1] is filled with the trajectory's first row in the shared tables
+                tab = tr.table()
+                p[1], p[2] = n_rows, tab.shape[1]
+                tables.append(tab); n_rows += tab.shape[1]
         first.append(len(types)); nseg.append(len(segs))
         if tr.is_composite():
             t0s.append(float(tr.t0)); durs.append(float(tr.duration))
@@ -284,4 +290,5 @@ def pack(trajs):
     par = np.stack(pars, axis=1)
     plain = all(d == 0. for d in durs) and all(n == 1 for n in nseg)
     uniform = types[0] if plain and len(set(types)) == 1 else -1
-    return PackedTrajectories(first, nseg, t0s, durs, types, ends, par, uniform)
+    return PackedTrajectories(first, nseg, t0s, durs, types, ends, par, uniform,
+                              tables=np.concatenate(tables, axis=1) if tables else None)

@@ -108,6 +108,29 @@ class TrajSiDemo(ddt.SpaceIndexedTraj):                      # :177-185
         super().__init__(ddt.TrajectoryLine([0, 20], [100, 20], v=100), dynamic)
 
 
+@register
+class TrajTabulated(ddt.Trajectory):                         # d2d/trajectory_factory.py:149-171
+    """Zero-order lookup of a planner solution (.npz with the keys of Planner.save_solution, 06_optyplan.py:135-139):
+    position of the first stored sample at or after t, ground velocity v (cos psi, sin psi) + wind, no higher derivatives."""
+    name, desc = "tabulated", "tabulated"
+    extends = (-5, 25, -10, 20)
+
+    def __init__(self, filename="./optyplan_exp0.npz"):
+        d = np.load(filename)
+        self.sol_time, self.sol_x, self.sol_y, self.sol_psi, self.sol_phi, self.sol_v, self.wind = \
+            [d[k] for k in ("sol_time", "sol_x", "sol_y", "sol_psi", "sol_phi", "sol_v", "wind")]
+        self.t0 = 0.
+        self.duration = self.sol_time[-1]
+
+    def table(self):
+        vx = self.sol_v * np.cos(self.sol_psi) + self.wind[:, 0]
+        vy = self.sol_v * np.sin(self.sol_psi) + self.wind[:, 1]
+        return np.stack([self.sol_time, self.sol_x, self.sol_y, vx, vy]).astype(np.float64)
+
+    def segments(self):
+        return [(_lib.SEG_TABLE, np.zeros(_lib.SEG_NPAR))]
+
+
 def print_available():
     print("Available trajectories:")
     for i, n in enumerate(list_available()):

@@ -53,8 +53,11 @@ enum {
   D2DX_SEG_CIRCLE = 1,  /* par: 0 t0 | 1 cx 2 cy | 3 r | 4 omega=v/r | 5 alpha0                   */
   D2DX_SEG_SLALOM = 2,  /* par: 0 t0 | 1 p1x 2 p1y | 3 (un*v)x 4 (un*v)y | 5 phase                */
   D2DX_SEG_POLY = 3,    /* par: 0 t0 | 1..8 x coefs[0][0..7] | 9..16 y coefs[0][0..7]             */
-  D2DX_SEG_SI_LINE = 4  /* par: 0 t0(unused) | 1 p1x 2 p1y 3 (un*v)x 4 (un*v)y (geometry, t0=0)
+  D2DX_SEG_SI_LINE = 4, /* par: 0 t0(unused) | 1 p1x 2 p1y 3 (un*v)x 4 (un*v)y (geometry, t0=0)
                                 | 5..12 lambda coefs[0][0..7]                                    */
+  D2DX_SEG_TABLE = 5    /* par: 0 t0(unused) | 1 first row in the tab_* arrays | 2 number of rows:
+                           TrajTabulated, d2d/trajectory_factory.py:149-171 (zero-order lookup of a
+                           planner solution: row = first sample time >= t, row 0 past the end)       */
 };
 #define D2DX_SEG_NPAR 17
 
@@ -71,6 +74,14 @@ typedef struct {
   const double* seg_par;     /* [D2DX_SEG_NPAR][S]                                               */
   int32_t uniform_type;      /* >= 0: every trajectory is ONE plain segment of this type and
                                 first_seg[b] == b (selects a specialised kernel); -1: mixed    */
+  /* sample tables of D2DX_SEG_TABLE segments (all NULL when there is none): time, x, y and the
+   * ground velocity v cos(psi) + wx, v sin(psi) + wy of each stored sample                        */
+  int32_t n_tab;
+  const double* tab_time;    /* [n_tab] */
+  const double* tab_x;       /* [n_tab] */
+  const double* tab_y;       /* [n_tab] */
+  const double* tab_vx;      /* [n_tab] */
+  const double* tab_vy;      /* [n_tab] */
 } d2dx_traj_table;
 
 /* Trajectory.get(t) for every trajectory and every t: Y[nT][8][B], row 2*k+c = k-th derivative of

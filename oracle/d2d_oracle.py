@@ -205,6 +205,22 @@ class SpaceIndexed:
         return Y
 
 
+class Tabulated:
+    """TrajTabulated, d2d/trajectory_factory.py:149-171: zero-order lookup of a planner solution."""
+    def __init__(self, sol_time, sol_x, sol_y, sol_psi, sol_v, wind):
+        self.sol_time, self.sol_x, self.sol_y, self.sol_psi, self.sol_v, self.wind = sol_time, sol_x, sol_y, sol_psi, sol_v, wind
+        self.t0 = 0.
+        self.duration = sol_time[-1]
+
+    def get(self, t):
+        Y = np.zeros((4, 2))
+        idx = np.argmin(t > self.sol_time)
+        Y[0] = self.sol_x[idx], self.sol_y[idx]
+        (wx, wy), v, psi = self.wind[idx], self.sol_v[idx], self.sol_psi[idx]
+        Y[1] = v * np.cos(psi) + wx, v * np.sin(psi) + wy
+        return Y
+
+
 # named trajectories, d2d/trajectory_factory.py
 def traj_two_lines():                                    # :29-37
     s1 = Line([0, 0], [50, 50], v=10., t0=0.)

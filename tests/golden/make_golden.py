@@ -498,14 +498,39 @@ def golden_colloc():
         print(f"  defect {fn}: N={len(tt)} h={hh:.3f} max={defects[fn]:.3e}")
 
 
+def golden_tabulated(sim):
+    """TrajTabulated (d2d/trajectory_factory.py:149-171) on two planner solutions shipped with the reference,
+    tracked by the DFFF controller: the hand-over from path B's output to path A's input (SURVEY 8f #3)."""
+    import io, contextlib
+    use_rk4(1)
+    out = {}
+    for tag, fn in (("exp0", "optyplan_exp0.npz"), ("exp13", "optyplan_exp13 - some traj.npz")):
+        path = os.path.join(REF, "src", "cache", fn)
+        with contextlib.redirect_stdout(io.StringIO()):
+            traj = ddtf.TrajTabulated(path)
+        d = np.load(path)
+        for k in ("sol_time", "sol_x", "sol_y", "sol_psi", "sol_phi", "sol_v", "wind"):
+            out[f"{tag}/{k}"] = d[k]
+        time = np.arange(0., traj.duration + 0.5, 0.01)          # runs past the end: exercises the wrap to row 0
+        wind = ddg.WindField([0.5, -0.3])
+        ac = ddyn.Aircraft()
+        X0 = ddg.DiffFlatness.state_and_input_from_output(traj.get(0.), wind.sample(0, None), ac)[0] + np.array([1., -2., 0.1, 0., 0.3])
+        X, U, Yref, Xref, K = run_dfff(sim, time, traj, wind, X0, np.zeros((len(time), 5)))
+        out[f"{tag}/X"] = X[::5]; out[f"{tag}/U"] = U[::5]; out[f"{tag}/Yref"] = Yref[::7]; out[f"{tag}/X0"] = X0
+        out[f"{tag}/T"] = np.array(len(time)); out[f"{tag}/Xlast"] = X[-1]
+        print(f"tabulated {tag}: {len(d['sol_time'])} rows, T={len(time)}, X[-1]={X[-1]}")
+    np.savez_compressed(os.path.join(HERE, "tabulated.npz"), **out)
+
+
 def main():
-    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc"]
+    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc", "tab"]
     sim = load_script("05_test_simulation.py", "ref05")
     if "c1" in what: golden_c1(sim)
     if "scen" in what: golden_scenarios(sim)
     if "units" in what: golden_units()
     if "form" in what: golden_formation()
     if "colloc" in what: golden_colloc()
+    if "tab" in what: golden_tabulated(sim)
 
 
 if __name__ == "__main__":

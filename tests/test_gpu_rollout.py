@@ -297,3 +297,21 @@ def test_minsnap_population_against_c_oracle(d2d):
     err = np.abs(res.X[ok] - ref["X"][ok]).max()
     print("min-snap population: max |dX| =", err, "over", int(ok.sum()), "scenarios")
     assert err < TOL
+
+
+@pytest.mark.parametrize("tag", ["exp0", "exp13"])
+def test_tabulated_trajectory_against_reference_golden(d2d, golden, tag, tmp_path):
+    """TrajTabulated (planner solution -> tracker reference, SURVEY 8f #3) on solutions shipped with the reference."""
+    from d2d_b200 import simulation, trajectory_factory as ddtf
+    g = golden["tabulated"]
+    fn = tmp_path / "plan.npz"
+    np.savez(fn, **{k: g[f"{tag}/{k}"] for k in ("sol_time", "sol_x", "sol_y", "sol_psi", "sol_phi", "sol_v", "wind")})
+    traj = ddtf.TrajTabulated(str(fn))
+    time = np.arange(0., traj.duration + 0.5, 0.01)
+    assert len(time) == int(g[f"{tag}/T"])
+    np.testing.assert_array_equal(traj.get_many(time[::7]), g[f"{tag}/Yref"])
+    other = ddtf.TrajCircle()                                # a mixed batch: tabulated next to an analytic trajectory
+    res = simulation.rollout(time, [other, traj], [0.5, -0.3], np.stack([np.array([60., 30., 1.5, 0., 10.]), g[f"{tag}/X0"]]))
+    np.testing.assert_allclose(res.X[1][::5], g[f"{tag}/X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.U[1][::5], g[f"{tag}/U"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(res.X_final[1], g[f"{tag}/Xlast"], rtol=0, atol=TOL)

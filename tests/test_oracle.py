@@ -225,3 +225,16 @@ def test_collision_all_pairs_gradient_is_exact_derivative():
 def test_sorted_inputs_12(golden):
     names = [str(s) for s in golden["colloc"]["sorted_inputs_12"]]
     assert names[:4] == ["phi0(t)", "phi1(t)", "phi10(t)", "phi11(t)"]
+
+
+@pytest.mark.parametrize("tag", ["exp0", "exp13"])
+def test_tabulated_trajectory(golden, tag):
+    g = golden["tabulated"]
+    tr = orc.Tabulated(g[f"{tag}/sol_time"], g[f"{tag}/sol_x"], g[f"{tag}/sol_y"], g[f"{tag}/sol_psi"], g[f"{tag}/sol_v"], g[f"{tag}/wind"])
+    T = int(g[f"{tag}/T"])
+    time = np.arange(0., tr.duration + 0.5, 0.01)
+    assert len(time) == T
+    np.testing.assert_array_equal(np.array([tr.get(t) for t in time[::7]]), g[f"{tag}/Yref"])
+    n = 401
+    X, U, _, _, _ = orc.run_simulation(time[:n], tr, [0.5, -0.3], g[f"{tag}/X0"])
+    np.testing.assert_allclose(X[::5], g[f"{tag}/X"][:len(X[::5])], rtol=0, atol=1e-10)
