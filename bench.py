@@ -27,7 +27,11 @@ METRIC = "closed-loop aircraft-steps/s"
 UNIT = "aircraft-steps/s"
 # Executed fp64 flop per aircraft-step of rollout_dfff_kernel<CIRCLE> (DADD + DMUL + 2 x DFMA thread-instructions
 # from the ncu capture under profiles/, divided by scenarios x steps); see DESIGN.md "Roofline accounting".
-FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "746"))
+FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "742"))
+# From the same capture (profiles/r1_final_rollout_dfff_circle.md, one launch of 1e6 scenarios x 1000 steps, log x100):
+# dram__bytes_read.sum + dram__bytes_write.sum, and the fp64 pipe's active fraction.
+NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 188.53e6 + 616.63e6
+NCU_FP64_PIPE_ACTIVE = 0.727
 LOG_BYTES_PER_LOGGED_SAMPLE = 56          # 5 state + 2 input doubles
 
 
@@ -326,7 +330,9 @@ def main():
     roofline = {"bound": "fp64", "kernel": "rollout_dfff_kernel<CIRCLE>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / peak_tf, "peak_source": "DFMA probe kernel timed in this run (MEASURED_PEAKS.json has no fp64 figure); nominal 37.2",
                 "flop_per_aircraft_step": FP64_FLOP_PER_STEP, "kernel_ms": kernel_ms, "steps_per_launch": steps_per_launch,
-                "traffic": None,
+                "traffic": NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH if (B, T_steps, args.log_every, args.chunks) == (10 ** 6, 10 ** 4, 100, 10) else None,
+                "traffic_note": "ncu dram bytes of one launch at the default sizes (profiles/r1_final_rollout_dfff_circle.md); algorithmic bytes = log_bytes_per_launch",
+                "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE, "log_bytes_per_launch": log_bytes,
                 "hbm": {"achieved_gbs": log_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak or 6650.0,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if hbm_peak else "fallback"}}
     cpu = None
