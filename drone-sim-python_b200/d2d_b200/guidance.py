@@ -104,7 +104,6 @@ class CircleTraj:
         e = np.asarray(((px - self.c[0]) ** 2 + (py - self.c[1]) ** 2) - r ** 2)
         n = np.asarray([2 * (px - self.c[0]), 2 * (py - self.c[1])])
         H = np.asarray([[2, 0], [0, 2]])
-        self._last_r = r
         return e, n, H
 
 
@@ -115,16 +114,13 @@ class GVFcontroller:
         self.traj, self.ac, self.wind = traj, ac, wind
 
     def get(self, X, ke, kd, e, n, H):
-        # (e, n) define the circle for this state: c = p - n/2, r^2 = |n/2|^2 - e
+        """(e, n) as returned by CircleTraj.get(X, r): they fix the circle for this state, c = p - n/2 and
+        r^2 = |n/2|^2 - e, which is what the device function takes.  H is the constant 2I of the circle."""
         eng = get_engine()
         X = np.asarray(X, dtype=np.float64).reshape(5)
         n = np.asarray(n, dtype=np.float64).reshape(2)
         c = X[:2] - n / 2
-        if self.traj is not None and hasattr(self.traj, "c"):
-            c = np.asarray(self.traj.c, dtype=np.float64).reshape(2)
-        r = np.sqrt(float(np.sum(np.square(n / 2)) - float(np.asarray(e).reshape(-1)[0])))
-        if self.traj is not None and hasattr(self.traj, "_last_r"):
-            r = float(np.asarray(self.traj._last_r).reshape(-1)[0])
+        r = np.sqrt(max(float(np.sum(np.square(n / 2))) - float(np.asarray(e).reshape(-1)[0]), 0.))
         out = eng.gvf(eng.to_device(X.reshape(5, 1)), eng.to_device(c.reshape(2, 1)), eng.to_device(np.array([r])), ke, kd)
         U, U1, U2 = out.cpu().numpy()[:, 0]
         return U, U1, U2
