@@ -3,7 +3,6 @@
 // SoA logs written with coalesced stores.  Replaces run_simulation (05_test_simulation.py:21-34).
 #include "d2dx_device.cuh"
 #include "d2dx_host.h"
-#include <stdlib.h>
 
 namespace d2dx {
 
@@ -191,194 +190,6 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Warp-specialised variant for uniform populations.  DFFFController.get splits into a state-INDEPENDENT half (trajectory,
-// flatness, linearisation, Riccati gain: `make_ref`) and a state-dependent half (`feedback`) followed by the RK4 step.
-// Here the two halves run in different warps of one block: producer warp p+4 computes the reference/gain of sample i+1
-// for 32 scenarios while consumer warp p integrates sample i of the same scenarios; a two-slot ring in shared memory
-// and four mbarriers per warp pair (full / empty per slot) hand the 13 doubles over.  Each role holds only its own
-// state in registers (producer: Riccati warm start; consumer: aircraft state), so more warps fit per SM.
-constexpr int kWsScen = 128;                  // scenarios per block
-constexpr int kWsThreads = 2 * kWsScen;
-constexpr int kRefWords = 13;                 // xr, yr, psir, phir, var, uphi, uv, k[6]
-#ifndef D2DX_WS_MIN_BLOCKS
-#define D2DX_WS_MIN_BLOCKS 3
-#endif
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))) : "memory");
-}
-
-template <int UNIFORM, bool LOGGING, bool LOGREF>
-__global__ void __launch_bounds__(kWsThreads, D2DX_WS_MIN_BLOCKS) rollout_dfff_ws_kernel(const RolloutArgs a) {
-  constexpr int kRows = (UNIFORM == D2DX_SEG_CIRCLE) ? 6 : (UNIFORM == D2DX_SEG_LINE) ? 5 : D2DX_SEG_NPAR;
-  __shared__ __align__(128) double spar[kRows + 5][kWsScen];   // trajectory parameters, then wind x/y, -1/tau_phi, -1/tau_v, tau_v
-  __shared__ __align__(128) double ring[2][kRefWords][kWsScen];
-  __shared__ __align__(8) uint64_t bar_full[4][2], bar_empty[4][2], bar_tma;
-  const int B = a.s.B;
-  const int tid = threadIdx.x;
-  const int col = tid & (kWsScen - 1);          // scenario column of this thread (same for the two roles)
-  const bool producer = tid >= kWsScen;
-  const int pair = col >> 5;
-  const int b_raw = blockIdx.x * kWsScen + col;
-  const bool active = b_raw < B;
-  const int b = active ? b_raw : B - 1;
-  const d2dx_traj_table& tt = a.s.traj;
-  const int S = tt.n_seg;
-
-  {   // stage parameters (TMA bulk rows when the tile is full), per-scenario constants, barriers
-    const int b0 = blockIdx.x * kWsScen;
-    const bool bulk = (b0 + kWsScen <= S) && ((S & 1) == 0);
-    if (tid == 0) {
-      mbar_init(&bar_tma, 1);
-      for (int p = 0; p < 4; ++p) for (int k = 0; k < 2; ++k) { mbar_init(&bar_full[p][k], 32); mbar_init(&bar_empty[p][k], 32); }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (bulk) {
-      if (tid == 0) {
-        mbar_expect_tx(&bar_tma, kRows * kWsScen * 8);
-        for (int k = 0; k < kRows; ++k) tma_load_1d(&spar[k][0], tt.seg_par + (size_t)k * S + b0, kWsScen * 8, &bar_tma);
-      }
-      mbar_wait(&bar_tma, 0);
-    } else if (!producer) {
-      for (int k = 0; k < kRows; ++k) spar[k][col] = tt.seg_par[(size_t)k * S + b];
-    }
-    if (!producer) {
-      spar[kRows + 0][col] = a.s.wind[b]; spar[kRows + 1][col] = a.s.wind[B + b];
-      spar[kRows + 2][col] = -1.0 / a.s.ac[b]; spar[kRows + 3][col] = -1.0 / a.s.ac[B + b];
-      spar[kRows + 4][col] = a.s.ac[B + b];
-    }
-    __syncthreads();
-  }
-  auto P = [&](int k) { return spar[k][col]; };
-  auto load_ac = [&]() {
-    AcPar ap;
-    ap.wx = spar[kRows + 0][col]; ap.wy = spar[kRows + 1][col];
-    ap.n_inv_tau_phi = spar[kRows + 2][col]; ap.n_inv_tau_v = spar[kRows + 3][col];
-    return ap;
-  };
-  const int log_every = a.o.log_every > 0 ? a.o.log_every : 1;
-  const int n_samples = a.i_end - a.i_begin + (a.final_control ? 1 : 0);
-
-  if (producer) {
-    // ---------------- reference + gain, one sample ahead of the consumer ----------------
-    CareState cs = {0.0, 1.0, 1.0, 0.0, 0.0};
-    bool cold = true;
-    if (a.o.care_state) {
-      cs.C = a.o.care_state[b]; cs.S = a.o.care_state[B + b]; cs.al = a.o.care_state[2 * (size_t)B + b];
-      cs.dth = a.o.care_state[3 * (size_t)B + b]; cs.dal = a.o.care_state[4 * (size_t)B + b];
-      cold = !(cs.al > 0.0);
-    }
-    int flags = 0;
-    for (int n = 0; n < n_samples; ++n) {
-      const int slot = n & 1;
-      if (n >= 2) mbar_wait(&bar_empty[pair][slot], ((n >> 1) - 1) & 1);      // consumer has drained this slot
-      FlatOut Y;
-      segment_eval<false>(UNIFORM, P, a.time[a.i_begin + n], Y);
-      RefCtl r;
-      make_ref(Y, load_ac(), spar[kRows + 4][col], a.cc, cs, cold, flags, r);
-      double* q = &ring[slot][0][col];
-      q[0 * kWsScen] = r.xr; q[1 * kWsScen] = r.yr; q[2 * kWsScen] = r.psir; q[5 * kWsScen] = r.uphi; q[6 * kWsScen] = r.uv;
-      if (LOGREF) { q[3 * kWsScen] = r.phir; q[4 * kWsScen] = r.var; }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) q[(7 + k) * kWsScen] = r.k[k];
-      mbar_arrive(&bar_full[pair][slot]);
-    }
-    if (active) {
-      if (a.o.flags && flags) atomicOr(&a.o.flags[b], flags);
-      if (a.o.care_state) {
-        a.o.care_state[b] = cs.C; a.o.care_state[B + b] = cs.S; a.o.care_state[2 * (size_t)B + b] = cold ? 0.0 : cs.al;
-        a.o.care_state[3 * (size_t)B + b] = cs.dth; a.o.care_state[4 * (size_t)B + b] = cs.dal;
-      }
-    }
-    return;
-  }
-
-  // ---------------- consumer: feedback, logging, RK4, perturbations ----------------
-  double X[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) X[k] = a.s.X0[(size_t)k * B + b];
-  double sum_sq = 0.0, max_sq = 0.0;
-  int ev = 0, ev_end = 0, ev_next = 0x7fffffff;
-  if (a.s.pert_begin) {
-    ev = a.s.pert_begin[b]; ev_end = a.s.pert_begin[b + 1];
-    while (ev < ev_end && a.s.pert_step[ev] <= a.i_begin) ++ev;
-    if (ev < ev_end) ev_next = a.s.pert_step[ev];
-  }
-  double t = a.time[a.i_begin];
-  for (int n = 0; n < n_samples; ++n) {
-    const int i = a.i_begin + n, slot = n & 1;
-    mbar_wait(&bar_full[pair][slot], (n >> 1) & 1);
-    RefCtl ref;
-    const double* q = &ring[slot][0][col];
-    ref.xr = q[0 * kWsScen]; ref.yr = q[1 * kWsScen]; ref.psir = q[2 * kWsScen]; ref.uphi = q[5 * kWsScen]; ref.uv = q[6 * kWsScen];
-    if (LOGREF) { ref.phir = q[3 * kWsScen]; ref.var = q[4 * kWsScen]; }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) ref.k[k] = q[(7 + k) * kWsScen];
-    mbar_arrive(&bar_empty[pair][slot]);
-    double u_phi, u_v;
-    feedback(ref, X, a.g, u_phi, u_v);
-    const double ex = X[0] - ref.xr, ey = X[1] - ref.yr, d2 = ex * ex + ey * ey;
-    sum_sq += d2; max_sq = d2 > max_sq ? d2 : max_sq;
-    if (LOGGING && active && (i % log_every) == 0) {
-      const size_t row = (size_t)(i / log_every);
-      if (a.o.X_log) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) a.o.X_log[(row * 5 + k) * B + b] = X[k];
-      }
-      if (a.o.U_log) { a.o.U_log[(row * 2) * B + b] = u_phi; a.o.U_log[(row * 2 + 1) * B + b] = u_v; }
-      if (LOGREF && a.o.Xr_log) {
-        double* w = a.o.Xr_log + row * 5 * B + b;
-        w[0] = ref.xr; w[(size_t)B] = ref.yr; w[2 * (size_t)B] = ref.psir; w[3 * (size_t)B] = ref.phir; w[4 * (size_t)B] = ref.var;
-      }
-      if (LOGREF && a.o.K_log) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) a.o.K_log[(row * 6 + k) * B + b] = ref.k[k];
-      }
-    }
-    if (i == a.i_end) break;
-    const double t1 = a.time[i + 1];
-    rk4_step(load_ac(), X, u_phi, u_v, t1 - t, a.nsub);
-    t = t1;
-    if (i + 1 == ev_next) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) X[k] += a.s.pert_dx[(size_t)k * a.s.n_events + ev];
-      ++ev;
-      ev_next = ev < ev_end ? a.s.pert_step[ev] : 0x7fffffff;
-    }
-  }
-  int flags = isfinite(X[0] + X[1] + X[2] + X[3] + X[4]) ? 0 : 1;
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) a.o.X_final[(size_t)k * B + b] = X[k];
-    if (a.o.sum_sq_err) a.o.sum_sq_err[b] += sum_sq;
-    if (a.o.max_err) a.o.max_err[b] = fmax(a.o.max_err[b], sqrt(max_sq));
-    if (a.o.flags && flags) atomicOr(&a.o.flags[b], flags);
-  }
-  if (a.o.pop_stats) {
-    const double ws = warp_sum(active ? sum_sq : 0.0);
-    const double wm = warp_max(active ? sqrt(max_sq) : 0.0);
-    if ((tid & 31) == 0) { atomicAdd(a.o.pop_stats, ws); atomic_max_double(a.o.pop_stats + 1, wm); }
-  }
-}
-
-static bool use_warp_specialised() {
-  static const int on = [] { const char* e = getenv("D2DX_ROLLOUT_WS"); return e ? atoi(e) : 0; }();
-  return on != 0;
-}
-
-template <int UNIFORM>
-static int launch_rollout_ws(const RolloutArgs& a, bool logging, cudaStream_t st) {
-  const int grid = (a.s.B + kWsScen - 1) / kWsScen;
-  const bool logref = a.o.Xr_log || a.o.K_log;
-  if (logref) rollout_dfff_ws_kernel<UNIFORM, true, true><<<grid, kWsThreads, 0, st>>>(a);
-  else if (logging) rollout_dfff_ws_kernel<UNIFORM, true, false><<<grid, kWsThreads, 0, st>>>(a);
-  else rollout_dfff_ws_kernel<UNIFORM, false, false><<<grid, kWsThreads, 0, st>>>(a);
-  D2DX_LAUNCH_CHECK("rollout_dfff_ws_kernel");
-  return D2DX_OK;
-}
-
 template <int UNIFORM>
 static int launch_rollout(const RolloutArgs& a, bool logging, cudaStream_t st) {
   const int grid = (a.s.B + kRolloutThreads - 1) / kRolloutThreads;
@@ -418,7 +229,6 @@ extern "C" int d2dx_rollout_dfff(d2dx_handle* h, const d2dx_scenarios* s, const 
   D2DX_CUDA(cudaSetDevice(h->device));
   const bool logging = out->X_log || out->U_log || out->Xr_log || out->K_log;
   cudaStream_t st = as_stream(stream);
-  if (use_warp_specialised() && s->traj.uniform_type == D2DX_SEG_CIRCLE) return launch_rollout_ws<D2DX_SEG_CIRCLE>(a, logging, st);
   switch (s->traj.uniform_type) {
     case D2DX_SEG_CIRCLE: return launch_rollout<D2DX_SEG_CIRCLE>(a, logging, st);
     case D2DX_SEG_POLY: return launch_rollout<D2DX_SEG_POLY>(a, logging, st);
