@@ -336,14 +336,14 @@ def main():
                 "hbm": {"achieved_gbs": log_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak or 6650.0,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if hbm_peak else "fallback"}}
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:               # reported baseline: rank 0 at N = 1 only
         from oracle import c_oracle as co
         cores = co.max_threads()
         rate, cores, sample, _ = cpu_port_run(512 * cores, min(1000, T_steps), args.seed)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "python_port_1core": python_port_rate()}
     secondary = None
-    if not args.no_secondary:
+    if not args.no_secondary and world == 1:
         try:
             secondary = secondary_metrics(eng, hbm_peak or 6650.0)
         except Exception as e:                          # never lose the headline line over a side metric
