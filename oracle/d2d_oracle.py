@@ -480,6 +480,87 @@ def run_formation(c, r, n_ac, t_end, ke, kd, kr, z_des, dt=0.05, nsub=5, X1=None
 
 
 # ---------------------------------------------------------------------------
+# 5-state LQR tracker on sampled references  (Controllers.py:50-186, 10_opt_traj_tracking.py:18-90)
+# ---------------------------------------------------------------------------
+def compute_derivatives(x_ref, y_ref, dt):
+    """ComputeDerivatives, 10_opt_traj_tracking.py:18-25."""
+    Fdx = np.gradient(x_ref, edge_order=2) / dt
+    Fddx = np.gradient(Fdx, edge_order=2) / dt
+    Fdy = np.gradient(y_ref, edge_order=2) / dt
+    Fddy = np.gradient(Fdy, edge_order=2) / dt
+    return Fdx, Fdy, Fddx, Fddy
+
+
+def flatness5(Y, Yd, Ydd, Yddd, w, tau_phi=TAU_PHI, tau_v=TAU_V, g=G):
+    """DiffFlatness.ComputeFlatness, Controllers.py:62-108, formulas as written (note c1's first product
+    v_ax*v_ax_dot and the cancelling c2 terms, :95-96)."""
+    X, U = np.zeros(5), np.zeros(2)
+    v_ax, v_ay = Yd[0] - w[0], Yd[1] - w[1]
+    v2 = v_ax ** 2 + v_ay ** 2
+    v_ax_dot, v_ay_dot = Ydd[0], Ydd[1]
+    v_ax_ddot, v_ay_ddot = Yddd[0], Yddd[1]
+    X[0], X[1] = Y[0], Y[1]
+    X[2] = np.arctan2(v_ay, v_ax)
+    X[3] = np.arctan2((v_ax * v_ay_dot - v_ay * v_ax_dot), g * np.sqrt(v2))
+    X[4] = np.sqrt(v2)
+    va_dot = (v_ax * v_ax_dot + v_ay * v_ay_dot) / np.sqrt(v2)
+    c1 = 1 + ((v_ax * v_ax_dot - v_ax_dot * v_ay) ** 2) / v2
+    c2 = v_ax * v_ay_ddot + v_ax_dot * v_ay_dot - v_ax_ddot * v_ay - v_ax_dot * v_ay_dot
+    c3 = (v_ax * v_ax_dot + v_ay * v_ay_dot) * (v_ax * v_ay_dot - v_ax_dot * v_ay)
+    phi_dot = (1 / c1) * (1 / v2) * (c2 * np.sqrt(v2) - c3 / np.sqrt(v2))
+    U[0] = tau_phi * phi_dot + X[3]
+    U[1] = tau_v * va_dot + X[4]
+    return X, U
+
+
+def cont_jac_5(Xr, tau_phi=TAU_PHI, tau_v=TAU_V, g=G):
+    """Aircraft.cont_jac in full, d2d/dynamic.py:32-43."""
+    psi, phi, va = Xr[2], Xr[3], Xr[4]
+    spsi, cpsi = np.sin(psi), np.cos(psi)
+    cphi2, tan_phi = np.cos(phi) ** 2, np.tan(phi)
+    A = np.array([[0., 0., -va * spsi, 0., cpsi],
+                  [0., 0., va * cpsi, 0., spsi],
+                  [0., 0., 0., g / va / (1 + cphi2), g / va ** 2 * tan_phi],
+                  [0., 0., 0., -1 / tau_phi, 0],
+                  [0., 0., 0., 0., -1 / tau_v]])
+    B = np.array([[0, 0], [0, 0], [0, 0], [1 / tau_phi, 0], [0, 1 / tau_v]])
+    return A, B
+
+
+_Q5, _PHI_LIM5 = np.diag([1, 1, 0.1, 0.01, 0.01]), np.deg2rad(60)        # Controllers.py:149,152
+
+
+def tracker_gain(X, Y, Yd, Ydd, Yddd, w, tau_phi=TAU_PHI, tau_v=TAU_V):
+    """DiffController.ComputeGain, Controllers.py:159-186 -> Xr, dX, U, K (2x5)."""
+    Xr, Ur = flatness5(Y, Yd, Ydd, Yddd, w, tau_phi, tau_v)
+    dX = X - Xr
+    dX[2] = (dX[2] + np.pi) % (2 * np.pi) - np.pi
+    dX[3] = (dX[3] + np.pi) % (2 * np.pi) - np.pi
+    dX = np.clip(dX, -_ERR_SATS, _ERR_SATS)
+    A, B = cont_jac_5(Xr, tau_phi, tau_v)
+    K = lqr(A, B, _Q5, _R)
+    U = np.clip(Ur - K @ dX, [-_PHI_LIM5, 4], [_PHI_LIM5, 20])
+    return Xr, dX, U, K
+
+
+def run_tracker(time_opt, x_ref, y_ref, w, X0s, nsub=10, tau_phi=TAU_PHI, tau_v=TAU_V):
+    """implement_controller, 10_opt_traj_tracking.py:27-90, with rk4_step for LSODA.  x_ref, y_ref: (T, n_ac)."""
+    T, n_ac = x_ref.shape
+    dt = time_opt[1] - time_opt[0]
+    X = np.zeros((T, n_ac, 5)); U = np.zeros((T, n_ac, 2)); Xr_log = np.zeros((T, n_ac, 5)); dX_log = np.zeros((T, n_ac, 5))
+    K_log = np.zeros((T - 1, n_ac, 2, 5))
+    D = [compute_derivatives(x_ref[:, j], y_ref[:, j], dt) for j in range(n_ac)]
+    X[0] = np.asarray(X0s, float)
+    for i in range(1, T):
+        for j in range(n_ac):
+            Fdx, Fdy, Fddx, Fddy = D[j]
+            Xr, dX, Uc, K = tracker_gain(X[i - 1, j].copy(), [x_ref[i, j], y_ref[i, j]], [Fdx[i], Fdy[i]], [Fddx[i], Fddy[i]], [0, 0], w, tau_phi, tau_v)
+            X[i, j] = rk4_step(X[i - 1, j], Uc, w, dt, nsub, tau_phi, tau_v)
+            U[i - 1, j], dX_log[i - 1, j], Xr_log[i - 1, j], K_log[i - 1, j] = Uc, dX, Xr, K
+    return X, U, Xr_log, dX_log, K_log
+
+
+# ---------------------------------------------------------------------------
 # collocation  (d2d/opty_utils.py:38-50 EoM, backward Euler as opty's default)
 # ---------------------------------------------------------------------------
 def planner_timing(t0, t1, hz):

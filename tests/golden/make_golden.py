@@ -522,8 +522,55 @@ def golden_tabulated(sim):
     np.savez_compressed(os.path.join(HERE, "tabulated.npz"), **out)
 
 
+def golden_tracker():
+    """Controllers.DiffController (5-state LQR, Controllers.py:139-186) driven by implement_controller of
+    10_opt_traj_tracking.py:27-90 on two planner outputs shipped with the reference.  The script's own
+    loop is used unmodified; only Aircraft.disc_dyn is the fixed-step RK4 (nsub = 10: dt = 0.1 s, tau_phi = 0.01 s)."""
+    import pandas as pd
+    cwd = os.getcwd()
+    os.chdir(os.path.join(REF, "src"))
+    use_rk4(10)
+    try:
+        s10 = load_script("10_opt_traj_tracking.py", "ref10")       # runs its main() once on import (plots are stubbed)
+        import Controllers as ctl_mod
+        out = {}
+        X0s = ((0, 40, np.deg2rad(0), 0, 12), (25, 20, np.deg2rad(0), 0, 12), (25, -20, np.deg2rad(0), 0, 12), (0, -40, np.deg2rad(0), 0, 12))
+        for tag, fn, w in (("simple", "opt_states_simple_traj.csv", [0, 0]), ("opt", "opt_states.csv", [1.0, -0.5])):
+            df = pd.read_csv(fn)
+            # capture the gains: implement_controller creates its own DiffController, so record through the class
+            Ks = []
+            orig = ctl_mod.DiffController.ComputeGain
+
+            def rec(self, *a, _o=orig, **k):
+                r = _o(self, *a, **k); Ks.append(self.K[-1].copy()); return r
+            ctl_mod.DiffController.ComputeGain = rec
+            X, U, Xr, Yd, Ydd, t, dX = s10.implement_controller(4, df, 10, w, X0s)
+            ctl_mod.DiffController.ComputeGain = orig
+            out[f"{tag}/time"] = t; out[f"{tag}/wind"] = np.array(w, dtype=float); out[f"{tag}/X0s"] = np.array(X0s, dtype=float)
+            out[f"{tag}/x_ref"] = np.stack([df[f"x_{i+1}"].to_numpy() for i in range(4)], 1)
+            out[f"{tag}/y_ref"] = np.stack([df[f"y_{i+1}"].to_numpy() for i in range(4)], 1)
+            out[f"{tag}/X"] = X; out[f"{tag}/U"] = U; out[f"{tag}/Xr"] = Xr; out[f"{tag}/dX"] = dX
+            out[f"{tag}/Yd"] = Yd; out[f"{tag}/Ydd"] = Ydd
+            out[f"{tag}/K"] = np.array(Ks).reshape(len(t) - 1, 4, 2, 5)
+            print(f"tracker {tag}: T={len(t)} X[-1,0]={X[-1,0]} end-point miss of aircraft 1: "
+                  f"{np.hypot(X[-1,0,0]-df['x_1'].iloc[-1], X[-1,0,1]-df['y_1'].iloc[-1]):.3f} m")
+        # single calls of ComputeFlatness with a non-zero third derivative
+        rng = np.random.default_rng(5)
+        n = 32
+        Y = rng.normal(0, 1, (n, 4, 2)) * np.array([50., 8., 2., 0.5])[None, :, None]
+        W = rng.normal(0, 2, (n, 2))
+        Xr = np.zeros((n, 5)); Ur = np.zeros((n, 2))
+        for i in range(n):
+            Xr[i], Ur[i] = ctl_mod.DiffFlatness(list(W[i])).ComputeFlatness(0., Y[i, 0], Y[i, 1], Y[i, 2], Y[i, 3])
+        out["flat/Y"] = Y; out["flat/W"] = W; out["flat/Xr"] = Xr; out["flat/Ur"] = Ur
+        np.savez_compressed(os.path.join(HERE, "tracker.npz"), **out)
+    finally:
+        os.chdir(cwd)
+        use_rk4(1)
+
+
 def main():
-    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc", "tab"]
+    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc", "tab", "tracker"]
     sim = load_script("05_test_simulation.py", "ref05")
     if "c1" in what: golden_c1(sim)
     if "scen" in what: golden_scenarios(sim)
@@ -531,6 +578,7 @@ def main():
     if "form" in what: golden_formation()
     if "colloc" in what: golden_colloc()
     if "tab" in what: golden_tabulated(sim)
+    if "tracker" in what: golden_tracker()
 
 
 if __name__ == "__main__":

@@ -238,3 +238,24 @@ def test_tabulated_trajectory(golden, tag):
     n = 401
     X, U, _, _, _ = orc.run_simulation(time[:n], tr, [0.5, -0.3], g[f"{tag}/X0"])
     np.testing.assert_allclose(X[::5], g[f"{tag}/X"][:len(X[::5])], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("tag", ["simple", "opt"])
+def test_tracker_5state_lqr(golden, tag):
+    """Controllers.DiffController + implement_controller (SURVEY 8f #1) vs the unmodified reference."""
+    g = golden["tracker"]
+    X, U, Xr, dX, K = orc.run_tracker(g[f"{tag}/time"], g[f"{tag}/x_ref"], g[f"{tag}/y_ref"], g[f"{tag}/wind"], g[f"{tag}/X0s"])
+    np.testing.assert_allclose(X, g[f"{tag}/X"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(U, g[f"{tag}/U"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(Xr, g[f"{tag}/Xr"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(dX, g[f"{tag}/dX"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(K, g[f"{tag}/K"], rtol=1e-9, atol=1e-10)
+
+
+def test_flatness5_single_calls(golden):
+    g = golden["tracker"]
+    for i in range(len(g["flat/Y"])):
+        Y = g["flat/Y"][i]
+        Xr, Ur = orc.flatness5(Y[0], Y[1], Y[2], Y[3], g["flat/W"][i])
+        np.testing.assert_allclose(Xr, g["flat/Xr"][i], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(Ur, g["flat/Ur"][i], rtol=1e-12, atol=1e-13)
