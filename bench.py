@@ -177,6 +177,17 @@ def secondary_metrics(eng, hbm_peak):
     z = np.ones(n_ac - 1) * 2 * np.pi / n_ac
     Xf = eng.empty(5, M)
     dt = timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3)
+    # 5-state LQR tracker on sampled circle references: dt 0.1 s, RK4 nsub 10, T = 101 samples
+    M, T = eng.sm_count * 1024, 101
+    tt = np.arange(T) * 0.1
+    rr, vv = rng.uniform(30, 60, M), rng.uniform(10, 14, M)
+    om = vv / rr
+    al = om[None, :] * tt[:, None]
+    ref = np.stack([rr * np.cos(al), rr * np.sin(al), -vv * np.sin(al), vv * np.cos(al), -vv * om * np.cos(al), -vv * om * np.sin(al)], 1)
+    X0t = eng.to_device(np.ascontiguousarray(np.stack([rr + 1., 0 * rr - 1., 0 * rr + np.pi / 2, 0 * rr, vv], 0)))
+    refd, wz, act, Xft = eng.to_device(ref), eng.zeros(2, M), eng.to_device(np.stack([np.full(M, 0.01), np.full(M, 1.)])), eng.empty(5, M)
+    dtt = timed(lambda: eng.rollout_tracker(refd, X0t, wz, act, 0.1, 0, T - 1, 10, X_final=Xft), 3)
+    out["tracker_lqr5_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dtt, "rk4_substeps_per_s": M * (T - 1) * 10 / dtt, "aircraft": M, "ms_per_launch": dtt * 1e3}
     out["formation_c2_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dt, "rk4_substeps_per_s": M * (T - 1) * 5 / dt, "formations": F, "ms_per_launch": dt * 1e3}
     return out
 

@@ -41,6 +41,20 @@ class RolloutOut(C.Structure):
                 ("care_state", c_dp), ("pop_stats", c_dp)]
 
 
+class TrackerGains(C.Structure):
+    _fields_ = [("q", C.c_double * 5), ("r", C.c_double * 2), ("err_sat", C.c_double * 5),
+                ("u_lo", C.c_double * 2), ("u_hi", C.c_double * 2)]
+
+
+class Tracker(C.Structure):
+    _fields_ = [("M", C.c_int32), ("T", C.c_int32), ("ref", c_dp), ("X0", c_dp), ("wind", c_dp), ("ac", c_dp), ("dt", C.c_double)]
+
+
+class TrackerOut(C.Structure):
+    _fields_ = [("X_log", c_dp), ("U_log", c_dp), ("Xr_log", c_dp), ("dX_log", c_dp), ("K_log", c_dp), ("X_final", c_dp),
+                ("flags", c_dp), ("lqr_state", c_dp)]
+
+
 class Formations(C.Structure):
     _fields_ = [("F", C.c_int32), ("n_ac", C.c_int32), ("n_e", C.c_int32),
                 ("X0", c_dp), ("c", c_dp), ("r", c_dp), ("ac", c_dp),
@@ -91,6 +105,10 @@ def _load():
         "d2dx_dfff_default_gains": (C.c_int, [P(DfffGains)]),
         "d2dx_dfff_control": (C.c_int, [H, P(TrajTable), c_dp, dbl, c_dp, c_dp, P(DfffGains), c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_rollout_dfff": (C.c_int, [H, P(Scenarios), c_dp, i32, i32, i32, i32, P(DfffGains), P(RolloutOut), c_dp]),
+        "d2dx_tracker_default_gains": (C.c_int, [P(TrackerGains)]),
+        "d2dx_flatness5": (C.c_int, [H, i32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_tracker_control": (C.c_int, [H, i32, c_dp, c_dp, c_dp, c_dp, P(TrackerGains), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_rollout_tracker": (C.c_int, [H, P(Tracker), i32, i32, i32, P(TrackerGains), P(TrackerOut), c_dp]),
         "d2dx_dcf": (C.c_int, [H, i32, i32, i32, P(dbl), P(dbl), dbl, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_gvf": (C.c_int, [H, i32, c_dp, c_dp, c_dp, dbl, dbl, c_dp, c_dp]),
         "d2dx_rollout_formation": (C.c_int, [H, P(Formations), dbl, i32, i32, i32, P(FormationOut), c_dp]),

@@ -209,6 +209,32 @@ class Engine:
         self.launches += 1
         return X_final
 
+    # ---- 5-state LQR tracker ---------------------------------------------------------------------
+    def flatness5(self, Ys, W, ac):
+        n = Ys.shape[1]; Xr = self.empty(5, n); Ur = self.empty(2, n)
+        check(lib.d2dx_flatness5(self.h, n, _ptr(Ys), _ptr(W), _ptr(ac), _ptr(Xr), _ptr(Ur), self.stream_ptr()), "d2dx_flatness5")
+        self.launches += 1
+        return Xr, Ur
+
+    def tracker_control(self, X, Ys, W, ac, gains=None, lqr_state=None):
+        n = X.shape[1]; U = self.empty(2, n); Xr = self.empty(5, n); dX = self.empty(5, n); K = self.empty(10, n)
+        check(lib.d2dx_tracker_control(self.h, n, _ptr(X), _ptr(Ys), _ptr(W), _ptr(ac), C.byref(gains) if gains is not None else None,
+                                       _ptr(U), _ptr(Xr), _ptr(dX), _ptr(K), _ptr(lqr_state), self.stream_ptr()), "d2dx_tracker_control")
+        self.launches += 1
+        return U, Xr, dX, K
+
+    def rollout_tracker(self, ref, X0, wind, ac, dt, i_begin, i_end, nsub, gains=None, X_log=None, U_log=None, Xr_log=None,
+                        dX_log=None, K_log=None, X_final=None, flags=None, lqr_state=None):
+        T, _, M = ref.shape
+        if X_final is None:
+            X_final = self.empty(5, M)
+        t = _lib.Tracker(M, T, _ptr(ref), _ptr(X0), _ptr(wind), _ptr(ac), float(dt))
+        o = _lib.TrackerOut(_ptr(X_log), _ptr(U_log), _ptr(Xr_log), _ptr(dX_log), _ptr(K_log), _ptr(X_final), _ptr(flags), _ptr(lqr_state))
+        check(lib.d2dx_rollout_tracker(self.h, C.byref(t), int(i_begin), int(i_end), int(nsub),
+                                       C.byref(gains) if gains is not None else None, C.byref(o), self.stream_ptr()), "d2dx_rollout_tracker")
+        self.launches += 1
+        return X_final
+
     # ---- collocation -------------------------------------------------------------------------------
     def colloc_sizes(self, prob, layout=_lib.JAC_COMPACT):
         s = (C.c_int64 * 3)()

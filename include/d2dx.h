@@ -157,6 +157,48 @@ int d2dx_rollout_dfff(d2dx_handle* h, const d2dx_scenarios* s, const double* tim
                       int32_t i_end, int32_t nsub, int32_t final_control,
                       const d2dx_dfff_gains* gains_host, const d2dx_rollout_out* out, void* stream);
 
+/* -------- 5-state LQR tracker on sampled references --------
+ * Replaces Controllers.DiffFlatness.ComputeFlatness (Controllers.py:62-108), DiffController.ComputeGain (:159-186) and
+ * the loop of implement_controller (10_opt_traj_tracking.py:72-89): full-state LQR with Q = diag(q), R = diag(r) on the
+ * complete linearisation of d2d/dynamic.py:32-43, references given by samples of the flat output and its derivatives. */
+typedef struct {
+  double q[5];               /* reference: 1, 1, 0.1, 0.01, 0.01   (q[0] must equal q[1])                 */
+  double r[2];               /* reference: 8, 1                                                           */
+  double err_sat[5];         /* reference: 20, 20, pi/3, pi/4, 1                                          */
+  double u_lo[2], u_hi[2];   /* reference: (-60 deg, 4), (60 deg, 20)                                     */
+} d2dx_tracker_gains;
+int d2dx_tracker_default_gains(d2dx_tracker_gains* g_host);
+/* ComputeFlatness for n references: Ys[8][n] (rows as d2dx_traj_eval: Y, Yd, Ydd, Yddd) -> Xr[5][n], Ur[2][n] */
+int d2dx_flatness5(d2dx_handle* h, int32_t n, const double* Ys, const double* W, const double* ac, double* Xr,
+                   double* Ur, void* stream);
+/* ComputeGain for n aircraft: X[5][n], Ys[8][n] -> U[2][n]; optional Xr[5][n], dX[5][n], K[10][n] (row-major 2x5);
+ * lqr_state[7][n] (optional, in/out, zero-initialised) warm-starts the Riccati solve */
+int d2dx_tracker_control(d2dx_handle* h, int32_t n, const double* X, const double* Ys, const double* W,
+                         const double* ac, const d2dx_tracker_gains* gains_host, double* U, double* Xr, double* dX,
+                         double* K, double* lqr_state, void* stream);
+typedef struct {
+  int32_t M, T;              /* aircraft, reference samples                                                */
+  const double* ref;         /* [T][6][M]  x, y, xd, yd, xdd, ydd of each sample (third derivative = 0,
+                                          10_opt_traj_tracking.py:77)                                    */
+  const double* X0;          /* [5][M]                                                                    */
+  const double* wind;        /* [2][M]                                                                    */
+  const double* ac;          /* [2][M]  tau_phi, tau_v                                                    */
+  double dt;                 /* sample spacing (time_opt[1] - time_opt[0], :42)                           */
+} d2dx_tracker;
+typedef struct {
+  double* X_log;             /* [T][5][M] or NULL   row i = state at sample i                             */
+  double* U_log;             /* [T][2][M] or NULL   row i-1 = input applied from sample i-1 to i          */
+  double* Xr_log;            /* [T][5][M] or NULL   row i-1 (X_ref_array)                                  */
+  double* dX_log;            /* [T][5][M] or NULL   row i-1 (dX_array)                                     */
+  double* K_log;             /* [T][10][M] or NULL  row i-1                                                */
+  double* X_final;           /* [5][M]                                                                    */
+  int32_t* flags;            /* [M] or NULL  |= 1 non-finite state, 2 Riccati not converged               */
+  double* lqr_state;         /* [7][M] or NULL  warm start carried between calls                          */
+} d2dx_tracker_out;
+/* for i in (i_begin, i_end]: (Xr, dX, U) = ComputeGain(X[i-1], sample i); X[i] = rk4(X[i-1], U, dt, nsub) */
+int d2dx_rollout_tracker(d2dx_handle* h, const d2dx_tracker* in, int32_t i_begin, int32_t i_end, int32_t nsub,
+                         const d2dx_tracker_gains* gains_host, const d2dx_tracker_out* out, void* stream);
+
 /* -------- circular formation (DCF + GVF) -------- */
 /* DCFController.get, d2d/guidance.py:103-126, for F formations of n_ac aircraft.
  * p[2][F*n_ac], c[2][F*n_ac] (aircraft f*n_ac+j), Binc[n_ac][n_e] (host, row-major, shared by all
