@@ -167,6 +167,20 @@ def secondary_metrics(eng, hbm_peak):
         out[tag] = {**extra, "evals_per_s": n_prob / dt, "ms_per_launch": dt * 1e3, "aircraft_nodes_per_launch": n_ac * N * n_prob,
                     "roofline": {"bound": "hbm" if n_prob > 1 else "launch latency", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_alg / dt / 1e9 / hbm_peak}}
+    # CPU figure for the collocation path: the NumPy oracle (lambdified-EoM class of the survey) on one core, C3
+    try:
+        from oracle import d2d_oracle as orc
+        N3 = 1001
+        f3 = rng.normal(0, 3., 5 * N3) + 12. * (np.arange(5 * N3) >= 4 * N3)
+        t0 = _time.perf_counter()
+        reps = 50
+        for _ in range(reps):
+            orc.colloc_residual(f3, N3, 1, 0.02, (0., 0.), [(k, 0, 0.) for k in range(3)])
+            orc.colloc_jac_compact(f3, N3, 1, 0.02)
+            orc.cost_and_grad(f3, N3, 1, dict(vsp=12., kvel=1.))
+        out["c3_cpu_numpy_1core"] = {"evals_per_s": reps / (_time.perf_counter() - t0), "kind": "port", "cores": 1}
+    except Exception as e:
+        out["c3_cpu_numpy_1core"] = {"error": str(e)}
     # formation rollout, config C2 replicated: F formations of 6 aircraft, 1200 samples, dt 0.05, RK4 nsub 5
     from d2d_b200.simulation import chain_incidence
     n_ac, T = 6, 1200
@@ -177,18 +191,18 @@ def secondary_metrics(eng, hbm_peak):
     z = np.ones(n_ac - 1) * 2 * np.pi / n_ac
     Xf = eng.empty(5, M)
     dt = timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3)
+    out["formation_c2_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dt, "rk4_substeps_per_s": M * (T - 1) * 5 / dt, "formations": F, "ms_per_launch": dt * 1e3}
     # 5-state LQR tracker on sampled circle references: dt 0.1 s, RK4 nsub 10, T = 101 samples
-    M, T = eng.sm_count * 1024, 101
-    tt = np.arange(T) * 0.1
-    rr, vv = rng.uniform(30, 60, M), rng.uniform(10, 14, M)
+    Mt, Tt = eng.sm_count * 1024, 101
+    tt = np.arange(Tt) * 0.1
+    rr, vv = rng.uniform(30, 60, Mt), rng.uniform(10, 14, Mt)
     om = vv / rr
     al = om[None, :] * tt[:, None]
     ref = np.stack([rr * np.cos(al), rr * np.sin(al), -vv * np.sin(al), vv * np.cos(al), -vv * om * np.cos(al), -vv * om * np.sin(al)], 1)
     X0t = eng.to_device(np.ascontiguousarray(np.stack([rr + 1., 0 * rr - 1., 0 * rr + np.pi / 2, 0 * rr, vv], 0)))
-    refd, wz, act, Xft = eng.to_device(ref), eng.zeros(2, M), eng.to_device(np.stack([np.full(M, 0.01), np.full(M, 1.)])), eng.empty(5, M)
-    dtt = timed(lambda: eng.rollout_tracker(refd, X0t, wz, act, 0.1, 0, T - 1, 10, X_final=Xft), 3)
-    out["tracker_lqr5_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dtt, "rk4_substeps_per_s": M * (T - 1) * 10 / dtt, "aircraft": M, "ms_per_launch": dtt * 1e3}
-    out["formation_c2_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dt, "rk4_substeps_per_s": M * (T - 1) * 5 / dt, "formations": F, "ms_per_launch": dt * 1e3}
+    refd, wz, act, Xft = eng.to_device(ref), eng.zeros(2, Mt), eng.to_device(np.stack([np.full(Mt, 0.01), np.full(Mt, 1.)])), eng.empty(5, Mt)
+    dtt = timed(lambda: eng.rollout_tracker(refd, X0t, wz, act, 0.1, 0, Tt - 1, 10, X_final=Xft), 3)
+    out["tracker_lqr5_batch"] = {"aircraft_steps_per_s": Mt * (Tt - 1) / dtt, "rk4_substeps_per_s": Mt * (Tt - 1) * 10 / dtt, "aircraft": Mt, "ms_per_launch": dtt * 1e3}
     return out
 
 

@@ -31,7 +31,7 @@ __device__ __forceinline__ bool enabled(double k) { return (k == k) && k != 0.0;
 // EXTRA = obstacle and / or pairwise collision terms present (exp, shared-memory pair loop); the plain instantiation is
 // the lean HBM-bound path (residual + Jacobian + input cost + gradient) and is held to 64 registers for occupancy.
 template <bool EXTRA>
-__global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(const __grid_constant__ CollocArgs a) {
+__global__ void __launch_bounds__(kCollocThreads, EXTRA ? 5 : 8) colloc_kernel(const __grid_constant__ CollocArgs a) {
   extern __shared__ double spos[];                 // [n_total][2][TN] positions (+ two gradient accumulators of the same shape)
   const d2dx_colloc_problem& P = a.p;
   const int N = P.N, n_ac = P.n_ac, TN = a.TN;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
   const double ih = 1.0 / P.h;
   const double sN = P.obj_scale / N;               // _p.obj_scale/_p.num_nodes
   const double norm_in = sN / P.in_div;
-  const double col_kr = P.kcol_k / P.rcol;
+  const double col_kr = P.kcol_k / P.rcol;           // (k/r): one multiplication per pair component instead of dx / r * k
   double s_v = 0.0, s_phi = 0.0, s_obs = 0.0, s_col = 0.0;
 
   for (int a_l = al; a_l < n_ac; a_l += a.APP) {
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
           double es, f = 1.0;
           if (P.obs_kind == 0) es = clip(exp(r * r - (dx * dx + dy * dy)), 0.0, 1e3);
           else {
-            const double ux = dx / r * 2.0, uy = dy / r * 2.0;
+            const double kr = 2.0 / r, ux = dx * kr, uy = dy * kr;
             es = fm::exp_neg(-(ux * ux + uy * uy));
             if (P.exact_grad) f = (2.0 / r) * (2.0 / r);
           }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
         for (int b = b_lo; b < b_hi; ++b) {
           if (b == g_glob) continue;
           const double dx = x - spos[(b * 2) * TN + il], dy = y - spos[(b * 2 + 1) * TN + il];
-          const double ux = dx / P.rcol * P.kcol_k, uy = dy / P.rcol * P.kcol_k;
+          const double ux = dx * col_kr, uy = dy * col_kr;
           const double es = fm::exp_neg(-(ux * ux + uy * uy));
           if (g_glob < b) s_col += es;
           gx += P.kcol * (sN * -2.0 * dx * es) * f;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 4 : 8) colloc_kernel(c
           int b = a_l + k; if (b >= n) b -= n;
           const double dx = spos[(a_l * 2) * TN + il] - spos[(b * 2) * TN + il];
           const double dy = spos[(a_l * 2 + 1) * TN + il] - spos[(b * 2 + 1) * TN + il];
-          const double ux = dx / P.rcol * P.kcol_k, uy = dy / P.rcol * P.kcol_k;
+          const double ux = dx * col_kr, uy = dy * col_kr;
           const double es = fm::exp_neg(-(ux * ux + uy * uy));
           s_col += es;
           const double wx = P.kcol * (sN * -2.0 * dx * es) * f, wy = P.kcol * (sN * -2.0 * dy * es) * f;
