@@ -250,6 +250,7 @@ def main():
         print(json.dumps(line))
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner / debug lines must not share stdout with the JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
