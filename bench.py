@@ -250,7 +250,11 @@ def main():
         print(json.dumps(line))
         return
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner / debug lines must not share stdout with the JSON line
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner, ...) write to fd 1 directly, so fd 1 is pointed
+    # at stderr for the whole run and the JSON line goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -380,7 +384,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
             "checks": {"nonfinite_or_unconverged_scenarios": flags_bad, "population_rms_pos_err": float(np.sqrt(pop[0].item() / (B * world * (T_steps + 1)))),
                        "population_max_pos_err": float(pop[1].item())}}
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
