@@ -192,6 +192,25 @@ def secondary_metrics(eng, hbm_peak):
     Xf = eng.empty(5, M)
     dt = timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3)
     out["formation_c2_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dt, "rk4_substeps_per_s": M * (T - 1) * 5 / dt, "formations": F, "ms_per_launch": dt * 1e3}
+    # C5's second population: randomised min-snap polynomials, POLY-specialised rollout kernel, 2000 steps
+    from d2d_b200 import trajectory as ddt
+    from d2d_b200.simulation import MonteCarloRollout
+    Bp, Tp, dur = 500000, 2000, 33.65
+    Y0 = np.zeros((Bp, 2, 4)); Y1 = np.zeros((Bp, 2, 4))
+    a0, a1 = rng.uniform(-0.5, 0.5, Bp), rng.uniform(1.0, 2.0, Bp)
+    Y0[:, 0, 0], Y0[:, 1, 0] = rng.uniform(-20, 20, Bp), rng.uniform(-20, 20, Bp)
+    Y0[:, 0, 1], Y0[:, 1, 1] = 10 * np.cos(a0), 10 * np.sin(a0)
+    Y1[:, 0, 0], Y1[:, 1, 0] = Y0[:, 0, 0] + rng.uniform(150, 250, Bp), Y0[:, 1, 0] + rng.uniform(150, 250, Bp)
+    Y1[:, 0, 1], Y1[:, 1, 1] = 10 * np.cos(a1), 10 * np.sin(a1)
+    msb = ddt.MinSnapBatch.from_boundaries(Y0, Y1, dur)
+    mcp = MonteCarloRollout(Bp, np.arange(Tp + 1) * 0.01, _lib.SEG_POLY, log_every=100, n_chunks=2, host_log=False)
+    parp = np.zeros((_lib.SEG_NPAR, Bp)); parp[1:9] = msb.coefs0[:, 0].T; parp[9:17] = msb.coefs0[:, 1].T
+    X0p = np.stack([Y0[:, 0, 0] + 1., Y0[:, 1, 0] - 1., a0, 0 * a0, 0 * a0 + 10.], 1)
+    mcp.set_inputs(parp, np.zeros((Bp, 2)), X0p); mcp.upload()
+    dtp = timed(mcp.run_device, 3)
+    out["c5_minsnap_population"] = {"aircraft_steps_per_s": Bp * Tp / dtp, "scenarios": Bp, "steps": Tp, "ms_per_sweep": dtp * 1e3,
+                                    "unconverged_or_nonfinite": int(mcp.d_flags.ne(0).sum().item())}
+    del mcp
     # 5-state LQR tracker on sampled circle references: dt 0.1 s, RK4 nsub 10, T = 101 samples
     Mt, Tt = eng.sm_count * 1024, 101
     tt = np.arange(Tt) * 0.1
