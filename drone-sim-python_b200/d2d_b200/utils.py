@@ -1,0 +1,20 @@
+"""Small helpers of `d2d.utils` (d2d/utils.py:7-18) kept for import compatibility."""
+import numpy as np
+
+
+def norm_mpi_pi(v):
+    """Wrap an angle to [-pi, pi) with floored modulo (d2d/utils.py:7)."""
+    return (v + np.pi) % (2 * np.pi) - np.pi
+
+
+class WindField:
+    """Constant wind with the numeric / symbolic sampling names of d2d/utils.py:10-18."""
+
+    def __init__(self, w=[0., 0.]):
+        self.w = w
+
+    def sample_num(self, _x, _y, _t):
+        return self.w
+
+    def sample_sym(self, _x, _y, _t):
+        return self.w
