@@ -315,3 +315,37 @@ def test_tabulated_trajectory_against_reference_golden(d2d, golden, tag, tmp_pat
     np.testing.assert_allclose(res.X[1][::5], g[f"{tag}/X"], rtol=0, atol=TOL)
     np.testing.assert_allclose(res.U[1][::5], g[f"{tag}/U"], rtol=0, atol=TOL)
     np.testing.assert_allclose(res.X_final[1], g[f"{tag}/Xlast"], rtol=0, atol=TOL)
+
+
+def test_step_by_step_duck_typed_api_under_d2d_alias(d2d, golden):
+    """A caller written in the reference's style (`import d2d.dynamic as ddyn`, one controller call and one disc_dyn
+    call per step, as the loop body of 05_test_simulation.py:28-32) runs against the package aliased as `d2d`."""
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == "d2d" or k.startswith("d2d.")}
+    try:
+        for m in ("dynamic", "guidance", "trajectory", "trajectory_factory", "scenario", "utils", "opty_utils", "multiopty_utils"):
+            sys.modules[f"d2d.{m}"] = __import__(f"d2d_b200.{m}", fromlist=[m])
+        sys.modules["d2d"] = d2d
+        import d2d.dynamic as ddyn
+        import d2d.guidance as ddg
+        import d2d.trajectory as ddt
+        g = golden["dfff_c1"]
+        time = g["time"][:60]
+        traj, ac, wind = ddt.TrajectoryCircle(alpha0=3 * np.pi / 2), ddyn.Aircraft(), ddg.WindField([5, 0])
+        ctl = ddg.DFFFController(traj, ac, wind)
+        X, U = np.zeros((len(time), ddyn.Aircraft.s_size)), np.zeros((len(time), ddyn.Aircraft.i_size))
+        X[0] = g["X0"]
+        for i in range(1, len(time)):
+            U[i - 1] = ctl.get(X[i - 1], time[i - 1])
+            X[i] = ac.disc_dyn(X[i - 1], U[i - 1], wind, time[i - 1], time[i] - time[i - 1])
+        np.testing.assert_allclose(X, g["X"][:60], rtol=0, atol=TOL)
+        np.testing.assert_allclose(U[:-1], g["U"][:59], rtol=0, atol=TOL)
+        np.testing.assert_allclose(np.array(ctl.K), g["K"][:59], rtol=0, atol=TOL)
+        Yr = traj.get(0.5)
+        assert Yr.shape == (4, 2)
+        Xr, Ur, Xrd = ddg.DiffFlatness.state_and_input_from_output(Yr, wind.sample(0.5, Yr[0]), ac)
+        assert Xr.shape == (5,) and Ur.shape == (2,)
+    finally:
+        for k in [k for k in sys.modules if k == "d2d" or k.startswith("d2d.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
