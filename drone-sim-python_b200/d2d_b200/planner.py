@@ -139,6 +139,44 @@ class MultiPlanner(_PlannerBase):
         self.sol_psi, self.sol_v, self.sol_phi = [s[k] for k in self._slice_psi], [s[k] for k in self._slice_v], [s[k] for k in self._slice_phi]
 
 
+    def load_csv(self, filename):
+        """Reads a solution exported by save_csv / by 07_multioptyplan.py:476-489 into `self.solution`."""
+        import pandas as pd
+        df = pd.read_csv(filename)
+        N, n = self.num_nodes, self.acs.nb_aicraft
+        if len(df) != N:
+            raise ValueError(f"{filename}: {len(df)} rows for a {N}-node problem")
+        sol = np.zeros(5 * n * N)
+        for i in range(n):
+            sol[self._slice_x[i]], sol[self._slice_y[i]], sol[self._slice_psi[i]] = df[f"x_{i + 1}"], df[f"y_{i + 1}"], df[f"psi_{i + 1}"]
+            sol[self._slice_phi[i]], sol[self._slice_v[i]] = df[f"phi_{i + 1}"], df[f"v_{i + 1}"]
+        self.solution = sol
+        self.interpret_solution()
+
+    def save_csv(self, filename):
+        """time, x_i, y_i, psi_i, phi_i, v_i (1-based i) per node -- the export of 07_multioptyplan.py:476-489, the
+        input format of the tracker (10_opt_traj_tracking.py:30-38)."""
+        import pandas as pd
+        self.interpret_solution()
+        cols = {"time": self.sol_time}
+        for i in range(self.acs.nb_aicraft):
+            cols[f"x_{i + 1}"], cols[f"y_{i + 1}"], cols[f"psi_{i + 1}"] = self.sol_x[i], self.sol_y[i], self.sol_psi[i]
+            cols[f"phi_{i + 1}"], cols[f"v_{i + 1}"] = self.sol_phi[i], self.sol_v[i]
+        pd.DataFrame(cols).to_csv(filename, index=False)
+
+
+def compute_or_load(_p, force_recompute=False, filename="/tmp/optyplan.npz", tol=1e-5, max_iter=1500, initial_guess=None):
+    """Cache front end of 06_optyplan.py:152-164: loads a cached solution when there is one; computing a new one needs
+    an NLP solver driving `_p.prob` (outside the engine)."""
+    import os
+    if force_recompute or not os.path.exists(filename):
+        _p.configure(tol, max_iter)
+        _p.run(_p.get_initial_guess() if initial_guess is None else initial_guess)      # raises: no solver in the engine
+        _p.save_solution(filename)
+    else:
+        _p.load_solution(filename)
+
+
 class exp_0:
     """Single-aircraft experiment 0 (d2d/optyplan_scenarios.py:9-28); other experiments subclass and override."""
     ncases = 1
