@@ -35,8 +35,45 @@ class RolloutResult:
     pass
 
 
+def _family(tr):
+    """Kernel family of a trajectory: the segment type when a specialised rollout kernel exists for it, else -1."""
+    from . import _lib
+    if tr.is_composite():
+        return -1
+    segs = tr.segments()
+    return segs[0][0] if len(segs) == 1 and segs[0][0] in (_lib.SEG_CIRCLE, _lib.SEG_POLY, _lib.SEG_LINE) else -1
+
+
+def _rollout_by_family(time, trajs, wind, X0, perts, tau_phi, tau_v, fams, **kw):
+    """Mixed populations: one launch per trajectory family (warps stay homogeneous and the specialised kernels apply,
+    SURVEY section 7 "sort scenarios by type"), results scattered back to the caller's order."""
+    B = len(trajs)
+    wind = np.broadcast_to(np.asarray(wind, dtype=np.float64).reshape(-1, 2), (B, 2))
+    tp = np.broadcast_to(np.asarray(tau_phi, dtype=np.float64), (B,))
+    tv = np.broadcast_to(np.asarray(tau_v, dtype=np.float64), (B,))
+    parts = []
+    for fam in sorted(set(fams)):
+        idx = np.nonzero(np.asarray(fams) == fam)[0]
+        sub = rollout(time, [trajs[i] for i in idx], wind[idx], X0[idx], perts=None if perts is None else [perts[i] for i in idx],
+                      tau_phi=tp[idx], tau_v=tv[idx], group_by_family=False, **kw)
+        parts.append((idx, sub))
+    res = RolloutResult()
+    first = parts[0][1]
+    res.time_log = first.time_log
+    for name in ("X_final", "sum_sq_err", "max_err", "flags", "X", "U", "Xref", "K"):
+        if hasattr(first, name):
+            ref = getattr(first, name)
+            out = np.zeros((B,) + ref.shape[1:], dtype=ref.dtype)
+            for idx, sub in parts:
+                out[idx] = getattr(sub, name)
+            setattr(res, name, out)
+    res.pop_sum_sq_err = float(sum(sub.pop_sum_sq_err for _, sub in parts))
+    res.pop_max_err = float(max(sub.pop_max_err for _, sub in parts))
+    return res
+
+
 def rollout(time, trajs, wind, X0, perts=None, tau_phi=0.01, tau_v=1., nsub=1, log_every=1, log_ref=False,
-            final_control=True, gains=None, engine=None, chunk_steps=None, return_log=True):
+            final_control=True, gains=None, engine=None, chunk_steps=None, return_log=True, group_by_family=True):
     """Batched run_simulation (05_test_simulation.py:21-34) for B aircraft-scenarios.
 
     time   (T,) sample grid shared by all scenarios (np.arange as the reference builds it)
@@ -49,6 +86,11 @@ def rollout(time, trajs, wind, X0, perts=None, tau_phi=0.01, tau_v=1., nsub=1, l
     T = len(time)
     X0 = np.asarray(X0, dtype=np.float64).reshape(-1, 5)
     B = len(X0)
+    if group_by_family and isinstance(trajs, (list, tuple)) and B >= 256 and len(trajs) == B:
+        fams = [_family(tr) for tr in trajs]
+        if len(set(fams)) > 1:
+            return _rollout_by_family(time, trajs, wind, X0, perts, tau_phi, tau_v, fams, nsub=nsub, log_every=log_every, log_ref=log_ref,
+                                      final_control=final_control, gains=gains, engine=eng, chunk_steps=chunk_steps, return_log=return_log)
     packed = ddt.pack(trajs)
     if packed.n_traj != B:
         raise ValueError(f"{packed.n_traj} trajectories for {B} initial states")

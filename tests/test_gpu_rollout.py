@@ -349,3 +349,37 @@ def test_step_by_step_duck_typed_api_under_d2d_alias(d2d, golden):
         for k in [k for k in sys.modules if k == "d2d" or k.startswith("d2d.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_mixed_population_grouped_by_family_equals_generic_kernel(d2d):
+    """A mixed population is split into one launch per trajectory family (specialised kernels); the result equals the
+    single generic-kernel launch in the caller's order."""
+    from d2d_b200 import simulation, trajectory, trajectory_factory as ddtf
+    rng = np.random.default_rng(21)
+    trajs, X0 = [], []
+    for k in range(420):
+        kind = k % 4
+        if kind == 0:
+            tr = trajectory.TrajectoryCircle(c=[rng.uniform(-20, 20), rng.uniform(-20, 20)], r=rng.uniform(30, 60), v=rng.uniform(10, 12), alpha0=rng.uniform(0, 6))
+        elif kind == 1:
+            tr = trajectory.MinSnapPoly([[0, 10, 0, 0], [rng.uniform(-5, 5), 0, 0, 0]], [[200, 0, 0, 0], [200, 10, 0, 0]], duration=33.65)
+        elif kind == 2:
+            tr = trajectory.TrajectoryLine([0, rng.uniform(0, 30)], [100, 25], v=10.)
+        else:
+            tr = ddtf.TrajSquare()
+        trajs.append(tr)
+        X0.append([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(-0.3, 0.3), 0., 10.])
+    X0 = np.array(X0)
+    for b, tr in enumerate(trajs):
+        if isinstance(tr, trajectory.TrajectoryCircle):
+            X0[b, :2] += tr.c + np.array([tr.r * np.cos(tr.alpha0), tr.r * np.sin(tr.alpha0)]); X0[b, 2] += tr.alpha0 + np.pi / 2
+    time = np.arange(0, 3., 0.01)
+    wind = rng.normal(0, 1., (len(trajs), 2))
+    a = simulation.rollout(time, trajs, wind, X0, log_every=5, log_ref=True)
+    b = simulation.rollout(time, trajs, wind, X0, log_every=5, log_ref=True, group_by_family=False)
+    for name in ("X", "U", "Xref", "K", "X_final"):
+        np.testing.assert_allclose(getattr(a, name), getattr(b, name), rtol=0, atol=1e-12, err_msg=name)
+    for name in ("sum_sq_err", "max_err"):
+        np.testing.assert_allclose(getattr(a, name), getattr(b, name), rtol=1e-12, err_msg=name)
+    np.testing.assert_allclose(a.pop_sum_sq_err, b.pop_sum_sq_err, rtol=1e-12)
+    assert a.pop_max_err == b.pop_max_err and not a.flags.any()
