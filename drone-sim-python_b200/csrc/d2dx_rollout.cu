@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
   const int log_every = a.o.log_every > 0 ? a.o.log_every : 1;
   const int n_samples = a.i_end - a.i_begin + (a.final_control ? 1 : 0);
   double t = a.time[a.i_begin];
+  // samples until the next logged one (a countdown instead of an integer modulo per step)
+  int log_in = (log_every - a.i_begin % log_every) % log_every;
   for (int n = 0; n < n_samples; ++n) {
     const int i = a.i_begin + n;
     // ---- DFFFController.get: reference + gain (state-independent), then the state feedback ----
@@ -139,7 +141,9 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
     feedback(ref, X, a.g, u_phi, u_v);
     const double ex = X[0] - ref.xr, ey = X[1] - ref.yr, d2 = ex * ex + ey * ey;
     sum_sq += d2; max_sq = d2 > max_sq ? d2 : max_sq;
-    if (LOGGING && active && (i % log_every) == 0) {
+    const bool log_now = LOGGING && log_in == 0;
+    log_in = log_now ? log_every - 1 : log_in - 1;
+    if (log_now && active) {
       const size_t row = (size_t)(i / log_every);
       if (a.o.X_log) {
 #pragma unroll
