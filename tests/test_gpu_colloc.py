@@ -155,6 +155,16 @@ def test_opty_name_sorted_input_order(golden):
     for k, nm in enumerate(names):
         src = numeric.index(nm)
         np.testing.assert_array_equal(gb[(3 * n_ac + k) * N:(3 * n_ac + k + 1) * N], ga[(3 * n_ac + src) * N:(3 * n_ac + src + 1) * N])
+    # opty-dense layout under the same permutation (two problems in one launch: structural zeros laid down once per problem)
+    d = CollocationProblem(n_ac, N, h, cost=cs, input_order="opty", layout="dense")
+    jd = d.con_jac(np.stack([fp, fp]))
+    rd, cd = d.jacobianstructure()
+    rc, cc = b.jacobianstructure()
+    A = np.zeros((b.num_constraints, b.num_free)); A[rc, cc] = jb
+    for q in range(2):
+        Bm = np.zeros_like(A); np.add.at(Bm, (rd, cd), jd[q])
+        np.testing.assert_array_equal(A, Bm)
+    assert jd.shape[1] == (N - 1) * 3 * n_ac * 8 * n_ac and np.count_nonzero(jd[0]) <= 12 * n_ac * (N - 1)
 
 
 def test_sharded_evaluation_single_gpu_emulation(golden):
