@@ -535,7 +535,8 @@ def golden_tracker():
         import Controllers as ctl_mod
         out = {}
         X0s = ((0, 40, np.deg2rad(0), 0, 12), (25, 20, np.deg2rad(0), 0, 12), (25, -20, np.deg2rad(0), 0, 12), (0, -40, np.deg2rad(0), 0, 12))
-        for tag, fn, w in (("simple", "opt_states_simple_traj.csv", [0, 0]), ("opt", "opt_states.csv", [1.0, -0.5])):
+        for tag, fn, w in (("simple", "opt_states_simple_traj.csv", [0, 0]), ("opt", "opt_states.csv", [1.0, -0.5]),
+                           ("hf", "opt_states_hf.csv", [0, 0]), ("stline", "opt_states_st_line.csv", [0.5, 0.5]), ("inf", "inf_traj_10s.csv", [0, 0])):
             df = pd.read_csv(fn)
             # capture the gains: implement_controller creates its own DiffController, so record through the class
             Ks = []
@@ -544,14 +545,16 @@ def golden_tracker():
             def rec(self, *a, _o=orig, **k):
                 r = _o(self, *a, **k); Ks.append(self.K[-1].copy()); return r
             ctl_mod.DiffController.ComputeGain = rec
-            X, U, Xr, Yd, Ydd, t, dX = s10.implement_controller(4, df, 10, w, X0s)
+            X0s_run = X0s if tag in ("simple", "opt") else tuple((df[f"x_{i+1}"].iloc[0] + 1., df[f"y_{i+1}"].iloc[0] - 1., df[f"psi_{i+1}"].iloc[0], 0., 12.) for i in range(4))
+            X, U, Xr, Yd, Ydd, t, dX = s10.implement_controller(4, df, 10, w, X0s_run)
             ctl_mod.DiffController.ComputeGain = orig
-            out[f"{tag}/time"] = t; out[f"{tag}/wind"] = np.array(w, dtype=float); out[f"{tag}/X0s"] = np.array(X0s, dtype=float)
+            out[f"{tag}/time"] = t; out[f"{tag}/wind"] = np.array(w, dtype=float); out[f"{tag}/X0s"] = np.array(X0s_run, dtype=float)
             out[f"{tag}/x_ref"] = np.stack([df[f"x_{i+1}"].to_numpy() for i in range(4)], 1)
             out[f"{tag}/y_ref"] = np.stack([df[f"y_{i+1}"].to_numpy() for i in range(4)], 1)
-            out[f"{tag}/X"] = X; out[f"{tag}/U"] = U; out[f"{tag}/Xr"] = Xr; out[f"{tag}/dX"] = dX
-            out[f"{tag}/Yd"] = Yd; out[f"{tag}/Ydd"] = Ydd
-            out[f"{tag}/K"] = np.array(Ks).reshape(len(t) - 1, 4, 2, 5)
+            out[f"{tag}/X"] = X; out[f"{tag}/U"] = U
+            if tag in ("simple", "opt"):
+                out[f"{tag}/Xr"] = Xr; out[f"{tag}/dX"] = dX; out[f"{tag}/Yd"] = Yd; out[f"{tag}/Ydd"] = Ydd
+                out[f"{tag}/K"] = np.array(Ks).reshape(len(t) - 1, 4, 2, 5)
             print(f"tracker {tag}: T={len(t)} X[-1,0]={X[-1,0]} end-point miss of aircraft 1: "
                   f"{np.hypot(X[-1,0,0]-df['x_1'].iloc[-1], X[-1,0,1]-df['y_1'].iloc[-1]):.3f} m")
         # single calls of ComputeFlatness with a non-zero third derivative

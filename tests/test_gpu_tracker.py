@@ -24,6 +24,17 @@ def test_tracker_against_reference_golden(golden, tag):
     print(tag, "max |dX| =", np.abs(X - g[f"{tag}/X"]).max(), " max |dK| =", np.abs(K[:-1] - g[f"{tag}/K"]).max())
 
 
+@pytest.mark.parametrize("tag", ["hf", "stline", "inf"])
+def test_tracker_on_the_other_shipped_planner_outputs(golden, tag):
+    """opt_states_hf.csv, opt_states_st_line.csv and inf_traj_10s.csv (phase 3 of the full-mission scripts)."""
+    from d2d_b200 import controllers
+    g = golden["tracker"]
+    X, U, *_rest = controllers.track(g[f"{tag}/time"], g[f"{tag}/x_ref"], g[f"{tag}/y_ref"], g[f"{tag}/wind"], g[f"{tag}/X0s"])
+    assert not _rest[-1].any()
+    np.testing.assert_allclose(X, g[f"{tag}/X"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(U, g[f"{tag}/U"], rtol=0, atol=TOL)
+
+
 def test_tracker_drop_in_call_sequence(golden):
     """implement_controller(n_ac, df, v, w, X0s) with a DataFrame, and the single-call classes."""
     import pandas as pd

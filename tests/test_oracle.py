@@ -240,6 +240,14 @@ def test_tabulated_trajectory(golden, tag):
     np.testing.assert_allclose(X[::5], g[f"{tag}/X"][:len(X[::5])], rtol=0, atol=1e-10)
 
 
+@pytest.mark.parametrize("tag", ["hf", "stline", "inf"])
+def test_tracker_other_outputs(golden, tag):
+    g = golden["tracker"]
+    X, U, *_ = orc.run_tracker(g[f"{tag}/time"], g[f"{tag}/x_ref"], g[f"{tag}/y_ref"], g[f"{tag}/wind"], g[f"{tag}/X0s"])
+    np.testing.assert_allclose(X, g[f"{tag}/X"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(U, g[f"{tag}/U"], rtol=0, atol=1e-10)
+
+
 @pytest.mark.parametrize("tag", ["simple", "opt"])
 def test_tracker_5state_lqr(golden, tag):
     """Controllers.DiffController + implement_controller (SURVEY 8f #1) vs the unmodified reference."""
