@@ -383,3 +383,21 @@ def test_mixed_population_grouped_by_family_equals_generic_kernel(d2d):
         np.testing.assert_allclose(getattr(a, name), getattr(b, name), rtol=1e-12, err_msg=name)
     np.testing.assert_allclose(a.pop_sum_sq_err, b.pop_sum_sq_err, rtol=1e-12)
     assert a.pop_max_err == b.pop_max_err and not a.flags.any()
+
+
+@pytest.mark.parametrize("nsub,tau_phi,dt", [(3, 0.01, 0.01), (1, 0.9667, 0.02), (10, 0.01, 0.1)])
+def test_dfff_rollout_substeps_and_time_constants_against_oracle(d2d, nsub, tau_phi, dt):
+    """RK4 sub-stepping, other time constants and coarser control periods in the DFFF rollout (the fast stage-heading
+    path must hand over to the generic one when the increments grow)."""
+    from oracle import d2d_oracle as orc
+    from d2d_b200 import simulation, trajectory
+    time = np.arange(0, 150 * dt - 1e-9, dt)
+    specs = [dict(c=[30., 30.], r=30., v=10., alpha0=4.0), dict(c=[0., 0.], r=-25., v=12., alpha0=1.0)]
+    X0 = np.array([[12., 5., 1.0, 0.1, 9.], [-20., 18., -2.0, 0., 12.]])
+    wind = [1.5, -1.0]
+    res = simulation.rollout(time, [trajectory.TrajectoryCircle(**s) for s in specs], wind, X0, tau_phi=tau_phi, tau_v=1.3, nsub=nsub)
+    assert not res.flags.any()
+    for b, s in enumerate(specs):
+        Xo, Uo, _, _, _ = orc.run_simulation(time, orc.Circle(**s), wind, X0[b], nsub=nsub, tau_phi=tau_phi, tau_v=1.3)
+        np.testing.assert_allclose(res.X[b], Xo, rtol=0, atol=TOL)
+        np.testing.assert_allclose(res.U[b], Uo, rtol=0, atol=TOL)
