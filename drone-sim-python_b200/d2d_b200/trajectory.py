@@ -118,9 +118,8 @@ class PolynomialOne:
                 self.coefs[d, pw] = arr(d, pw + d) * self.coefs[0, pw + d]
 
     def get(self, t):
-        # evaluate lambda(t) rows through the SI segment with an identity-like geometry:
-        # geometry p1 = 0, un*v = (1, 0)  ->  Y[k,0] = lambda^(k)(t) for k >= 1; row 0 is clipped by the SI
-        # contract, so the value row comes from a plain POLY segment instead.
+        """Value and three derivatives at t -> (4,).  Evaluated on the device as the x component of a plain polynomial
+        segment whose y coefficients are zero."""
         eng = get_engine()
         par = np.zeros(_lib.SEG_NPAR)
         par[1:9] = self.coefs[0]
