@@ -83,3 +83,23 @@ def test_c3_batch_4096_properties(golden):
         fd_r = (pc.con(f0 + d) - pc.con(f0 - d)) / 2e-6
         col = np.zeros(pc.num_constraints); sel = cc == k; col[rc[sel]] = jac[7][sel]
         np.testing.assert_allclose(col, fd_r, rtol=0, atol=2e-5)
+
+
+def test_long_horizon_against_c_oracle():
+    """10^5 control steps (1000 s of flight, circle phases up to ~500 rad): no drift between the engine and the C oracle."""
+    from d2d_b200 import simulation, trajectory
+    from oracle import c_oracle as co
+    import bench
+    B, T = 64, 10 ** 5
+    w = bench.workload(B, 777)
+    w["r"] = np.clip(w["r"], 35., None)                 # keep the required bank below the 45 deg limit: trackable circles
+    X0 = bench.flat_state0(w) + w["noise"]
+    time = np.arange(T + 1) * 0.01
+    res = simulation.rollout(time, trajectory.CircleBatch(w["cx"], w["cy"], w["r"], w["v"], w["a0"]), w["wind"], X0, log_every=1000)
+    ty, par = co.circle_par(w["cx"], w["cy"], w["r"], w["v"], w["a0"])
+    ref = co.rollout(time, ty, par, w["wind"], X0, log_every=1000)
+    ok = ref["max_err"] < 10.
+    assert ok.sum() >= B // 2 and not res.flags.any()
+    err = np.abs(res.X[ok] - ref["X"][ok]).max()
+    print("long horizon: max |dX| =", err, "over", int(ok.sum()), "scenarios x 101 logged samples")
+    assert err < 1e-9
