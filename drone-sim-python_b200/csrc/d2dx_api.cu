@@ -72,6 +72,11 @@ __global__ void __launch_bounds__(kThreads) disc_dyn_kernel(int n, const double*
   for (int k = 0; k < 5; ++k) Xn[(size_t)k * n + i] = x[k];
 }
 
+__global__ void __launch_bounds__(kThreads) norm_mpi_pi_kernel(int n, const double* __restrict__ v, double* __restrict__ out) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i < n) out[i] = wrap_pi(v[i]);
+}
+
 // Aircraft.cont_jac, d2d/dynamic.py:32-43 (both "as written" entries kept)
 __global__ void __launch_bounds__(kThreads) cont_jac_kernel(int n, const double* __restrict__ Xr, const double* __restrict__ ac,
                                                              double* __restrict__ A, double* __restrict__ Bm) {
@@ -257,6 +262,14 @@ int d2dx_traj_eval(d2dx_handle* h, const d2dx_traj_table* tt, int32_t nT, const 
   D2DX_CUDA(cudaSetDevice(h->device));
   traj_eval_kernel<<<grid_for((long)tt->n_traj * nT), kThreads, 0, as_stream(stream)>>>(*tt, nT, time, Y);
   D2DX_LAUNCH_CHECK("traj_eval_kernel");
+  return D2DX_OK;
+}
+
+int d2dx_norm_mpi_pi(d2dx_handle* h, int32_t n, const double* v, double* out, void* stream) {
+  D2DX_CHECK_ARG(h && n > 0 && v && out, "d2dx_norm_mpi_pi: bad argument");
+  D2DX_CUDA(cudaSetDevice(h->device));
+  norm_mpi_pi_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, v, out);
+  D2DX_LAUNCH_CHECK("norm_mpi_pi_kernel");
   return D2DX_OK;
 }
 

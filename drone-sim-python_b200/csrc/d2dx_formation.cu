@@ -142,6 +142,15 @@ __global__ void __launch_bounds__(kFormThreads) gvf_kernel(int n, const double* 
   out[i] = U; out[(size_t)n + i] = U1; out[2 * (size_t)n + i] = U2;
 }
 
+__global__ void __launch_bounds__(kFormThreads) circle_implicit_kernel(int n, const double* __restrict__ X, const double* __restrict__ c,
+                                                                        const double* __restrict__ r, double* __restrict__ out) {
+  const int i = blockIdx.x * kFormThreads + threadIdx.x;
+  if (i >= n) return;
+  const double dx = X[i] - c[i], dy = X[(size_t)n + i] - c[(size_t)n + i];
+  out[i] = (dx * dx + dy * dy) - r[i] * r[i];             // e = |p - c|^2 - r^2   (d2d/guidance.py:140)
+  out[(size_t)n + i] = 2.0 * dx; out[2 * (size_t)n + i] = 2.0 * dy;   // n = grad e    (:144)
+}
+
 int formation_resident_threads_per_sm() {
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_formation_kernel, kFormThreads, 0);
@@ -188,6 +197,15 @@ extern "C" int d2dx_dcf(d2dx_handle* h, int32_t F, int32_t n_ac, int32_t n_e, co
   const long warps = ((long)F + a.fpw - 1) / a.fpw;
   dcf_kernel<<<(int)((warps * 32 + kFormThreads - 1) / kFormThreads), kFormThreads, 0, as_stream(stream)>>>(a);
   D2DX_LAUNCH_CHECK("dcf_kernel");
+  return D2DX_OK;
+}
+
+extern "C" int d2dx_circle_implicit(d2dx_handle* h, int32_t n, const double* X, const double* c, const double* r, double* out,
+                                    void* stream) {
+  D2DX_CHECK_ARG(h && n > 0 && X && c && r && out, "d2dx_circle_implicit: bad argument");
+  D2DX_CUDA(cudaSetDevice(h->device));
+  circle_implicit_kernel<<<(n + kFormThreads - 1) / kFormThreads, kFormThreads, 0, as_stream(stream)>>>(n, X, c, r, out);
+  D2DX_LAUNCH_CHECK("circle_implicit_kernel");
   return D2DX_OK;
 }
 

@@ -110,6 +110,8 @@ def _load():
         "d2dx_tracker_control": (C.c_int, [H, i32, c_dp, c_dp, c_dp, c_dp, P(TrackerGains), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_rollout_tracker": (C.c_int, [H, P(Tracker), i32, i32, i32, P(TrackerGains), P(TrackerOut), c_dp]),
         "d2dx_dcf": (C.c_int, [H, i32, i32, i32, P(dbl), P(dbl), dbl, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_norm_mpi_pi": (C.c_int, [H, i32, c_dp, c_dp, c_dp]),
+        "d2dx_circle_implicit": (C.c_int, [H, i32, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_gvf": (C.c_int, [H, i32, c_dp, c_dp, c_dp, dbl, dbl, c_dp, c_dp]),
         "d2dx_rollout_formation": (C.c_int, [H, P(Formations), dbl, i32, i32, i32, P(FormationOut), c_dp]),
         "d2dx_colloc_sizes": (C.c_int, [P(CollocProblem), i32, P(i64)]),

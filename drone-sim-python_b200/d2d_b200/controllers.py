@@ -52,7 +52,8 @@ class DiffController:
         self._state = None
 
     def RestrictAngle(self, theta):
-        return (theta + np.pi) % (2 * np.pi) - np.pi
+        from .guidance import norm_mpi_pi
+        return norm_mpi_pi(theta)
 
     def _gains(self, eng):
         from . import _lib

@@ -187,6 +187,18 @@ class Engine:
         self.launches += 1
         return Ur, e[:F * n_e]
 
+    def norm_mpi_pi(self, v):
+        out = torch.empty_like(v)
+        check(lib.d2dx_norm_mpi_pi(self.h, v.numel(), _ptr(v), _ptr(out), self.stream_ptr()), "d2dx_norm_mpi_pi")
+        self.launches += 1
+        return out
+
+    def circle_implicit(self, X, c, r):
+        n = X.shape[1]; out = self.empty(3, n)
+        check(lib.d2dx_circle_implicit(self.h, n, _ptr(X), _ptr(c), _ptr(r), _ptr(out), self.stream_ptr()), "d2dx_circle_implicit")
+        self.launches += 1
+        return out
+
     def gvf(self, X, c, r, ke, kd):
         n = X.shape[1]; out = self.empty(3, n)
         check(lib.d2dx_gvf(self.h, n, _ptr(X), _ptr(c), _ptr(r), float(ke), float(kd), _ptr(out), self.stream_ptr()), "d2dx_gvf")

@@ -11,9 +11,11 @@ from .engine import get_engine
 
 
 def norm_mpi_pi(v):
-    """Wrap to [-pi, pi) with floored modulo (d2d/guidance.py:10).  Host-side convenience only; the kernels
-    carry their own bit-identical wrap."""
-    return (v + np.pi) % (2 * np.pi) - np.pi
+    """Wrap to [-pi, pi) with floored modulo (d2d/guidance.py:10), evaluated by the engine (bit-identical to NumPy's `%`)."""
+    eng = get_engine()
+    a = np.asarray(v, dtype=np.float64)
+    out = eng.norm_mpi_pi(eng.to_device(np.ascontiguousarray(a.reshape(-1)))).cpu().numpy().reshape(a.shape)
+    return float(out) if a.ndim == 0 else out
 
 
 class WindField:
@@ -92,19 +94,18 @@ class DCFController:
 
 
 class CircleTraj:
-    """Implicit circle e = |p - c|^2 - r^2 (d2d/guidance.py:133-146).  Pure parameter arithmetic on three
-    scalars; kept on the host because its outputs only feed `GVFcontroller.get`, which recomputes them on the
-    device from (X, c, r)."""
+    """Implicit circle e = |p - c|^2 - r^2, its gradient n and Hessian H = 2I (d2d/guidance.py:133-146)."""
 
     def __init__(self, c=np.array([0, 0])):
         self.c = c
 
     def get(self, X, r=1):
-        px, py = X[0], X[1]
-        e = np.asarray(((px - self.c[0]) ** 2 + (py - self.c[1]) ** 2) - r ** 2)
-        n = np.asarray([2 * (px - self.c[0]), 2 * (py - self.c[1])])
-        H = np.asarray([[2, 0], [0, 2]])
-        return e, n, H
+        eng = get_engine()
+        Xd = eng.to_device(np.asarray(X, dtype=np.float64).reshape(5, 1))
+        cd = eng.to_device(np.asarray(self.c, dtype=np.float64).reshape(2, 1))
+        rd = eng.to_device(np.asarray(r, dtype=np.float64).reshape(1))
+        e, nx, ny = eng.circle_implicit(Xd, cd, rd).cpu().numpy()[:, 0]
+        return np.asarray(e), np.asarray([nx, ny]), np.asarray([[2, 0], [0, 2]])
 
 
 class GVFcontroller:

@@ -1,10 +1,5 @@
 """Small helpers of `d2d.utils` (d2d/utils.py:7-18) kept for import compatibility."""
-import numpy as np
-
-
-def norm_mpi_pi(v):
-    """Wrap an angle to [-pi, pi) with floored modulo (d2d/utils.py:7)."""
-    return (v + np.pi) % (2 * np.pi) - np.pi
+from .guidance import norm_mpi_pi  # noqa: F401  (d2d/utils.py:7; evaluated by the engine)
 
 
 class WindField:

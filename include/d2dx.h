@@ -103,6 +103,9 @@ int d2dx_cont_jac(d2dx_handle* h, int32_t n, const double* Xr, const double* ac,
 int d2dx_flatness(d2dx_handle* h, int32_t n, const double* Ys, const double* W, const double* ac,
                   double* Xr, double* Ur, double* Xrdot, void* stream);
 
+/* norm_mpi_pi, d2d/utils.py:7 / d2d/guidance.py:10: out[i] = (v[i] + pi) % (2 pi) - pi with NumPy's floored modulo */
+int d2dx_norm_mpi_pi(d2dx_handle* h, int32_t n, const double* v, double* out, void* stream);
+
 /* controller constants of DFFFController.get, d2d/guidance.py:69,79,87-88 */
 typedef struct {
   double q_pos, q_psi;       /* Q = diag(q_pos, q_pos, q_psi)   reference: 1, 0.1                */
@@ -206,6 +209,9 @@ int d2dx_rollout_tracker(d2dx_handle* h, const d2dx_tracker* in, int32_t i_begin
 int d2dx_dcf(d2dx_handle* h, int32_t F, int32_t n_ac, int32_t n_e, const double* Binc_host,
              const double* z_des_host, double kr, const double* p, const double* c, double* Ur,
              double* e_deg, void* stream);
+/* CircleTraj.get, d2d/guidance.py:137-146: X[5][n], c[2][n], r[n] -> out[3][n] = (e, n_x, n_y); H is the constant 2 I */
+int d2dx_circle_implicit(d2dx_handle* h, int32_t n, const double* X, const double* c, const double* r, double* out,
+                         void* stream);
 /* CircleTraj.get + GVFcontroller.get, d2d/guidance.py:137-146,155-181: X[5][n], c[2][n], r[n] ->
  * out[3][n] = (U, U1, U2) */
 int d2dx_gvf(d2dx_handle* h, int32_t n, const double* X, const double* c, const double* r, double ke,

@@ -401,3 +401,16 @@ def test_dfff_rollout_substeps_and_time_constants_against_oracle(d2d, nsub, tau_
         Xo, Uo, _, _, _ = orc.run_simulation(time, orc.Circle(**s), wind, X0[b], nsub=nsub, tau_phi=tau_phi, tau_v=1.3)
         np.testing.assert_allclose(res.X[b], Xo, rtol=0, atol=TOL)
         np.testing.assert_allclose(res.U[b], Uo, rtol=0, atol=TOL)
+
+
+def test_small_helpers_run_on_the_engine(d2d, golden):
+    """norm_mpi_pi and CircleTraj.get go through the C ABI as well (no host arithmetic on the path)."""
+    from d2d_b200 import guidance, utils
+    u = golden["units"]
+    np.testing.assert_array_equal(guidance.norm_mpi_pi(u["ang"]), u["wrapped"])          # bit-identical to NumPy's floored %
+    assert guidance.norm_mpi_pi(4.0) == (4.0 + np.pi) % (2 * np.pi) - np.pi and utils.norm_mpi_pi is guidance.norm_mpi_pi
+    e, n, H = guidance.CircleTraj(np.array([0, -20])).get(np.array([20, 30, -np.pi / 2, 0, 10.]), 60)
+    assert float(e) == -700.0 and list(n) == [40.0, 100.0] and H.tolist() == [[2, 0], [0, 2]]
+    l0 = d2d.get_engine().launches
+    guidance.norm_mpi_pi(np.zeros(3)); guidance.CircleTraj().get(np.zeros(5), 1.)
+    assert d2d.get_engine().launches == l0 + 2
