@@ -121,6 +121,8 @@ def _load():
         "d2dx_colloc_eval": (C.c_int, [H, P(CollocProblem), i32, c_dp, i32, u32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_colloc_eval_shard": (C.c_int, [H, P(CollocProblem), i32, i32, c_dp, c_dp, u32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_colloc_pack_positions": (C.c_int, [H, i32, i32, c_dp, c_dp, c_dp]),
+        "d2dx_shoot_forward": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_shoot_adjoint": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_dfma_burn": (C.c_int, [H, i32, i32, i32, c_dp, c_dp]),
         "d2dx_math_probe": (C.c_int, [H, i32, c_dp, c_dp, c_dp, c_dp]),
     }

@@ -284,6 +284,17 @@ class Engine:
 
 
     # ---- diagnostics -------------------------------------------------------------------------------
+    # ---- single shooting (planner NLP solve) ------------------------------------------------------------
+    def shoot_forward(self, prob, P, u, bounds, p0, p1, u_phys, xs, c):
+        b = (C.c_double * 4)(*bounds) if bounds is not None else None
+        check(lib.d2dx_shoot_forward(self.h, C.byref(prob), P, _ptr(u), b, _ptr(p0), _ptr(p1), _ptr(u_phys), _ptr(xs), _ptr(c),
+                                     self.stream_ptr()), "d2dx_shoot_forward")
+
+    def shoot_adjoint(self, prob, P, u, bounds, u_phys, xs, c, lam, rho, cost, lagr, grad):
+        b = (C.c_double * 4)(*bounds) if bounds is not None else None
+        check(lib.d2dx_shoot_adjoint(self.h, C.byref(prob), P, _ptr(u), b, _ptr(u_phys), _ptr(xs), _ptr(c), _ptr(lam), _ptr(rho),
+                                     _ptr(cost), _ptr(lagr), _ptr(grad), self.stream_ptr()), "d2dx_shoot_adjoint")
+
     def math_probe(self, x, y):
         """Engine elementary functions on device arrays x, y -> [7][n] (sin, cos, atan2(y,x), atan x, y/x, sqrt|x|, rsqrt|x|)."""
         n = x.numel(); out = self.empty(7, n)

@@ -1,8 +1,11 @@
 """Planner front-ends -- the `Planner` classes of 06_optyplan.py:25-145 (single aircraft) and
 07_multioptyplan.py:28-121 (aircraft set), with `self.prob` backed by the collocation kernel instead of
 opty's generated code.  `prob` exposes what IPOPT calls (`obj`, `obj_grad`, `con`, `con_jac`,
-`jacobianstructure`, `num_free`); the NLP solve itself (cyipopt / IPOPT) is outside the hot path."""
+`jacobianstructure`, `num_free`); `run()` solves the NLP on the GPU by single shooting (d2d_b200/shooting.py)
+instead of IPOPT."""
 import numpy as np
+
+from . import shooting
 
 from . import multiopty_utils as d2mou
 from . import opty_utils as d2ou
@@ -18,9 +21,43 @@ class _PlannerBase:
     def configure(self, tol=1e-8, max_iter=3000):
         self.tol, self.max_iter = tol, max_iter
 
-    def run(self, initial_guess=None, **_):
-        raise NotImplementedError("the IPOPT solve (prob.solve) is not part of the engine; drive self.prob's callbacks "
-                                  "from your NLP solver (cyipopt.Problem accepts this object as problem_obj)")
+    def run(self, initial_guess=None, n_starts=1, seed=0, verbose=False, **_):
+        """`self.solution, info = prob.solve(initial_guess)` of 06_optyplan.py:117-125 / 07_multioptyplan.py:80-88,
+        solved by single shooting + augmented Lagrangian (shooting.solve).  Only the input part of `initial_guess`
+        seeds the solve (the states follow from the inputs).  n_starts > 1 adds randomly perturbed starts solved in the
+        same launches; the feasible one of least cost is kept.  State bounds (x/y_constraint) are not enforced: they are
+        checked on the result and reported in `self.info["state_bounds_ok"]`."""
+        guess = self.get_initial_guess() if initial_guess is None else np.asarray(initial_guess, dtype=float)
+        n, N = self._n_ac, self.num_nodes
+        phi = np.stack([guess[sl] for sl in self._phi_slices()])[:, :, None]
+        v = np.stack([guess[sl] for sl in self._v_slices()])[:, :, None]
+        phi_b, v_b = self._bounds["phi"], self._bounds["v"]
+        if n_starts > 1:
+            rng = np.random.default_rng(seed)
+            k = np.concatenate([[0.], np.ones(n_starts - 1)])                     # start 0 is the caller's guess
+            phi = phi + k * rng.normal(0., 0.25 * (phi_b[1] - phi_b[0]), (n, 1, n_starts))
+            v = v + k * rng.normal(0., 0.25 * (v_b[1] - v_b[0]), (n, 1, n_starts))
+        p0, p1 = self._boundary_states()
+        nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts)
+        tol = getattr(self, "tol", 1e-8)
+        theta, info = shooting.solve(nlp, nlp.theta_of(np.clip(phi, *phi_b), np.clip(v, *v_b)), ctol=min(tol, 1e-6),
+                                     max_inner=min(getattr(self, "max_iter", 3000), 500), verbose=verbose)
+        frees = nlp.free_vectors()
+        if self.prob.c.perm_phi:                                                  # opty input order: place the input blocks by rank
+            frees = self._to_opty_order(frees)
+        feas = info["c_max"] < 100 * min(tol, 1e-6)
+        best = int(np.argmin(np.where(feas, info["cost"], np.inf))) if feas.any() else int(np.argmin(info["c_max"]))
+        self.solution = frees[best].copy()
+        info.update(best=best, feasible=bool(feas[best]), solutions=frees)
+        ok = True
+        for key, sls in (("x", self._x_slices()), ("y", self._y_slices())):
+            if key in self._bounds:
+                lo, hi = self._bounds[key]
+                ok = ok and all(self.solution[sl].min() >= lo - 1e-9 and self.solution[sl].max() <= hi + 1e-9 for sl in sls)
+        info["state_bounds_ok"] = ok
+        self.info = info
+        self.interpret_solution()
+        return info
 
     def evaluate(self, free):
         """residual, Jacobian values, cost, gradient at `free` in one fused launch."""
@@ -49,6 +86,14 @@ class Planner(_PlannerBase):
             w = exp.wind.sample_num(0., 0., 0.)
             self.prob = CollocationProblem(1, N, self.time_step, wind=w, inst=self._instance_constraints,
                                            cost=exp.cost.spec(), obj_scale=self.obj_scale, layout=jac_layout, multi=False)
+
+    _n_ac = 1
+    def _phi_slices(self): return [self._slice_phi]
+    def _v_slices(self): return [self._slice_v]
+    def _x_slices(self): return [self._slice_x]
+    def _y_slices(self): return [self._slice_y]
+    def _boundary_states(self):
+        return np.array(self.exp.p0[:3], float).reshape(3, 1), np.array(self.exp.p1[:3], float).reshape(3, 1)
 
     def get_initial_guess(self, kind="tri", seed=None):                             # :79-115
         N = self.num_nodes
@@ -108,11 +153,34 @@ class MultiPlanner(_PlannerBase):
         n1 = _node_of(scen.t1, scen.t0, self.time_step, N)
         self._instance_constraints = [(3 * i + k, n0, p[k]) for i, p in enumerate(scen.p0s) for k in range(3)] + \
                                      [(3 * i + k, n1, p[k]) for i, p in enumerate(scen.p1s) for k in range(3)]   # :53-56
+        self._bounds = {"phi": scen.phi_constraint, "v": scen.v_constraint}           # :58-64
+        if getattr(scen, "x_constraint", None) is not None: self._bounds["x"] = scen.x_constraint
+        if getattr(scen, "y_constraint", None) is not None: self._bounds["y"] = scen.y_constraint
         if initialize:
             w = scen.wind.sample_num(0., 0., 0.)
             self.prob = CollocationProblem(n, N, self.time_step, wind=w, inst=self._instance_constraints,
                                            cost=scen.cost.spec(), obj_scale=self.obj_scale, layout=jac_layout,
                                            input_order=input_order, multi=True)
+
+    @property
+    def _n_ac(self): return self.acs.nb_aicraft
+    def _phi_slices(self): return self._slice_phi
+    def _v_slices(self): return self._slice_v
+    def _x_slices(self): return self._slice_x
+    def _y_slices(self): return self._slice_y
+    def _boundary_states(self):
+        return np.array([p[:3] for p in self.scen.p0s], float).T, np.array([p[:3] for p in self.scen.p1s], float).T
+
+    def _to_opty_order(self, frees):
+        """numeric input blocks [phi_0..phi_{n-1} | v_0..v_{n-1}] -> opty's name-sorted block order."""
+        n, N = self.acs.nb_aicraft, self.num_nodes
+        names = [f"phi{i}" for i in range(n)] + [f"v{i}" for i in range(n)]
+        rank = {nm: k for k, nm in enumerate(sorted(names))}
+        out = frees.copy()
+        o = 3 * n * N
+        for j, nm in enumerate(names):
+            out[:, o + rank[nm] * N:o + (rank[nm] + 1) * N] = frees[:, o + j * N:o + (j + 1) * N]
+        return out
 
     def get_initial_guess(self, what="tri", seed=None):                             # :94-112
         N, n = self.num_nodes, self.acs.nb_aicraft
@@ -166,12 +234,12 @@ class MultiPlanner(_PlannerBase):
 
 
 def compute_or_load(_p, force_recompute=False, filename="/tmp/optyplan.npz", tol=1e-5, max_iter=1500, initial_guess=None):
-    """Cache front end of 06_optyplan.py:152-164: loads a cached solution when there is one; computing a new one needs
-    an NLP solver driving `_p.prob` (outside the engine)."""
+    """Cache front end of 06_optyplan.py:152-164: loads a cached solution when there is one, else solves (`_p.run`)
+    and saves."""
     import os
     if force_recompute or not os.path.exists(filename):
         _p.configure(tol, max_iter)
-        _p.run(_p.get_initial_guess() if initial_guess is None else initial_guess)      # raises: no solver in the engine
+        _p.run(_p.get_initial_guess() if initial_guess is None else initial_guess)
         _p.save_solution(filename)
     else:
         _p.load_solution(filename)

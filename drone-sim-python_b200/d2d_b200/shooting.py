@@ -1,0 +1,148 @@
+"""NLP driver for the planners: what `prob.solve(initial_guess)` (opty -> IPOPT) does in
+06_optyplan.py:117-125 and 07_multioptyplan.py:80-88, re-posed for the GPU.
+
+The backward-Euler defects of the collocation constraints fix the states once the inputs are chosen, so the solver
+iterates on the inputs only (single shooting on the collocation grid): the 3 n_ac (N-1) defect constraints hold by
+construction, the initial states are data, and only the 3 n_ac terminal conditions remain -- handled by an augmented
+Lagrangian.  The input bounds are removed by the substitution phi = mid + half sin(theta).  Each Lagrangian/gradient
+evaluation is two kernel launches (`d2dx_shoot_forward`, `d2dx_shoot_adjoint`) for P problems at once (multi-start or
+a population of boundary conditions); the quasi-Newton update around them is batched limited-memory BFGS on device
+tensors (vector algebra only).  The result satisfies the reference's constraints (`CollocationProblem.con`) to the
+requested tolerance; like any local method it returns a local optimum that can differ from IPOPT's."""
+import numpy as np
+import torch
+
+
+
+class ShootingNLP:
+    """P simultaneous problems sharing one description (`prob`: a CollocationProblem, which supplies n_ac, N, h, wind
+    and the cost).  p0, p1: (3, n_ac) or (3, n_ac, P) initial states / terminal targets (x, y, psi)."""
+
+    def __init__(self, prob, p0, p1, phi_bounds, v_bounds, P=1, engine=None):
+        self.eng = e = engine or prob.eng
+        self.prob, self.c_prob = prob, prob.c
+        self.n_ac, self.N, self.P = prob.n_ac, prob.N, int(P)
+        self.bounds = (float(phi_bounds[0]), float(phi_bounds[1]), float(v_bounds[0]), float(v_bounds[1]))
+        self.mid = np.array([0.5 * (self.bounds[0] + self.bounds[1]), 0.5 * (self.bounds[2] + self.bounds[3])])
+        self.half = np.array([0.5 * (self.bounds[1] - self.bounds[0]), 0.5 * (self.bounds[3] - self.bounds[2])])
+        bc = lambda a: e.to_device(np.ascontiguousarray(np.broadcast_to(
+            np.asarray(a, np.float64).reshape(3, self.n_ac, -1), (3, self.n_ac, self.P))))
+        self.p0, self.p1 = bc(p0), bc(p1)
+        n_ac, N = self.n_ac, self.N
+        self.n = 2 * n_ac * N
+        self.u_phys, self.xs = e.empty(2, n_ac, N, self.P), e.empty(3, n_ac, N, self.P)
+        self.c = e.empty(3, n_ac, self.P)
+        self.lam, self.rho = e.zeros(3, n_ac, self.P), e.zeros(self.P) + 10.
+        self.cost, self.lagr, self.grad = e.empty(self.P), e.empty(self.P), e.empty(2, n_ac, N, self.P)
+        self.nfev = 0
+
+    # ---- variables ------------------------------------------------------------------------------------
+    def theta_of(self, phi, v):
+        """host (n_ac, N[, P]) physical inputs -> device theta (n, P); values are clipped just inside the bounds."""
+        u = np.stack([np.asarray(phi, np.float64).reshape(self.n_ac, self.N, -1), np.asarray(v, np.float64).reshape(self.n_ac, self.N, -1)])
+        s = (u - self.mid[:, None, None, None]) / self.half[:, None, None, None]
+        th = np.arcsin(np.clip(s, -0.999, 0.999))
+        return self.eng.to_device(np.ascontiguousarray(np.broadcast_to(th, (2, self.n_ac, self.N, self.P)))).reshape(self.n, self.P)
+
+    def evaluate(self, theta):
+        """theta: device (n, P).  Returns fresh (lagrangian (P,), gradient (n, P)); cost, c, xs, u_phys stay in the buffers."""
+        e = self.eng
+        e.shoot_forward(self.c_prob, self.P, theta, self.bounds, self.p0, self.p1, self.u_phys, self.xs, self.c)
+        e.shoot_adjoint(self.c_prob, self.P, theta, self.bounds, self.u_phys, self.xs, self.c, self.lam, self.rho,
+                        self.cost, self.lagr, self.grad)
+        self.nfev += 1
+        return self.lagr.clone(), self.grad.reshape(self.n, self.P).clone()
+
+    def free_vectors(self):
+        """(P, num_free) host array in the planner's layout [x,y,psi per aircraft | phi per aircraft | v per aircraft]
+        from the last evaluation."""
+        xs = self.xs.permute(3, 1, 0, 2).reshape(self.P, -1)                      # [P][ac][k][N]
+        u = self.u_phys.permute(3, 0, 1, 2).reshape(self.P, -1)                   # [P][phi|v][ac][N]
+        return torch.cat([xs, u], dim=1).cpu().numpy()
+
+
+def lbfgs(fun, x, m=20, maxit=500, gtol=1e-10, ftol=1e-10, window=10, ls_max=30):
+    """Batched limited-memory BFGS with Armijo backtracking: column p of x (n, P) is an independent problem.
+    fun(x) -> (f (P,), g (n, P)) fresh tensors.  A problem stops when |g|_inf <= gtol, when f fell by less than
+    ftol max(1, |f|) over the last `window` iterations, or when its line search fails twice in a row.
+    Returns x, f, g, iterations."""
+    n, P = x.shape
+    kw = dict(dtype=x.dtype, device=x.device)
+    f, g = fun(x)
+    S, Y, rh = torch.zeros(m, n, P, **kw), torch.zeros(m, n, P, **kw), torch.zeros(m, P, **kw)
+    gamma, have = torch.ones(P, **kw), torch.zeros(P, dtype=torch.bool, device=x.device)
+    done = torch.zeros(P, dtype=torch.bool, device=x.device)
+    head = cnt = it = 0
+    f_hist = []
+    for it in range(maxit):
+        gn = g.abs().amax(0)
+        done = done | (gn <= gtol)
+        f_hist.append(f)
+        if len(f_hist) > window:
+            f_old = f_hist.pop(0)
+            done = done | ((f_old - f) <= ftol * f.abs().clamp_min(1.0))
+        if bool(done.all()):
+            break
+        q, al = g.clone(), []
+        order = [(head - 1 - j) % m for j in range(min(cnt, m))]                # newest -> oldest
+        for j in order:
+            a = rh[j] * (S[j] * q).sum(0)
+            al.append(a)
+            q -= a * Y[j]
+        r = q * gamma
+        for j, a in zip(reversed(order), reversed(al)):
+            r += S[j] * (a - rh[j] * (Y[j] * r).sum(0))
+        d = -r
+        bad = ~((g * d).sum(0) < -1e-14 * gn * gn)                               # not a descent direction -> steepest descent
+        scale0 = 1.0 / g.abs().sum(0).clamp_min(1e-300)
+        d = torch.where(bad | ~have, -g * torch.where(have, gamma, scale0), d)
+        alpha, acc = torch.ones(P, **kw), done.clone()
+        xn, fn, gnew = x.clone(), f.clone(), g.clone()
+        for _ in range(ls_max):
+            xt = x + alpha * d
+            ft, gt = fun(xt)
+            ok = (ft <= f + 1e-4 * alpha * (g * d).sum(0) + 1e-15 * f.abs()) & ~acc & torch.isfinite(ft)
+            xn, fn, gnew = torch.where(ok, xt, xn), torch.where(ok, ft, fn), torch.where(ok, gt, gnew)
+            acc = acc | ok
+            if bool(acc.all()):
+                break
+            alpha = torch.where(acc, alpha, alpha * 0.5)
+        failed = ~acc
+        s, y = xn - x, gnew - g
+        sy, ss, yy = (s * y).sum(0), (s * s).sum(0), (y * y).sum(0)
+        good = (sy > 1e-10 * torch.sqrt(ss * yy)) & acc & ~done
+        S[head], Y[head] = s * good, y * good
+        rh[head] = torch.where(good, 1.0 / sy.clamp_min(1e-300), torch.zeros_like(sy))
+        gamma, have = torch.where(good, sy / yy.clamp_min(1e-300), gamma), have | good
+        head, cnt = (head + 1) % m, cnt + 1
+        if bool(failed.any()):                                                   # drop the history of the problems that stalled
+            S[:, :, failed], Y[:, :, failed], rh[:, failed] = 0, 0, 0
+            done = done | (failed & (bad | ~have))
+            have = have & ~failed
+        x, f, g = xn, fn, gnew
+    return x, f, g, it
+
+
+def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner=500, rho0=10., rho_max=1e6, m=20, verbose=False):
+    """Augmented-Lagrangian loop around `lbfgs`.  Returns theta and an info dict; `nlp.free_vectors()` then gives the
+    planner-layout solutions.  Per problem: lam += rho c after each inner solve; rho x3 (up to rho_max) when |c| did
+    not fall to a quarter of its previous value."""
+    nlp.lam.zero_()
+    nlp.rho.fill_(rho0)
+    total, c_prev = 0, None
+    for outer in range(max_outer):
+        theta, f, g, it = lbfgs(nlp.evaluate, theta, m=m, maxit=max_inner, gtol=gtol, ftol=ftol)
+        total += it
+        nlp.evaluate(theta)                                                      # buffers at the returned point
+        cmax = nlp.c.abs().amax(dim=(0, 1))
+        if verbose:
+            print(f"outer {outer}: inner its {it}, cost {nlp.cost.min().item():.6e}..{nlp.cost.max().item():.6e}, "
+                  f"|c| {cmax.max().item():.2e}, rho {nlp.rho.max().item():.0f}")
+        if bool((cmax < ctol).all()):
+            break
+        nlp.lam += nlp.rho * nlp.c
+        slow = (cmax > ctol) & ((cmax > 0.25 * c_prev) if c_prev is not None else torch.ones_like(cmax, dtype=torch.bool))
+        nlp.rho.copy_(torch.where(slow, (nlp.rho * 3).clamp_max(rho_max), nlp.rho))
+        c_prev = cmax
+    return theta, {"outer": outer + 1, "iterations": total, "nfev": nlp.nfev, "c_max": cmax.cpu().numpy(),
+                   "cost": nlp.cost.cpu().numpy()}

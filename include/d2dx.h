@@ -310,6 +310,28 @@ int d2dx_colloc_eval_shard(d2dx_handle* h, const d2dx_colloc_problem* p_local_ho
 int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const double* free_local,
                                double* pos, void* stream);
 
+/* -------- single-shooting evaluation of the planner NLP --------
+ * On the backward-Euler grid the defects of d2dx_colloc_eval determine the states from the inputs:
+ *   psi_i = psi_{i-1} + h g tan(phi_i)/v_i,  x_i = x_{i-1} + h (v_i cos psi_i - w_x),  y_i = y_{i-1} + h (v_i sin psi_i - w_y),
+ * so a solver can iterate on the inputs only.  For P problems at once (problem index fastest):
+ *   u[2][n_ac][N][P]      inputs phi, v at every node (node 0 enters the cost only)
+ *   p0[3][n_ac][P], p1[3][n_ac][P]   initial state and terminal target (x, y, psi) of each aircraft
+ *   lam[3][n_ac][P], rho[P]          augmented-Lagrangian multipliers / penalty of the terminal constraints
+ * d2dx_shoot_forward fills xs[3][n_ac][N][P] (x, y, psi) and c[3][n_ac][P] = state(N-1) - p1.
+ * d2dx_shoot_adjoint (after forward, same arguments) returns
+ *   cost[P]  = planner cost of d2dx_colloc_problem (exact value) ,
+ *   lagr[P]  = cost + sum lam.c + rho/2 |c|^2 ,   grad[2][n_ac][N][P] = d lagr / d u   (exact derivatives).
+ * `p_host` supplies n_ac, N, h, wind and the cost description (instance constraints, permutations and exact_grad are
+ * ignored: the terminal targets come from p1, gradients are always exact).
+ * Box constraints by substitution: with `bounds` = {phi_lo, phi_hi, v_lo, v_hi} (HOST array; NULL = none) `u` holds
+ * angles theta with phi = mid + half sin(theta) (likewise v); forward writes the physical inputs to u_phys (same shape
+ * as u), adjoint reads them and returns the gradient with respect to theta. */
+int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t P, const double* u, const double* bounds,
+                       const double* p0, const double* p1, double* u_phys, double* xs, double* c, void* stream);
+int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t P, const double* u, const double* bounds,
+                       const double* u_phys, const double* xs, const double* c, const double* lam, const double* rho,
+                       double* cost, double* lagr, double* grad, void* stream);
+
 /* -------- diagnostics -------- */
 /* FP64 roofline probe: every thread runs `iters` rounds of 16 independent DFMA chains (32*iters flop per
  * thread); the caller times it with CUDA events.  sink: device double[1] (keeps the chains alive). */

@@ -730,3 +730,34 @@ def cost_and_grad(free, N, n_ac, spec, multi=None):
             grad[sx[b]] += kcol * (s / N * 2. * dx * es) * f
             grad[sy[b]] += kcol * (s / N * 2. * dy * es) * f
     return cost, grad
+
+
+# ---------------------------------------------------------------------------
+# single shooting on the collocation grid (checker of d2dx_shoot_forward / d2dx_shoot_adjoint)
+# ---------------------------------------------------------------------------
+def shoot_states(phi, v, p0, h, wind, g=G):
+    """States that zero the backward-Euler defects of `colloc_residual` for given inputs.  phi, v: (n_ac, N)
+    (node 0 unused); p0: (3, n_ac).  Returns x, y, psi of shape (n_ac, N)."""
+    phi, v, p0 = np.atleast_2d(phi), np.atleast_2d(v), np.asarray(p0, float).reshape(3, -1)
+    z = np.zeros((phi.shape[0], 1))
+    psi = p0[2][:, None] + np.hstack([z, np.cumsum(h * g * np.tan(phi[:, 1:]) / v[:, 1:], axis=1)])
+    x = p0[0][:, None] + np.hstack([z, np.cumsum(h * (v[:, 1:] * np.cos(psi[:, 1:]) - wind[0]), axis=1)])
+    y = p0[1][:, None] + np.hstack([z, np.cumsum(h * (v[:, 1:] * np.sin(psi[:, 1:]) - wind[1]), axis=1)])
+    return x, y, psi
+
+
+def shoot_free(phi, v, p0, h, wind):
+    """Planner-layout free vector [x, y, psi per aircraft | phi per aircraft | v per aircraft] of a shooting point."""
+    x, y, psi = shoot_states(phi, v, p0, h, wind)
+    return np.concatenate([np.concatenate([x[a], y[a], psi[a]]) for a in range(x.shape[0])] + [np.ravel(phi), np.ravel(v)])
+
+
+def shoot_lagrangian(phi, v, p0, p1, h, wind, spec, lam, rho, multi=None):
+    """cost (reference cost classes, exact value), c = terminal state - p1 (3, n_ac), and
+    cost + sum lam c + rho/2 |c|^2."""
+    phi, v = np.atleast_2d(phi), np.atleast_2d(v)
+    n_ac, N = phi.shape
+    x, y, psi = shoot_states(phi, v, p0, h, wind)
+    cost, _ = cost_and_grad(shoot_free(phi, v, p0, h, wind), N, n_ac, spec, multi)
+    c = np.stack([x[:, -1], y[:, -1], psi[:, -1]]) - np.asarray(p1, float).reshape(3, -1)
+    return cost, c, cost + np.sum(np.asarray(lam) * c) + 0.5 * rho * np.sum(c * c)

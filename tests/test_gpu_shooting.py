@@ -1,0 +1,141 @@
+"""Planner NLP solve on the engine: shooting kernels against the NumPy oracle (values bit-close,
+gradients against central differences of the oracle), consistency with the collocation constraints, and the
+planners' run() checked by the reference's own constraint residual and against a cached IPOPT solution's cost."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "drone-sim-python_b200"))
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+pytestmark = pytest.mark.gpu
+
+from oracle import d2d_oracle as orc  # noqa: E402
+
+
+def _setup(n_ac, N, P, bounded, seed=0):
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    from d2d_b200.shooting import ShootingNLP
+    rng = np.random.default_rng(seed)
+    h, wind = 0.1, (1.0, -0.5)
+    spec = dict(vsp=12., kvel=3., kbank=2., kcol=10., rcol=10., pairs="all", exact_grad=True, kobs=1.5,
+                obstacles=[(5., 2., 6.), (12., -3., 4.)], obs_kind=1)
+    cs = CostSpec(vsp=12., kvel=3., kbank=2., kcol=10., rcol=10., all_pairs=True, kobs=1.5,
+                  obstacles=[(5., 2., 6.), (12., -3., 4.)], obs_kind=1)
+    prob = CollocationProblem(n_ac, N, h, wind=wind, cost=cs, obj_scale=2.0, multi=n_ac > 1)
+    spec["obj_scale"] = 2.0
+    p0 = rng.uniform(-5, 5, (3, n_ac, P)); p1 = rng.uniform(-5, 25, (3, n_ac, P))
+    pb, vb = (-0.6, 0.5), (9., 15.)
+    nlp = ShootingNLP(prob, p0, p1, pb, vb, P=P)
+    phi = rng.uniform(-0.4, 0.4, (n_ac, N, P)); v = rng.uniform(9.5, 14.5, (n_ac, N, P))
+    return prob, nlp, spec, h, wind, p0, p1, phi, v, (pb, vb), rng
+
+
+@pytest.mark.parametrize("n_ac,N,P", [(1, 40, 1), (3, 25, 4), (5, 12, 130)])
+def test_shoot_value_and_gradient_against_oracle(n_ac, N, P):
+    import torch
+    prob, nlp, spec, h, wind, p0, p1, phi, v, (pb, vb), rng = _setup(n_ac, N, P, True)
+    nlp.lam.copy_(torch.as_tensor(rng.normal(0, 1, (3, n_ac, P)))); nlp.rho.copy_(torch.as_tensor(rng.uniform(1, 50, P)))
+    lam, rho = nlp.lam.cpu().numpy(), nlp.rho.cpu().numpy()
+    theta = nlp.theta_of(phi, v)
+    L, g = nlp.evaluate(theta)
+    L, g, th = L.cpu().numpy(), g.cpu().numpy().reshape(2, n_ac, N, P), theta.cpu().numpy().reshape(2, n_ac, N, P)
+    cost, c = nlp.cost.cpu().numpy(), nlp.c.cpu().numpy()
+    xs, up = nlp.xs.cpu().numpy(), nlp.u_phys.cpu().numpy()
+    mid, half = nlp.mid, nlp.half
+
+    def lag(thp, p):
+        ph, vv = mid[0] + half[0] * np.sin(thp[0]), mid[1] + half[1] * np.sin(thp[1])
+        return orc.shoot_lagrangian(ph, vv, p0[:, :, p], p1[:, :, p], h, wind, spec, lam[:, :, p], rho[p], multi=n_ac > 1)
+
+    for p in range(0, P, max(P // 4, 1)):
+        co, cc, Lo = lag(th[:, :, :, p], p)
+        assert abs(cost[p] - co) <= 1e-12 * max(1, abs(co))
+        np.testing.assert_allclose(c[:, :, p], cc, rtol=0, atol=1e-11)
+        assert abs(L[p] - Lo) <= 1e-11 * max(1, abs(Lo))
+        x, y, psi = orc.shoot_states(up[0, :, :, p], up[1, :, :, p], p0[:, :, p], h, wind)
+        np.testing.assert_allclose(xs[:, :, :, p], np.stack([x, y, psi]), rtol=0, atol=1e-11)
+        for _ in range(12):                                     # gradient: central differences of the oracle
+            k, a, i = rng.integers(2), rng.integers(n_ac), rng.integers(N)
+            e = np.zeros_like(th[:, :, :, p]); e[k, a, i] = 1e-4
+            F = lambda s_: lag(th[:, :, :, p] + s_ * e, p)[2]
+            fd = (8 * (F(1) - F(-1)) - (F(2) - F(-2))) / 12e-4     # 4th-order central difference
+            assert abs(g[k, a, i, p] - fd) <= 1e-7 * max(1., abs(fd)), (k, a, i, g[k, a, i, p], fd)
+    # the shooting point zeroes the defects of the collocation constraints (engine's own evaluator)
+    res = prob.con(nlp.free_vectors())
+    assert np.abs(res[:, :3 * n_ac * (N - 1)]).max() < 1e-10
+
+
+def test_shoot_unbounded_gradient():
+    """bounds = NULL: u are the physical inputs and the gradient is with respect to them."""
+    import torch
+    prob, nlp, spec, h, wind, p0, p1, phi, v, _, rng = _setup(2, 20, 2, False)
+    e = nlp.eng
+    u = e.to_device(np.ascontiguousarray(np.stack([phi, v])))
+    e.shoot_forward(prob.c, 2, u, None, nlp.p0, nlp.p1, None, nlp.xs, nlp.c)
+    nlp.rho.fill_(7.0)
+    e.shoot_adjoint(prob.c, 2, u, None, None, nlp.xs, nlp.c, nlp.lam, nlp.rho, nlp.cost, nlp.lagr, nlp.grad)
+    g, L = nlp.grad.cpu().numpy(), nlp.lagr.cpu().numpy()
+    lag = lambda ph, vv, p: orc.shoot_lagrangian(ph, vv, p0[:, :, p], p1[:, :, p], h, wind, spec, np.zeros((3, 2)), 7.0, multi=True)[2]
+    for p in range(2):
+        assert abs(L[p] - lag(phi[:, :, p], v[:, :, p], p)) <= 1e-11 * abs(L[p])
+        for (k, a, i) in ((0, 0, 3), (1, 1, 7), (0, 1, 19), (1, 0, 0), (1, 0, 19)):
+            d = np.zeros((2, 2, 20)); d[k, a, i] = 1e-4
+            F = lambda s_: lag(phi[:, :, p] + s_ * d[0], v[:, :, p] + s_ * d[1], p)
+            fd = (8 * (F(1) - F(-1)) - (F(2) - F(-2))) / 12e-4
+            assert abs(g[k, a, i, p] - fd) <= 1e-7 * max(1., abs(fd))
+
+
+def test_planner_run_single_aircraft():
+    """Planner.run() on exp_0 (06_optyplan.py) and on the C3 grid: feasible to 1e-7 by the reference's constraints; on
+    the C3 grid the cost is not above the cached IPOPT solution's (golden c3/sol, cost 8.09e-8)."""
+    from d2d_b200 import planner as pl
+    p = pl.Planner(pl.exp_0)
+    p.configure(tol=1e-8)
+    info = p.run()
+    assert info["feasible"] and np.abs(p.prob.con(p.solution)).max() < 1e-7
+    assert abs(p.prob.obj(p.solution) - 0.75291) < 2e-4            # local optimum found by two independent solvers (DESIGN)
+    lo, hi = pl.exp_0.phi_constraint
+    assert p.sol_phi.min() >= lo - 1e-12 and p.sol_phi.max() <= hi + 1e-12 and p.sol_v.min() >= 9. and p.sol_v.max() <= 14.
+
+    class exp_c3(pl.exp_0):
+        t1, hz = 20., 50.
+    g = np.load(os.path.join(HERE, "golden", "colloc.npz"))
+    p = pl.Planner(exp_c3)
+    p.configure(tol=1e-8)
+    info = p.run()
+    assert np.abs(p.prob.con(p.solution)).max() < 1e-7
+    assert p.prob.obj(p.solution) <= p.prob.obj(g["c3/sol"]) + 1e-9
+
+
+def test_planner_run_multi_aircraft_multistart(tmp_path):
+    """MultiPlanner.run(): four crossing aircraft with collision and obstacle costs, several starts in one batch; the
+    kept solution is feasible, inside the input bounds, and the CSV export round-trips."""
+    from d2d_b200 import planner as pl, opty_utils as d2ou, multiopty_utils as d2mou
+
+    class scen4:
+        t0, t1, hz = 0., 10., 10.
+        p0s = [(0., 0., 0.), (0., 30., 0.), (80., 0., np.pi), (80., 30., np.pi)]
+        p1s = [(80., 30., 0.), (80., 0., 0.), (0., 30., np.pi), (0., 0., np.pi)]
+        vref, obj_scale = 12., 1.
+        wind = d2ou.WindField(w=[0., 0.])
+        cost = d2mou.CostComposit(kvel=1., kbank=1., kcol=10., vsp=12., rcol=5., all_pairs=True, obss=[(40., 15., 6.)], kobs=5., obs_kind=1)
+        phi_constraint = (-np.deg2rad(40.), np.deg2rad(40.))
+        v_constraint = (9., 15.)
+        x_constraint = y_constraint = None
+    p = pl.MultiPlanner(scen4)
+    p.configure(tol=1e-6)
+    info = p.run(n_starts=4)
+    assert info["feasible"] and info["solutions"].shape == (4, p.prob.num_free)
+    assert np.abs(p.prob.con(p.solution)).max() < 1e-5
+    for a in range(4):
+        assert np.abs(p.sol_phi[a]).max() <= np.deg2rad(40.) + 1e-12 and 9. - 1e-12 <= p.sol_v[a].min() and p.sol_v[a].max() <= 15. + 1e-12
+    assert info["cost"][info["best"]] <= info["cost"][0] + 1e-12 or not (info["c_max"][0] < 1e-4)
+    f = str(tmp_path / "sol.csv")
+    p.save_csv(f)
+    q = pl.MultiPlanner(scen4)
+    q.load_csv(f)
+    np.testing.assert_allclose(q.solution, p.solution, rtol=1e-13, atol=1e-13)

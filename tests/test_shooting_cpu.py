@@ -1,0 +1,57 @@
+"""Host-side pieces of the planner NLP solve that need no GPU: the oracle's shooting restatement against the oracle's
+collocation residual, and the batched L-BFGS driver on analytic problems."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "drone-sim-python_b200"))
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+from oracle import d2d_oracle as orc  # noqa: E402
+
+
+def test_oracle_shooting_point_zeroes_the_collocation_defects():
+    rng = np.random.default_rng(1)
+    n_ac, N, h, wind = 3, 50, 0.05, (1.5, -0.7)
+    phi, v = rng.uniform(-0.5, 0.5, (n_ac, N)), rng.uniform(9, 15, (n_ac, N))
+    p0 = rng.uniform(-10, 10, (3, n_ac))
+    free = orc.shoot_free(phi, v, p0, h, wind)
+    inst = [(3 * a + k, 0, p0[k, a]) for a in range(n_ac) for k in range(3)]
+    res = orc.colloc_residual(free, N, n_ac, h, wind, inst)
+    assert np.abs(res).max() < 1e-11
+    cost, c, L = orc.shoot_lagrangian(phi, v, p0, p0 + 1.0, h, wind, dict(vsp=12., kvel=1.), np.ones((3, n_ac)), 4.0, multi=True)
+    x, y, psi = orc.shoot_states(phi, v, p0, h, wind)
+    np.testing.assert_allclose(c, np.stack([x[:, -1], y[:, -1], psi[:, -1]]) - (p0 + 1.0))
+    assert abs(L - (cost + c.sum() + 2.0 * (c * c).sum())) < 1e-12
+
+
+def test_batched_lbfgs_independent_columns():
+    """Each column is its own problem: a convex quadratic, Rosenbrock chains with different starts, and one column that
+    starts at its optimum (must stay put while the others iterate)."""
+    from d2d_b200.shooting import lbfgs
+    n, P = 10, 4
+    A = torch.diag(torch.logspace(0, 3, n, dtype=torch.float64))
+    b = torch.arange(1, n + 1, dtype=torch.float64)
+
+    def fun(x):
+        f, g = torch.zeros(P, dtype=torch.float64), torch.zeros_like(x)
+        q = x[:, 0]
+        f[0], g[:, 0] = 0.5 * q @ A @ q - b @ q, A @ q - b
+        for p in (1, 2, 3):
+            z = x[:, p]
+            f[p] = (100 * (z[1:] - z[:-1] ** 2) ** 2 + (1 - z[:-1]) ** 2).sum()
+            g[:-1, p] = -400 * z[:-1] * (z[1:] - z[:-1] ** 2) - 2 * (1 - z[:-1])
+            g[1:, p] += 200 * (z[1:] - z[:-1] ** 2)
+        return f, g
+
+    x0 = torch.zeros(n, P, dtype=torch.float64)
+    x0[:, 2] = -1.2
+    x0[:, 3] = 1.0                                            # already optimal
+    x, f, g, it = lbfgs(fun, x0, maxit=2000, gtol=1e-9, ftol=0.0)
+    np.testing.assert_allclose(x[:, 0].numpy(), (b / torch.diag(A)).numpy(), rtol=1e-7)
+    np.testing.assert_allclose(x[:, 1].numpy(), 1.0, atol=1e-6)
+    np.testing.assert_allclose(x[:, 2].numpy(), 1.0, atol=1e-6)
+    assert torch.equal(x[:, 3], x0[:, 3]) and g.abs().max() < 1e-8
