@@ -222,6 +222,32 @@ def secondary_metrics(eng, hbm_peak):
     refd, wz, act, Xft = eng.to_device(ref), eng.zeros(2, Mt), eng.to_device(np.stack([np.full(Mt, 0.01), np.full(Mt, 1.)])), eng.empty(5, Mt)
     dtt = timed(lambda: eng.rollout_tracker(refd, X0t, wz, act, 0.1, 0, Tt - 1, 10, X_final=Xft), 3)
     out["tracker_lqr5_batch"] = {"aircraft_steps_per_s": Mt * (Tt - 1) / dtt, "rk4_substeps_per_s": Mt * (Tt - 1) * 10 / dtt, "aircraft": Mt, "ms_per_launch": dtt * 1e3}
+    # planner NLP solve by single shooting.  (a) one Lagrangian+gradient evaluation of a population:
+    # forward writes u_phys + states (2+3 doubles) and reads theta (2); adjoint reads theta, u_phys, states (7) and writes
+    # the gradient (2): 16 doubles = 128 algorithmic bytes per aircraft-node.  (b) whole solves: exp_0 on the C3 grid.
+    from d2d_b200 import planner as pl
+    from d2d_b200.shooting import ShootingNLP, solve as shoot_solve
+    Ps, Ns = 16384, 1001
+    probs = CollocationProblem(1, Ns, 0.02, cost=CostSpec(vsp=12., kvel=1.), multi=False)
+    nlp = ShootingNLP(probs, np.zeros((3, 1)), np.array([0., 30., np.pi]).reshape(3, 1), (-0.52, 0.52), (9., 14.), P=Ps)
+    th = eng.to_device(rng.uniform(-1., 1., (Ps, nlp.n)))
+    dts = timed(lambda: nlp.launch(th), 5)
+    out["shoot_eval_batch16384"] = {"evals_per_s": Ps / dts, "aircraft_nodes_per_s": Ps * Ns / dts, "ms_per_eval": dts * 1e3,
+                                    "roofline": {"bound": "hbm", "achieved": 128.0 * Ps * Ns / dts / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                 "frac": 128.0 * Ps * Ns / dts / 1e9 / hbm_peak}}
+    del nlp, th
+
+    class exp_c3(pl.exp_0):
+        t1, hz = 20., 50.
+    for tag, n_starts in (("planner_solve_c3_single", 1), ("planner_solve_c3_64starts", 64)):
+        p = pl.Planner(exp_c3)
+        p.configure(tol=1e-8)
+        torch.cuda.synchronize(); t0 = _time.perf_counter()
+        info = p.run(n_starts=n_starts)
+        torch.cuda.synchronize(); dt_solve = _time.perf_counter() - t0
+        out[tag] = {"seconds": dt_solve, "lbfgs_iterations": int(info["iterations"]), "evaluations": int(info["nfev"]), "ticks": int(info.get("ticks", 0)),
+                    "feasible_starts": int((info["c_max"] < 1e-6).sum()), "cost": float(info["cost"][info["best"]]),
+                    "constraint_residual_max": float(np.abs(p.prob.con(p.solution)).max())}
     return out
 
 

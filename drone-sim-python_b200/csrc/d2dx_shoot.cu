@@ -1,13 +1,17 @@
 // Single-shooting evaluation of the planner NLP: states from inputs on the backward-Euler grid of the
 // collocation constraints (d2d/opty_utils.py:38-50), planner cost (d2d/opty_utils.py:55-165, d2d/multiopty_utils.py:29-174)
-// and its exact gradient with respect to the inputs by one adjoint sweep.  One thread = one (problem, aircraft); the
-// problem index is the fastest one in every array, so a warp's accesses are coalesced.
+// and its exact gradient with respect to the inputs by one adjoint sweep.
+// One warp = one (problem, aircraft); lanes own consecutive nodes (coalesced rows of 32), and the recursions
+//   psi_i = psi_{i-1} + dpsi_i,  x_i = x_{i-1} + dx_i(psi_i),  y_i = ...        (forward: prefix sums)
+//   Gx_i = Gx_{i+1} + ax_i,  Gpsi_i = Gpsi_{i+1} + m_i(Gx_i, Gy_i)               (adjoint: suffix sums)
+// are warp-shuffle scans with a carry between rows, so a 1001-node problem costs 32 row steps instead of 1000 serial ones.
 #include "d2dx_device.cuh"
 #include "d2dx_host.h"
 
 namespace d2dx {
 
 constexpr int kShootThreads = 128;
+constexpr int kShootWarps = kShootThreads / 32;
 
 struct ShootArgs {
   d2dx_colloc_problem p;
@@ -20,125 +24,167 @@ struct ShootArgs {
 
 __device__ __forceinline__ bool on(double k) { return (k == k) && k != 0.0; }
 
-__global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __grid_constant__ ShootArgs a) {
-  const int N = a.p.N, n_ac = a.p.n_ac;
-  const size_t P = a.P;
-  const size_t t = (size_t)blockIdx.x * kShootThreads + threadIdx.x;
-  if (t >= P * n_ac) return;
-  const size_t p = t % P, ac = t / P;
-  const double h = a.p.h, wx = a.p.wind[0], wy = a.p.wind[1];
-  const size_t o_phi = ((0 * (size_t)n_ac + ac) * N) * P + p, o_v = ((1 * (size_t)n_ac + ac) * N) * P + p;
-  const double* phi = a.u + o_phi;
-  const double* v = a.u + o_v;
-  double* xo = a.xs + ((0 * (size_t)n_ac + ac) * N) * P + p;
-  double* yo = a.xs + ((1 * (size_t)n_ac + ac) * N) * P + p;
-  double* po = a.xs + ((2 * (size_t)n_ac + ac) * N) * P + p;
-  double x = a.p0[(0 * (size_t)n_ac + ac) * P + p], y = a.p0[(1 * (size_t)n_ac + ac) * P + p], psi = a.p0[(2 * (size_t)n_ac + ac) * P + p];
-  xo[0] = x; yo[0] = y; po[0] = psi;
-  for (int i = 0; i < N; ++i) {
-    double ph = phi[(size_t)i * P], vv = v[(size_t)i * P];
-    double sp, cp, s, c;
-    if (a.bounded) {
-      sincos_any(ph, s, c); ph = a.mid[0] + a.half[0] * s;
-      sincos_any(vv, s, c); vv = a.mid[1] + a.half[1] * s;
-      a.uphys[o_phi + (size_t)i * P] = ph; a.uphys[o_v + (size_t)i * P] = vv;
-    }
-    if (i == 0) continue;
-    sincos_any(ph, sp, cp);
-    psi += h * kG * sp * rcp_f(cp * vv);
-    sincos_any(psi, s, c);
-    x += h * (vv * c - wx);
-    y += h * (vv * s - wy);
-    xo[(size_t)i * P] = x; yo[(size_t)i * P] = y; po[(size_t)i * P] = psi;
+// inclusive prefix sum over the warp (lane order)
+__device__ __forceinline__ double warp_prefix(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
   }
-  a.c[(0 * (size_t)n_ac + ac) * P + p] = x - a.p1[(0 * (size_t)n_ac + ac) * P + p];
-  a.c[(1 * (size_t)n_ac + ac) * P + p] = y - a.p1[(1 * (size_t)n_ac + ac) * P + p];
-  a.c[(2 * (size_t)n_ac + ac) * P + p] = psi - a.p1[(2 * (size_t)n_ac + ac) * P + p];
+  return v;
+}
+// inclusive suffix sum over the warp (lane l gets sum over lanes >= l)
+__device__ __forceinline__ double warp_suffix(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += t;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __grid_constant__ ShootArgs a) {
+  const int N = a.p.N, n_ac = a.p.n_ac, lane = threadIdx.x & 31;
+  const long w = (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5);
+  if (w >= (long)a.P * n_ac) return;
+  const long p = w / n_ac;
+  const int ac = (int)(w % n_ac);
+  const double h = a.p.h, wx = a.p.wind[0], wy = a.p.wind[1];
+  const size_t ou = (size_t)p * 2 * n_ac * N, ox = (size_t)p * 3 * n_ac * N, ob = ((size_t)p * 3) * n_ac;
+  const double* phi_in = a.u + ou + (size_t)ac * N;
+  const double* v_in = a.u + ou + (size_t)(n_ac + ac) * N;
+  double* xo = a.xs + ox + (size_t)(0 * n_ac + ac) * N;
+  double* yo = a.xs + ox + (size_t)(1 * n_ac + ac) * N;
+  double* po = a.xs + ox + (size_t)(2 * n_ac + ac) * N;
+  double cx = a.p0[ob + 0 * n_ac + ac], cy = a.p0[ob + 1 * n_ac + ac], cpsi = a.p0[ob + 2 * n_ac + ac];   // carries
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < N;
+    double ph = 0.0, vv = 1.0, s, c;
+    if (valid) {
+      ph = phi_in[i]; vv = v_in[i];
+      if (a.bounded) {
+        sincos_any(ph, s, c); ph = a.mid[0] + a.half[0] * s;
+        sincos_any(vv, s, c); vv = a.mid[1] + a.half[1] * s;
+        a.uphys[ou + (size_t)ac * N + i] = ph; a.uphys[ou + (size_t)(n_ac + ac) * N + i] = vv;
+      }
+    }
+    const bool moves = valid && i > 0;                       // node 0 is the initial state
+    double sp, cp;
+    sincos_any(ph, sp, cp);
+    const double dpsi = moves ? h * kG * sp * rcp_f(cp * vv) : 0.0;
+    const double psi = cpsi + warp_prefix(dpsi, lane);
+    sincos_any(psi, s, c);
+    const double x = cx + warp_prefix(moves ? h * (vv * c - wx) : 0.0, lane);
+    const double y = cy + warp_prefix(moves ? h * (vv * s - wy) : 0.0, lane);
+    if (valid) { xo[i] = x; yo[i] = y; po[i] = psi; }
+    cpsi = __shfl_sync(0xffffffffu, psi, 31); cx = __shfl_sync(0xffffffffu, x, 31); cy = __shfl_sync(0xffffffffu, y, 31);
+  }
+  if (lane == 0) {
+    a.c[ob + 0 * n_ac + ac] = cx - a.p1[ob + 0 * n_ac + ac];
+    a.c[ob + 1 * n_ac + ac] = cy - a.p1[ob + 1 * n_ac + ac];
+    a.c[ob + 2 * n_ac + ac] = cpsi - a.p1[ob + 2 * n_ac + ac];
+  }
 }
 
 __global__ void __launch_bounds__(kShootThreads) shoot_adjoint_kernel(const __grid_constant__ ShootArgs a) {
   const d2dx_colloc_problem& Q = a.p;
-  const int N = Q.N, n_ac = Q.n_ac;
-  const size_t P = a.P;
-  const size_t t = (size_t)blockIdx.x * kShootThreads + threadIdx.x;
-  if (t >= P * n_ac) return;
-  const size_t p = t % P;
-  const int ac = (int)(t / P);
+  const int N = Q.N, n_ac = Q.n_ac, lane = threadIdx.x & 31;
+  const long w = (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5);
+  if (w >= (long)a.P * n_ac) return;
+  const long p = w / n_ac;
+  const int ac = (int)(w % n_ac);
   const double h = Q.h;
   const double sN = Q.obj_scale / N, norm_in = sN / Q.in_div;
   const bool use_obs = on(Q.kobs) && Q.n_obs > 0 && ac == 0;
   const bool use_col = on(Q.kcol) && n_ac > 1 && (Q.col_all_pairs || ac < 2);
+  const int b_lo = Q.col_all_pairs ? 0 : (ac == 0 ? 1 : 0), b_hi = Q.col_all_pairs ? n_ac : (ac == 0 ? 2 : 1);
   const double col_kr = Q.kcol_k / Q.rcol;
-  const double* uin = a.bounded ? a.uphys : a.u;
-  auto U = [&](int k, int b, int i) { return uin[((k * (size_t)n_ac + b) * N + i) * P + p]; };
-  auto XS = [&](int k, int b, int i) { return a.xs[((k * (size_t)n_ac + b) * N + i) * P + p]; };
+  const size_t ou = (size_t)p * 2 * n_ac * N, ox = (size_t)p * 3 * n_ac * N, ob = ((size_t)p * 3) * n_ac;
+  const double* uin = (a.bounded ? a.uphys : a.u) + ou;
+  const double* xs = a.xs + ox;
   const double rho = a.rho[p];
   double cterm[3], gl[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    cterm[k] = a.c[(k * (size_t)n_ac + ac) * P + p];
-    gl[k] = a.lam[(k * (size_t)n_ac + ac) * P + p] + rho * cterm[k];          // d lagr / d terminal state
+    cterm[k] = a.c[ob + k * n_ac + ac];
+    gl[k] = a.lam[ob + k * n_ac + ac] + rho * cterm[k];                         // d lagr / d terminal state
   }
-  double Gx = gl[0], Gy = gl[1], Gp = gl[2];
+  double Gx_c = gl[0], Gy_c = gl[1], Gp_c = gl[2];                              // carries: sums over the rows already done
   double cost = 0.0;
-  for (int i = N - 1; i >= 0; --i) {
-    const double x = XS(0, ac, i), y = XS(1, ac, i), psi = XS(2, ac, i), phi = U(0, ac, i), v = U(1, ac, i);
-    // direct cost terms at this node and their position gradient
+  for (int base = ((N - 1) / 32) * 32; base >= 0; base -= 32) {
+    const int i = base + lane;
+    const bool valid = i < N, moves = valid && i > 0;
+    double x = 0, y = 0, psi = 0, phi = 0, v = 1;
+    if (valid) {
+      x = xs[(size_t)(0 * n_ac + ac) * N + i]; y = xs[(size_t)(1 * n_ac + ac) * N + i]; psi = xs[(size_t)(2 * n_ac + ac) * N + i];
+      phi = uin[(size_t)ac * N + i]; v = uin[(size_t)(n_ac + ac) * N + i];
+    }
     const double dv = v - Q.vsp;
-    cost += norm_in * (Q.kvel * dv * dv + Q.kbank * phi * phi);
     double ax = 0.0, ay = 0.0;
-    if (use_obs) {
-      for (int o = 0; o < Q.n_obs; ++o) {
-        const double dx = x - Q.obs[o][0], dy = y - Q.obs[o][1], r = Q.obs[o][2];
-        if (Q.obs_kind == 0) {
-          const double raw = exp(r * r - (dx * dx + dy * dy));
-          const double es = clip(raw, 0.0, 1e3);
-          cost += Q.kobs * sN * es;
-          if (raw < 1e3) { ax += Q.kobs * sN * -2.0 * dx * es; ay += Q.kobs * sN * -2.0 * dy * es; }   // flat where the clip is active
-        } else {
-          const double kr = 2.0 / r, ux = dx * kr, uy = dy * kr;
+    if (valid) {
+      cost += norm_in * (Q.kvel * dv * dv + Q.kbank * phi * phi);
+      if (use_obs) {
+        for (int o = 0; o < Q.n_obs; ++o) {
+          const double dx = x - Q.obs[o][0], dy = y - Q.obs[o][1], r = Q.obs[o][2];
+          if (Q.obs_kind == 0) {
+            const double raw = exp(r * r - (dx * dx + dy * dy));
+            const double es = clip(raw, 0.0, 1e3);
+            cost += Q.kobs * sN * es;
+            if (raw < 1e3) { ax += Q.kobs * sN * -2.0 * dx * es; ay += Q.kobs * sN * -2.0 * dy * es; }   // flat where the clip is active
+          } else {
+            const double kr = 2.0 / r, ux = dx * kr, uy = dy * kr;
+            const double es = fm::exp_neg(-(ux * ux + uy * uy));
+            cost += Q.kobs * sN * es;
+            ax += Q.kobs * sN * -2.0 * kr * kr * dx * es; ay += Q.kobs * sN * -2.0 * kr * kr * dy * es;
+          }
+        }
+      }
+      if (use_col) {
+        for (int b = b_lo; b < b_hi; ++b) {
+          if (b == ac) continue;
+          const double dx = x - xs[(size_t)(0 * n_ac + b) * N + i], dy = y - xs[(size_t)(1 * n_ac + b) * N + i];
+          const double ux = dx * col_kr, uy = dy * col_kr;
           const double es = fm::exp_neg(-(ux * ux + uy * uy));
-          cost += Q.kobs * sN * es;
-          ax += Q.kobs * sN * -2.0 * kr * kr * dx * es; ay += Q.kobs * sN * -2.0 * kr * kr * dy * es;
+          if (ac < b) cost += Q.kcol * sN * es;                                 // each pair counted once
+          ax += Q.kcol * sN * -2.0 * col_kr * col_kr * dx * es; ay += Q.kcol * sN * -2.0 * col_kr * col_kr * dy * es;
         }
       }
     }
-    if (use_col) {
-      const int b_lo = Q.col_all_pairs ? 0 : (ac == 0 ? 1 : 0), b_hi = Q.col_all_pairs ? n_ac : (ac == 0 ? 2 : 1);
-      for (int b = b_lo; b < b_hi; ++b) {
-        if (b == ac) continue;
-        const double dx = x - XS(0, b, i), dy = y - XS(1, b, i);
-        const double ux = dx * col_kr, uy = dy * col_kr;
-        const double es = fm::exp_neg(-(ux * ux + uy * uy));
-        if (ac < b) cost += Q.kcol * sN * es;                                   // each pair counted once
-        ax += Q.kcol * sN * -2.0 * col_kr * col_kr * dx * es; ay += Q.kcol * sN * -2.0 * col_kr * col_kr * dy * es;
-      }
-    }
-    double* gphi = a.grad + ((0 * (size_t)n_ac + ac) * N + i) * P + p;
-    double* gv = a.grad + ((1 * (size_t)n_ac + ac) * N + i) * P + p;
-    const double dphi_cost = norm_in * Q.kbank * 2.0 * phi, dv_cost = norm_in * Q.kvel * 2.0 * dv;
-    double jphi = 1.0, jv = 1.0;                                                 // d(phi, v) / d theta
-    if (a.bounded) {
-      double s_, c_;
-      sincos_any(a.u[((0 * (size_t)n_ac + ac) * N + i) * P + p], s_, c_); jphi = a.half[0] * c_;
-      sincos_any(a.u[((1 * (size_t)n_ac + ac) * N + i) * P + p], s_, c_); jv = a.half[1] * c_;
-    }
-    if (i == 0) { *gphi = dphi_cost * jphi; *gv = dv_cost * jv; break; }                    // node 0: fixed state, inputs enter the cost only
-    if (i < N - 1) { Gx += ax; Gy += ay; } else { Gx = gl[0] + ax; Gy = gl[1] + ay; }
+    if (!moves) { ax = 0.0; ay = 0.0; }                                         // node 0 is fixed
+    const double Gx = Gx_c + warp_suffix(ax, lane), Gy = Gy_c + warp_suffix(ay, lane);
     double s, c, sp, cp;
     sincos_any(psi, s, c);
     sincos_any(phi, sp, cp);
-    Gp += Gx * (-h * v * s) + Gy * (h * v * c);                                  // x_i, y_i depend on psi_i
-    const double icv = rcp_f(cp * v);
-    *gphi = (Gp * h * kG * icv * rcp_f(cp) + dphi_cost) * jphi;                  // d psi_i / d phi_i = h g / (v cos^2 phi)
-    *gv = (Gp * (-h * kG * sp * icv * rcp_f(v)) + Gx * h * c + Gy * h * s + dv_cost) * jv;
+    const double m = moves ? Gx * (-h * v * s) + Gy * (h * v * c) : 0.0;        // x_i, y_i depend on psi_i
+    const double Gp = Gp_c + warp_suffix(m, lane);
+    if (valid) {
+      double jphi = 1.0, jv = 1.0;                                              // d(phi, v) / d theta
+      if (a.bounded) {
+        double s_, c_;
+        sincos_any(a.u[ou + (size_t)ac * N + i], s_, c_); jphi = a.half[0] * c_;
+        sincos_any(a.u[ou + (size_t)(n_ac + ac) * N + i], s_, c_); jv = a.half[1] * c_;
+      }
+      const double dphi_cost = norm_in * Q.kbank * 2.0 * phi, dv_cost = norm_in * Q.kvel * 2.0 * dv;
+      double gphi = dphi_cost, gv = dv_cost;
+      if (moves) {
+        const double icv = rcp_f(cp * v);
+        gphi += Gp * h * kG * icv * rcp_f(cp);                                  // d psi_i / d phi_i = h g / (v cos^2 phi)
+        gv += Gp * (-h * kG * sp * icv * rcp_f(v)) + Gx * h * c + Gy * h * s;
+      }
+      a.grad[ou + (size_t)ac * N + i] = gphi * jphi;
+      a.grad[ou + (size_t)(n_ac + ac) * N + i] = gv * jv;
+    }
+    Gx_c = __shfl_sync(0xffffffffu, Gx, 0); Gy_c = __shfl_sync(0xffffffffu, Gy, 0); Gp_c = __shfl_sync(0xffffffffu, Gp, 0);
   }
-  // lagrangian share of this aircraft
-  double lg = cost;
+  cost = warp_sum(cost);
+  if (lane == 0) {
+    double lg = cost;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) lg += a.lam[(k * (size_t)n_ac + ac) * P + p] * cterm[k] + 0.5 * rho * cterm[k] * cterm[k];
-  atomicAdd(a.cost + p, cost);
-  atomicAdd(a.lagr + p, lg);
+    for (int k = 0; k < 3; ++k) lg += a.lam[ob + k * n_ac + ac] * cterm[k] + 0.5 * rho * cterm[k] * cterm[k];
+    a.cost[(size_t)p * n_ac + ac] = cost;                                       // per-aircraft shares: the caller sums them in order
+    a.lagr[(size_t)p * n_ac + ac] = lg;
+  }
 }
 
 static void set_bounds(ShootArgs& a, const double* b) {
@@ -153,6 +199,8 @@ static int check(const d2dx_colloc_problem* p, int P, const char* who) {
   return D2DX_OK;
 }
 
+static unsigned shoot_grid(const d2dx_colloc_problem* p, int P) { return (unsigned)(((long)P * p->n_ac + kShootWarps - 1) / kShootWarps); }
+
 }  // namespace d2dx
 
 using namespace d2dx;
@@ -166,8 +214,7 @@ extern "C" int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p, 
   set_bounds(a, bounds);
   a.p = *p; a.P = P; a.u = u; a.p0 = p0; a.p1 = p1; a.uphys = u_phys; a.xs = xs; a.c = c;
   D2DX_CUDA(cudaSetDevice(h->device));
-  const long n = (long)P * p->n_ac;
-  shoot_forward_kernel<<<(unsigned)((n + kShootThreads - 1) / kShootThreads), kShootThreads, 0, as_stream(stream)>>>(a);
+  shoot_forward_kernel<<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
   D2DX_LAUNCH_CHECK("shoot_forward_kernel");
   return D2DX_OK;
 }
@@ -181,12 +228,10 @@ extern "C" int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p, 
   ShootArgs a = {};
   set_bounds(a, bounds);
   a.uphys = const_cast<double*>(u_phys);
-  a.p = *p; a.P = P; a.u = u; a.xs = const_cast<double*>(xs); a.c = const_cast<double*>(c); a.lam = lam; a.rho = rho; a.cost = cost; a.lagr = lagr; a.grad = grad;
+  a.p = *p; a.P = P; a.u = u; a.xs = const_cast<double*>(xs); a.c = const_cast<double*>(c); a.lam = lam;
+  a.rho = rho; a.cost = cost; a.lagr = lagr; a.grad = grad;
   D2DX_CUDA(cudaSetDevice(h->device));
-  D2DX_CUDA(cudaMemsetAsync(cost, 0, sizeof(double) * P, as_stream(stream)));
-  D2DX_CUDA(cudaMemsetAsync(lagr, 0, sizeof(double) * P, as_stream(stream)));
-  const long n = (long)P * p->n_ac;
-  shoot_adjoint_kernel<<<(unsigned)((n + kShootThreads - 1) / kShootThreads), kShootThreads, 0, as_stream(stream)>>>(a);
+  shoot_adjoint_kernel<<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
   D2DX_LAUNCH_CHECK("shoot_adjoint_kernel");
   return D2DX_OK;
 }

@@ -295,6 +295,19 @@ class Engine:
         check(lib.d2dx_shoot_adjoint(self.h, C.byref(prob), P, _ptr(u), b, _ptr(u_phys), _ptr(xs), _ptr(c), _ptr(lam), _ptr(rho),
                                      _ptr(cost), _ptr(lagr), _ptr(grad), self.stream_ptr()), "d2dx_shoot_adjoint")
 
+    def lbfgs_layout(self, P, n, n_con, opts):
+        off = (C.c_int64 * 8)()
+        check(lib.d2dx_lbfgs_layout(P, n, n_con, C.byref(opts), off), "d2dx_lbfgs_layout")
+        return list(off)
+
+    def lbfgs_init(self, P, n, n_con, opts, state, lam, rho):
+        check(lib.d2dx_lbfgs_init(self.h, P, n, n_con, C.byref(opts), _ptr(state), _ptr(lam), _ptr(rho), self.stream_ptr()), "d2dx_lbfgs_init")
+
+    def al_lbfgs_tick(self, P, n, n_con, opts, state, x_trial, f_parts, cost_parts, n_parts, grad, c, lam, rho, n_running):
+        check(lib.d2dx_al_lbfgs_tick(self.h, P, n, n_con, C.byref(opts), _ptr(state), _ptr(x_trial), _ptr(f_parts), _ptr(cost_parts),
+                                     n_parts, _ptr(grad), _ptr(c), _ptr(lam), _ptr(rho), _ptr(n_running), self.stream_ptr()),
+              "d2dx_al_lbfgs_tick")
+
     def math_probe(self, x, y):
         """Engine elementary functions on device arrays x, y -> [7][n] (sin, cos, atan2(y,x), atan x, y/x, sqrt|x|, rsqrt|x|)."""
         n = x.numel(); out = self.empty(7, n)

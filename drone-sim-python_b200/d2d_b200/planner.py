@@ -29,19 +29,20 @@ class _PlannerBase:
         checked on the result and reported in `self.info["state_bounds_ok"]`."""
         guess = self.get_initial_guess() if initial_guess is None else np.asarray(initial_guess, dtype=float)
         n, N = self._n_ac, self.num_nodes
-        phi = np.stack([guess[sl] for sl in self._phi_slices()])[:, :, None]
-        v = np.stack([guess[sl] for sl in self._v_slices()])[:, :, None]
+        phi = np.stack([guess[sl] for sl in self._phi_slices()])[None]
+        v = np.stack([guess[sl] for sl in self._v_slices()])[None]
         phi_b, v_b = self._bounds["phi"], self._bounds["v"]
         if n_starts > 1:
             rng = np.random.default_rng(seed)
-            k = np.concatenate([[0.], np.ones(n_starts - 1)])                     # start 0 is the caller's guess
-            phi = phi + k * rng.normal(0., 0.25 * (phi_b[1] - phi_b[0]), (n, 1, n_starts))
-            v = v + k * rng.normal(0., 0.25 * (v_b[1] - v_b[0]), (n, 1, n_starts))
+            k = np.concatenate([[0.], np.ones(n_starts - 1)])[:, None, None]      # start 0 is the caller's guess
+            phi = phi + k * rng.normal(0., 0.25 * (phi_b[1] - phi_b[0]), (n_starts, n, 1))
+            v = v + k * rng.normal(0., 0.25 * (v_b[1] - v_b[0]), (n_starts, n, 1))
         p0, p1 = self._boundary_states()
         nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts)
         tol = getattr(self, "tol", 1e-8)
-        theta, info = shooting.solve(nlp, nlp.theta_of(np.clip(phi, *phi_b), np.clip(v, *v_b)), ctol=min(tol, 1e-6),
-                                     max_inner=min(getattr(self, "max_iter", 3000), 500), verbose=verbose)
+        driver = shooting.solve_host if _.get("driver") == "host" else shooting.solve
+        theta, info = driver(nlp, nlp.theta_of(np.clip(phi, *phi_b), np.clip(v, *v_b)), ctol=min(tol, 1e-6),
+                             max_inner=min(getattr(self, "max_iter", 3000), 500), verbose=verbose)
         frees = nlp.free_vectors()
         if self.prob.c.perm_phi:                                                  # opty input order: place the input blocks by rank
             frees = self._to_opty_order(frees)

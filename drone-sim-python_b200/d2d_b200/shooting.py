@@ -16,7 +16,8 @@ import torch
 
 class ShootingNLP:
     """P simultaneous problems sharing one description (`prob`: a CollocationProblem, which supplies n_ac, N, h, wind
-    and the cost).  p0, p1: (3, n_ac) or (3, n_ac, P) initial states / terminal targets (x, y, psi)."""
+    and the cost).  p0, p1: (3, n_ac) or (P, 3, n_ac) initial states / terminal targets (x, y, psi).
+    Device arrays are problem-major (include/d2dx.h): theta/u_phys/grad (P, 2, n_ac, N), xs (P, 3, n_ac, N)."""
 
     def __init__(self, prob, p0, p1, phi_bounds, v_bounds, P=1, engine=None):
         self.eng = e = engine or prob.eng
@@ -26,39 +27,45 @@ class ShootingNLP:
         self.mid = np.array([0.5 * (self.bounds[0] + self.bounds[1]), 0.5 * (self.bounds[2] + self.bounds[3])])
         self.half = np.array([0.5 * (self.bounds[1] - self.bounds[0]), 0.5 * (self.bounds[3] - self.bounds[2])])
         bc = lambda a: e.to_device(np.ascontiguousarray(np.broadcast_to(
-            np.asarray(a, np.float64).reshape(3, self.n_ac, -1), (3, self.n_ac, self.P))))
+            np.asarray(a, np.float64).reshape(-1, 3, self.n_ac), (self.P, 3, self.n_ac))))
         self.p0, self.p1 = bc(p0), bc(p1)
         n_ac, N = self.n_ac, self.N
-        self.n = 2 * n_ac * N
-        self.u_phys, self.xs = e.empty(2, n_ac, N, self.P), e.empty(3, n_ac, N, self.P)
-        self.c = e.empty(3, n_ac, self.P)
-        self.lam, self.rho = e.zeros(3, n_ac, self.P), e.zeros(self.P) + 10.
-        self.cost, self.lagr, self.grad = e.empty(self.P), e.empty(self.P), e.empty(2, n_ac, N, self.P)
+        self.n, self.n_con = 2 * n_ac * N, 3 * n_ac
+        self.u_phys, self.xs = e.empty(self.P, 2, n_ac, N), e.empty(self.P, 3, n_ac, N)
+        self.c = e.empty(self.P, 3, n_ac)
+        self.lam, self.rho = e.zeros(self.P, 3, n_ac), e.zeros(self.P) + 10.
+        self.cost_ac, self.lagr_ac, self.grad = e.empty(self.P, n_ac), e.empty(self.P, n_ac), e.empty(self.P, 2, n_ac, N)
         self.nfev = 0
 
     # ---- variables ------------------------------------------------------------------------------------
     def theta_of(self, phi, v):
-        """host (n_ac, N[, P]) physical inputs -> device theta (n, P); values are clipped just inside the bounds."""
-        u = np.stack([np.asarray(phi, np.float64).reshape(self.n_ac, self.N, -1), np.asarray(v, np.float64).reshape(self.n_ac, self.N, -1)])
-        s = (u - self.mid[:, None, None, None]) / self.half[:, None, None, None]
+        """host (n_ac, N) or (P, n_ac, N) physical inputs -> device theta (P, n); values are clipped just inside the bounds."""
+        u = np.stack([np.asarray(phi, np.float64).reshape(-1, self.n_ac, self.N), np.asarray(v, np.float64).reshape(-1, self.n_ac, self.N)], 1)
+        s = (u - self.mid[None, :, None, None]) / self.half[None, :, None, None]
         th = np.arcsin(np.clip(s, -0.999, 0.999))
-        return self.eng.to_device(np.ascontiguousarray(np.broadcast_to(th, (2, self.n_ac, self.N, self.P)))).reshape(self.n, self.P)
+        return self.eng.to_device(np.ascontiguousarray(np.broadcast_to(th, (self.P, 2, self.n_ac, self.N)))).reshape(self.P, self.n)
 
-    def evaluate(self, theta):
-        """theta: device (n, P).  Returns fresh (lagrangian (P,), gradient (n, P)); cost, c, xs, u_phys stay in the buffers."""
+    def launch(self, theta):
+        """the two kernels of one evaluation at theta (P, n); results stay in the buffers (graph-capturable)."""
         e = self.eng
         e.shoot_forward(self.c_prob, self.P, theta, self.bounds, self.p0, self.p1, self.u_phys, self.xs, self.c)
         e.shoot_adjoint(self.c_prob, self.P, theta, self.bounds, self.u_phys, self.xs, self.c, self.lam, self.rho,
-                        self.cost, self.lagr, self.grad)
+                        self.cost_ac, self.lagr_ac, self.grad)
         self.nfev += 1
-        return self.lagr.clone(), self.grad.reshape(self.n, self.P).clone()
+
+    def evaluate(self, theta):
+        """theta: device (P, n).  Returns fresh (lagrangian (P,), gradient (P, n))."""
+        self.launch(theta)
+        return self.lagr_ac.sum(1), self.grad.reshape(self.P, self.n).clone()
+
+    @property
+    def cost(self): return self.cost_ac.sum(1)
 
     def free_vectors(self):
         """(P, num_free) host array in the planner's layout [x,y,psi per aircraft | phi per aircraft | v per aircraft]
         from the last evaluation."""
-        xs = self.xs.permute(3, 1, 0, 2).reshape(self.P, -1)                      # [P][ac][k][N]
-        u = self.u_phys.permute(3, 0, 1, 2).reshape(self.P, -1)                   # [P][phi|v][ac][N]
-        return torch.cat([xs, u], dim=1).cpu().numpy()
+        xs = self.xs.permute(0, 2, 1, 3).reshape(self.P, -1)                      # [P][ac][k][N]
+        return torch.cat([xs, self.u_phys.reshape(self.P, -1)], dim=1).cpu().numpy()
 
 
 def lbfgs(fun, x, m=20, maxit=500, gtol=1e-10, ftol=1e-10, window=10, ls_max=30):
@@ -123,26 +130,81 @@ def lbfgs(fun, x, m=20, maxit=500, gtol=1e-10, ftol=1e-10, window=10, ls_max=30)
     return x, f, g, it
 
 
-def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner=500, rho0=10., rho_max=1e6, m=20, verbose=False):
-    """Augmented-Lagrangian loop around `lbfgs`.  Returns theta and an info dict; `nlp.free_vectors()` then gives the
-    planner-layout solutions.  Per problem: lam += rho c after each inner solve; rho x3 (up to rho_max) when |c| did
-    not fall to a quarter of its previous value."""
+def solve_host(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner=500, rho0=10., rho_max=1e6, m=20, verbose=False):
+    """Augmented-Lagrangian loop around the torch `lbfgs` (lock-step line searches, host decisions every iteration) --
+    the cross-check of `solve`; same update rules."""
     nlp.lam.zero_()
     nlp.rho.fill_(rho0)
     total, c_prev = 0, None
+
+    def fun(xT):
+        f, g = nlp.evaluate(xT.t().contiguous())
+        return f, g.t().contiguous()
     for outer in range(max_outer):
-        theta, f, g, it = lbfgs(nlp.evaluate, theta, m=m, maxit=max_inner, gtol=gtol, ftol=ftol)
+        xT, f, g, it = lbfgs(fun, theta.t().contiguous(), m=m, maxit=max_inner, gtol=gtol, ftol=ftol)
+        theta = xT.t().contiguous()
         total += it
-        nlp.evaluate(theta)                                                      # buffers at the returned point
-        cmax = nlp.c.abs().amax(dim=(0, 1))
+        nlp.launch(theta)                                                        # buffers at the returned point
+        cmax = nlp.c.abs().amax(dim=(1, 2))
         if verbose:
             print(f"outer {outer}: inner its {it}, cost {nlp.cost.min().item():.6e}..{nlp.cost.max().item():.6e}, "
                   f"|c| {cmax.max().item():.2e}, rho {nlp.rho.max().item():.0f}")
         if bool((cmax < ctol).all()):
             break
-        nlp.lam += nlp.rho * nlp.c
+        nlp.lam += nlp.rho[:, None, None] * nlp.c
         slow = (cmax > ctol) & ((cmax > 0.25 * c_prev) if c_prev is not None else torch.ones_like(cmax, dtype=torch.bool))
         nlp.rho.copy_(torch.where(slow, (nlp.rho * 3).clamp_max(rho_max), nlp.rho))
         c_prev = cmax
     return theta, {"outer": outer + 1, "iterations": total, "nfev": nlp.nfev, "c_max": cmax.cpu().numpy(),
                    "cost": nlp.cost.cpu().numpy()}
+
+
+def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner=500, rho0=10., rho_max=1e6, m=20,
+          window=10, ls_max=30, ticks_per_check=64, max_ticks=None, use_graph=True, verbose=False):
+    """Device-resident solve: every tick = [d2dx_shoot_forward, d2dx_shoot_adjoint, d2dx_al_lbfgs_tick]; `ticks_per_check`
+    ticks are captured in one CUDA graph and replayed until no problem is iterating (one host read per replay).
+    Problems advance independently (own line search, multipliers, termination).  Returns theta (P, n) at the solutions
+    and an info dict; `nlp.free_vectors()` then gives the planner-layout solutions."""
+    from . import _lib
+    e, P, n, n_con = nlp.eng, nlp.P, nlp.n, nlp.n_con
+    o = _lib.LbfgsOptions(m=m, max_inner=max_inner, max_outer=max_outer, ls_max=ls_max, window=window, gtol=gtol, ftol=ftol,
+                          ctol=ctol, rho0=rho0, rho_max=rho_max)
+    off = e.lbfgs_layout(P, n, n_con, o)
+    state = e.empty(off[0])
+    n_running = e.zeros(1, dtype=torch.int32)
+    xt = theta.reshape(P, n).clone()
+    e.lbfgs_init(P, n, n_con, o, state, nlp.lam, nlp.rho)
+
+    def tick():
+        nlp.launch(xt)
+        e.al_lbfgs_tick(P, n, n_con, o, state, xt, nlp.lagr_ac, nlp.cost_ac, nlp.n_ac, nlp.grad, nlp.c, nlp.lam, nlp.rho, n_running)
+
+    def ticks():
+        for _ in range(ticks_per_check):
+            tick()
+    tick()                                                                       # warm-up outside the capture (lazy module load)
+    torch.cuda.synchronize(e.device)
+    replay = ticks
+    if use_graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=torch.cuda.Stream(device=e.device)):
+            ticks()
+        replay = g.replay
+    max_ticks = max_ticks or int(1.5 * max_outer * max_inner)
+    done_ticks = 1
+    while done_ticks < max_ticks:
+        replay()
+        done_ticks += ticks_per_check
+        running = int(n_running.item())
+        if verbose:
+            print(f"ticks {done_ticks}: {running} of {P} problems iterating")
+        if running == 0:
+            break
+    sc = state[off[3]:off[3] + P * off[6]].view(P, off[6])
+    meta = state[off[5]:off[5] + P * off[7] // 2].view(torch.int32).view(P, off[7])
+    theta = state[off[1]:off[1] + P * n].view(P, n).clone()
+    nlp.launch(theta)                                                            # buffers (states, physical inputs, c) at the solutions
+    meta_h = meta.cpu().numpy()
+    return theta, {"outer": int(meta_h[:, 6].max()), "iterations": int(meta_h[:, 10].max()), "nfev": int(meta_h[:, 5].max()),
+                   "ticks": done_ticks, "flag": meta_h[:, 0].copy(), "iterations_each": meta_h[:, 10].copy(),
+                   "c_max": nlp.c.abs().amax(dim=(1, 2)).cpu().numpy(), "cost": nlp.cost.cpu().numpy()}

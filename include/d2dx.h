@@ -313,14 +313,14 @@ int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const do
 /* -------- single-shooting evaluation of the planner NLP --------
  * On the backward-Euler grid the defects of d2dx_colloc_eval determine the states from the inputs:
  *   psi_i = psi_{i-1} + h g tan(phi_i)/v_i,  x_i = x_{i-1} + h (v_i cos psi_i - w_x),  y_i = y_{i-1} + h (v_i sin psi_i - w_y),
- * so a solver can iterate on the inputs only.  For P problems at once (problem index fastest):
- *   u[2][n_ac][N][P]      inputs phi, v at every node (node 0 enters the cost only)
- *   p0[3][n_ac][P], p1[3][n_ac][P]   initial state and terminal target (x, y, psi) of each aircraft
- *   lam[3][n_ac][P], rho[P]          augmented-Lagrangian multipliers / penalty of the terminal constraints
- * d2dx_shoot_forward fills xs[3][n_ac][N][P] (x, y, psi) and c[3][n_ac][P] = state(N-1) - p1.
- * d2dx_shoot_adjoint (after forward, same arguments) returns
- *   cost[P]  = planner cost of d2dx_colloc_problem (exact value) ,
- *   lagr[P]  = cost + sum lam.c + rho/2 |c|^2 ,   grad[2][n_ac][N][P] = d lagr / d u   (exact derivatives).
+ * so a solver can iterate on the inputs only.  For P problems at once (problem-major, node index fastest):
+ *   u[P][2][n_ac][N]      inputs phi, v at every node (node 0 enters the cost only)
+ *   p0[P][3][n_ac], p1[P][3][n_ac]   initial state and terminal target (x, y, psi) of each aircraft
+ *   lam[P][3][n_ac], rho[P]          augmented-Lagrangian multipliers / penalty of the terminal constraints
+ * d2dx_shoot_forward fills xs[P][3][n_ac][N] (x, y, psi) and c[P][3][n_ac] = state(N-1) - p1.
+ * d2dx_shoot_adjoint (after forward, same arguments) returns per-aircraft shares (sum over n_ac = the totals)
+ *   cost[P][n_ac]  of the planner cost of d2dx_colloc_problem (exact value),
+ *   lagr[P][n_ac]  of cost + sum lam.c + rho/2 |c|^2,   and grad[P][2][n_ac][N] = d lagr / d u   (exact derivatives).
  * `p_host` supplies n_ac, N, h, wind and the cost description (instance constraints, permutations and exact_grad are
  * ignored: the terminal targets come from p1, gradients are always exact).
  * Box constraints by substitution: with `bounds` = {phi_lo, phi_hi, v_lo, v_hi} (HOST array; NULL = none) `u` holds
@@ -331,6 +331,35 @@ int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_
 int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t P, const double* u, const double* bounds,
                        const double* u_phys, const double* xs, const double* c, const double* lam, const double* rho,
                        double* cost, double* lagr, double* grad, void* stream);
+
+/* -------- batched augmented-Lagrangian L-BFGS driver (the solver behind Planner.run; replaces prob.solve -> IPOPT,
+ * 06_optyplan.py:117-125, 07_multioptyplan.py:80-88) --------
+ * P independent problems  min f(x) s.t. c(x) = 0, x in R^n, n_con constraints each.  The caller evaluates the augmented
+ * Lagrangian L = f + lam.c + rho/2 |c|^2, its gradient and c at `x_trial`; one tick consumes that evaluation and writes
+ * the next point to evaluate into x_trial (L-BFGS direction, Armijo backtracking, multiplier/penalty updates and the
+ * termination tests are per problem, on the device).  [evaluate, tick] has no host decision inside and can be captured
+ * in a CUDA graph; *n_running (device) holds the number of problems still iterating after each tick. */
+typedef struct {
+  int32_t m;            /* history pairs (1..64) */
+  int32_t max_inner;    /* accepted steps per multiplier update */
+  int32_t max_outer;    /* multiplier updates */
+  int32_t ls_max;       /* halvings per line search */
+  int32_t window;       /* inner loop stops when L fell by < ftol max(1,|L|) over `window` accepted steps ... */
+  double gtol;          /* ... or |grad|_inf <= gtol */
+  double ftol;
+  double ctol;          /* a problem is solved when max|c| < ctol after an inner loop */
+  double rho0, rho_max; /* penalty: starts at rho0, x3 (up to rho_max) when max|c| did not fall to a quarter */
+} d2dx_lbfgs_options;
+/* offsets (in doubles) into the state buffer: [0] total size, [1] x[P][n], [2] g[P][n], [3] scalars[P][offsets[6]]
+ * (0 L, 4 previous max|c|, 5 max|c|, 6 cost), [4] c at x [P][n_con], [5] int32 meta[P][offsets[7]]
+ * (0 flag: 0/1 iterating, 2 solved, 3 stopped unsolved; 5 evaluations; 6 multiplier updates; 10 accepted steps). */
+int d2dx_lbfgs_layout(int32_t P, int32_t n, int32_t n_con, const d2dx_lbfgs_options* o, int64_t offsets[8]);
+int d2dx_lbfgs_init(d2dx_handle* h, int32_t P, int32_t n, int32_t n_con, const d2dx_lbfgs_options* o, double* state,
+                    double* lam, double* rho, void* stream);
+/* f_parts[P][n_parts]: shares of L summed in index order; cost_parts (nullable): shares of f, reported in scalars[6]. */
+int d2dx_al_lbfgs_tick(d2dx_handle* h, int32_t P, int32_t n, int32_t n_con, const d2dx_lbfgs_options* o, double* state,
+                       double* x_trial, const double* f_parts, const double* cost_parts, int32_t n_parts, const double* grad,
+                       const double* c, double* lam, double* rho, int32_t* n_running, void* stream);
 
 /* -------- diagnostics -------- */
 /* FP64 roofline probe: every thread runs `iters` rounds of 16 independent DFMA chains (32*iters flop per

@@ -16,54 +16,58 @@ pytestmark = pytest.mark.gpu
 from oracle import d2d_oracle as orc  # noqa: E402
 
 
-def _setup(n_ac, N, P, bounded, seed=0):
+def _setup(n_ac, N, P, seed=0):
     from d2d_b200.collocation import CollocationProblem, CostSpec
     from d2d_b200.shooting import ShootingNLP
     rng = np.random.default_rng(seed)
     h, wind = 0.1, (1.0, -0.5)
     spec = dict(vsp=12., kvel=3., kbank=2., kcol=10., rcol=10., pairs="all", exact_grad=True, kobs=1.5,
-                obstacles=[(5., 2., 6.), (12., -3., 4.)], obs_kind=1)
+                obstacles=[(5., 2., 6.), (12., -3., 4.)], obs_kind=1, obj_scale=2.0)
     cs = CostSpec(vsp=12., kvel=3., kbank=2., kcol=10., rcol=10., all_pairs=True, kobs=1.5,
                   obstacles=[(5., 2., 6.), (12., -3., 4.)], obs_kind=1)
     prob = CollocationProblem(n_ac, N, h, wind=wind, cost=cs, obj_scale=2.0, multi=n_ac > 1)
-    spec["obj_scale"] = 2.0
-    p0 = rng.uniform(-5, 5, (3, n_ac, P)); p1 = rng.uniform(-5, 25, (3, n_ac, P))
+    p0 = rng.uniform(-5, 5, (P, 3, n_ac)); p1 = rng.uniform(-5, 25, (P, 3, n_ac))
     pb, vb = (-0.6, 0.5), (9., 15.)
     nlp = ShootingNLP(prob, p0, p1, pb, vb, P=P)
-    phi = rng.uniform(-0.4, 0.4, (n_ac, N, P)); v = rng.uniform(9.5, 14.5, (n_ac, N, P))
-    return prob, nlp, spec, h, wind, p0, p1, phi, v, (pb, vb), rng
+    phi = rng.uniform(-0.4, 0.4, (P, n_ac, N)); v = rng.uniform(9.5, 14.5, (P, n_ac, N))
+    return prob, nlp, spec, h, wind, p0, p1, phi, v, rng
 
 
-@pytest.mark.parametrize("n_ac,N,P", [(1, 40, 1), (3, 25, 4), (5, 12, 130)])
+def _fd(F):
+    """4th-order central difference of F(s) at s = 0 with step 1e-4."""
+    return (8 * (F(1) - F(-1)) - (F(2) - F(-2))) / 12e-4
+
+
+@pytest.mark.parametrize("n_ac,N,P", [(1, 40, 1), (3, 25, 4), (5, 12, 130), (2, 97, 3)])
 def test_shoot_value_and_gradient_against_oracle(n_ac, N, P):
     import torch
-    prob, nlp, spec, h, wind, p0, p1, phi, v, (pb, vb), rng = _setup(n_ac, N, P, True)
-    nlp.lam.copy_(torch.as_tensor(rng.normal(0, 1, (3, n_ac, P)))); nlp.rho.copy_(torch.as_tensor(rng.uniform(1, 50, P)))
+    prob, nlp, spec, h, wind, p0, p1, phi, v, rng = _setup(n_ac, N, P)
+    nlp.lam.copy_(torch.as_tensor(rng.normal(0, 1, (P, 3, n_ac)))); nlp.rho.copy_(torch.as_tensor(rng.uniform(1, 50, P)))
     lam, rho = nlp.lam.cpu().numpy(), nlp.rho.cpu().numpy()
     theta = nlp.theta_of(phi, v)
     L, g = nlp.evaluate(theta)
-    L, g, th = L.cpu().numpy(), g.cpu().numpy().reshape(2, n_ac, N, P), theta.cpu().numpy().reshape(2, n_ac, N, P)
+    L, g, th = L.cpu().numpy(), g.cpu().numpy().reshape(P, 2, n_ac, N), theta.cpu().numpy().reshape(P, 2, n_ac, N)
     cost, c = nlp.cost.cpu().numpy(), nlp.c.cpu().numpy()
     xs, up = nlp.xs.cpu().numpy(), nlp.u_phys.cpu().numpy()
     mid, half = nlp.mid, nlp.half
 
     def lag(thp, p):
         ph, vv = mid[0] + half[0] * np.sin(thp[0]), mid[1] + half[1] * np.sin(thp[1])
-        return orc.shoot_lagrangian(ph, vv, p0[:, :, p], p1[:, :, p], h, wind, spec, lam[:, :, p], rho[p], multi=n_ac > 1)
+        return orc.shoot_lagrangian(ph, vv, p0[p], p1[p], h, wind, spec, lam[p], rho[p], multi=n_ac > 1)
 
     for p in range(0, P, max(P // 4, 1)):
-        co, cc, Lo = lag(th[:, :, :, p], p)
+        co, cc, Lo = lag(th[p], p)
         assert abs(cost[p] - co) <= 1e-12 * max(1, abs(co))
-        np.testing.assert_allclose(c[:, :, p], cc, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(c[p], cc, rtol=0, atol=1e-11)
         assert abs(L[p] - Lo) <= 1e-11 * max(1, abs(Lo))
-        x, y, psi = orc.shoot_states(up[0, :, :, p], up[1, :, :, p], p0[:, :, p], h, wind)
-        np.testing.assert_allclose(xs[:, :, :, p], np.stack([x, y, psi]), rtol=0, atol=1e-11)
-        for _ in range(12):                                     # gradient: central differences of the oracle
-            k, a, i = rng.integers(2), rng.integers(n_ac), rng.integers(N)
-            e = np.zeros_like(th[:, :, :, p]); e[k, a, i] = 1e-4
-            F = lambda s_: lag(th[:, :, :, p] + s_ * e, p)[2]
-            fd = (8 * (F(1) - F(-1)) - (F(2) - F(-2))) / 12e-4     # 4th-order central difference
-            assert abs(g[k, a, i, p] - fd) <= 1e-7 * max(1., abs(fd)), (k, a, i, g[k, a, i, p], fd)
+        x, y, psi = orc.shoot_states(up[p, 0], up[p, 1], p0[p], h, wind)
+        np.testing.assert_allclose(xs[p], np.stack([x, y, psi]), rtol=0, atol=1e-11)
+        picks = [(0, 0, 0), (1, n_ac - 1, N - 1), (0, n_ac - 1, N - 1), (1, 0, 1)] + \
+                [(rng.integers(2), rng.integers(n_ac), rng.integers(N)) for _ in range(10)]
+        for (k, a, i) in picks:                                   # gradient: central differences of the oracle
+            e = np.zeros_like(th[p]); e[k, a, i] = 1e-4
+            fd = _fd(lambda s_: lag(th[p] + s_ * e, p)[2])
+            assert abs(g[p, k, a, i] - fd) <= 1e-7 * max(1., abs(fd)) + 2e-11 * abs(Lo), (k, a, i, g[p, k, a, i], fd)   # + FD rounding: ~4 eps |L| / step
     # the shooting point zeroes the defects of the collocation constraints (engine's own evaluator)
     res = prob.con(nlp.free_vectors())
     assert np.abs(res[:, :3 * n_ac * (N - 1)]).max() < 1e-10
@@ -71,22 +75,82 @@ def test_shoot_value_and_gradient_against_oracle(n_ac, N, P):
 
 def test_shoot_unbounded_gradient():
     """bounds = NULL: u are the physical inputs and the gradient is with respect to them."""
-    import torch
-    prob, nlp, spec, h, wind, p0, p1, phi, v, _, rng = _setup(2, 20, 2, False)
+    prob, nlp, spec, h, wind, p0, p1, phi, v, rng = _setup(2, 20, 2)
     e = nlp.eng
-    u = e.to_device(np.ascontiguousarray(np.stack([phi, v])))
+    u = e.to_device(np.ascontiguousarray(np.stack([phi, v], 1)))
     e.shoot_forward(prob.c, 2, u, None, nlp.p0, nlp.p1, None, nlp.xs, nlp.c)
     nlp.rho.fill_(7.0)
-    e.shoot_adjoint(prob.c, 2, u, None, None, nlp.xs, nlp.c, nlp.lam, nlp.rho, nlp.cost, nlp.lagr, nlp.grad)
-    g, L = nlp.grad.cpu().numpy(), nlp.lagr.cpu().numpy()
-    lag = lambda ph, vv, p: orc.shoot_lagrangian(ph, vv, p0[:, :, p], p1[:, :, p], h, wind, spec, np.zeros((3, 2)), 7.0, multi=True)[2]
+    e.shoot_adjoint(prob.c, 2, u, None, None, nlp.xs, nlp.c, nlp.lam, nlp.rho, nlp.cost_ac, nlp.lagr_ac, nlp.grad)
+    g, L = nlp.grad.cpu().numpy(), nlp.lagr_ac.sum(1).cpu().numpy()
+    lag = lambda ph, vv, p: orc.shoot_lagrangian(ph, vv, p0[p], p1[p], h, wind, spec, np.zeros((3, 2)), 7.0, multi=True)[2]
     for p in range(2):
-        assert abs(L[p] - lag(phi[:, :, p], v[:, :, p], p)) <= 1e-11 * abs(L[p])
+        assert abs(L[p] - lag(phi[p], v[p], p)) <= 1e-11 * abs(L[p])
         for (k, a, i) in ((0, 0, 3), (1, 1, 7), (0, 1, 19), (1, 0, 0), (1, 0, 19)):
             d = np.zeros((2, 2, 20)); d[k, a, i] = 1e-4
-            F = lambda s_: lag(phi[:, :, p] + s_ * d[0], v[:, :, p] + s_ * d[1], p)
-            fd = (8 * (F(1) - F(-1)) - (F(2) - F(-2))) / 12e-4
-            assert abs(g[k, a, i, p] - fd) <= 1e-7 * max(1., abs(fd))
+            fd = _fd(lambda s_: lag(phi[p] + s_ * d[0], v[p] + s_ * d[1], p))
+            assert abs(g[p, k, a, i] - fd) <= 1e-7 * max(1., abs(fd)) + 2e-11 * abs(L[p])
+
+
+def test_device_driver_on_analytic_problems():
+    """d2dx_al_lbfgs_tick alone, fed by torch-evaluated functions: min |x - a|^2 s.t. sum x = 1 and x_0 - x_1 = 0.5
+    (closed-form KKT solution), one problem per block, different data per problem."""
+    import torch
+    from d2d_b200 import _lib
+    from d2d_b200.engine import get_engine
+    e = get_engine()
+    P, n, n_con = 5, 40, 2
+    rng = np.random.default_rng(3)
+    a = torch.as_tensor(rng.normal(0, 1, (P, n)), device=e.device)
+    A = torch.zeros(n_con, n, dtype=torch.float64, device=e.device); A[0] = 1.0; A[1, 0], A[1, 1] = 1.0, -1.0
+    b = torch.tensor([1.0, 0.5], dtype=torch.float64, device=e.device)
+    o = _lib.LbfgsOptions(m=10, max_inner=200, max_outer=40, ls_max=30, window=10, gtol=1e-12, ftol=1e-15, ctol=1e-10, rho0=10., rho_max=1e6)
+    off = e.lbfgs_layout(P, n, n_con, o)
+    state, lam, rho, nrun = e.empty(off[0]), e.empty(P, n_con), e.empty(P), e.zeros(1, dtype=torch.int32)
+    e.lbfgs_init(P, n, n_con, o, state, lam, rho)
+    xt = e.zeros(P, n)
+    for tick in range(4000):
+        c = xt @ A.t() - b
+        f = ((xt - a) ** 2).sum(1)
+        L = f + (lam * c).sum(1) + 0.5 * rho * (c * c).sum(1)
+        g = 2 * (xt - a) + (lam + rho[:, None] * c) @ A
+        e.al_lbfgs_tick(P, n, n_con, o, state, xt, L.reshape(P, 1).contiguous(), f.reshape(P, 1).contiguous(), 1, g.contiguous(), c.contiguous(), lam, rho, nrun)
+        if int(nrun.item()) == 0:
+            break
+    meta = state[off[5]:off[5] + P * off[7] // 2].view(torch.int32).view(P, off[7]).cpu().numpy()
+    assert (meta[:, 0] == 2).all(), meta[:, 0]
+    # KKT: x = a - A' mu / 2 with A x = b
+    Ah, ah = A.cpu().numpy(), a.cpu().numpy()
+    mu = np.linalg.solve(Ah @ Ah.T / 2, (ah @ Ah.T - b.cpu().numpy()).T).T
+    np.testing.assert_allclose(xt.cpu().numpy(), ah - mu @ Ah / 2, atol=1e-8)
+
+
+def test_device_and_host_drivers_agree_and_population_solves():
+    """The device-resident driver against the lock-step torch driver on the same problem (both feasible, costs equal to
+    1e-4), then a population of 48 turn problems with different targets solved in one go."""
+    from d2d_b200 import planner as pl
+    from d2d_b200 import shooting
+    p = pl.Planner(pl.exp_0)
+    p.configure(tol=1e-8)
+    info_d = p.run()
+    cost_d = p.prob.obj(p.solution)
+    assert np.abs(p.prob.con(p.solution)).max() < 1e-7
+    info_h = p.run(driver="host")
+    assert np.abs(p.prob.con(p.solution)).max() < 1e-7
+    assert abs(cost_d - p.prob.obj(p.solution)) < 1e-4
+    rng = np.random.default_rng(5)
+    P = 48
+    p1 = np.stack([rng.uniform(-10, 10, P), rng.uniform(25, 40, P), np.pi + rng.uniform(-0.5, 0.5, P)], 1).reshape(P, 3, 1)
+    nlp = shooting.ShootingNLP(p.prob, np.zeros((3, 1)), p1, pl.exp_0.phi_constraint, pl.exp_0.v_constraint, P=P)
+    N = p.num_nodes
+    theta, info = shooting.solve(nlp, nlp.theta_of(np.full((1, N), 0.1), np.full((1, N), 12.)), ctol=1e-8)
+    assert (info["flag"] == 2).sum() >= 0.8 * P, info["flag"]      # some targets need a turn tighter than the bank limit allows
+    frees = nlp.free_vectors()
+    ok = info["flag"] == 2
+    N3 = 3 * (N - 1)
+    res = p.prob.con(frees)
+    assert np.abs(res[:, :N3 + 3]).max() < 1e-10                   # defects and initial conditions of every problem
+    term = np.stack([frees[:, N - 1], frees[:, 2 * N - 1], frees[:, 3 * N - 1]], 1) - p1[:, :, 0]
+    assert np.abs(term[ok]).max() < 1e-8
 
 
 def test_planner_run_single_aircraft():
