@@ -22,7 +22,7 @@ struct ShootArgs {
   double mid[2], half[2];
 };
 
-__device__ __forceinline__ bool on(double k) { return (k == k) && k != 0.0; }
+__host__ __device__ __forceinline__ bool on(double k) { return (k == k) && k != 0.0; }
 
 // inclusive prefix sum over the warp (lane order)
 __device__ __forceinline__ double warp_prefix(double v, int lane) {
@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __gr
   }
 }
 
-__global__ void __launch_bounds__(kShootThreads) shoot_adjoint_kernel(const __grid_constant__ ShootArgs a) {
+// EXTRA = obstacle and/or collision terms present; the input-cost-only instance keeps the position-gradient code out
+template <bool EXTRA>
+__global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 6) shoot_adjoint_kernel(const __grid_constant__ ShootArgs a) {
   const d2dx_colloc_problem& Q = a.p;
   const int N = Q.N, n_ac = Q.n_ac, lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5);
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(kShootThreads) shoot_adjoint_kernel(const __gr
   const int ac = (int)(w % n_ac);
   const double h = Q.h;
   const double sN = Q.obj_scale / N, norm_in = sN / Q.in_div;
-  const bool use_obs = on(Q.kobs) && Q.n_obs > 0 && ac == 0;
-  const bool use_col = on(Q.kcol) && n_ac > 1 && (Q.col_all_pairs || ac < 2);
+  const bool use_obs = EXTRA && on(Q.kobs) && Q.n_obs > 0 && ac == 0;
+  const bool use_col = EXTRA && on(Q.kcol) && n_ac > 1 && (Q.col_all_pairs || ac < 2);
   const int b_lo = Q.col_all_pairs ? 0 : (ac == 0 ? 1 : 0), b_hi = Q.col_all_pairs ? n_ac : (ac == 0 ? 2 : 1);
   const double col_kr = Q.kcol_k / Q.rcol;
   const size_t ou = (size_t)p * 2 * n_ac * N, ox = (size_t)p * 3 * n_ac * N, ob = ((size_t)p * 3) * n_ac;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(kShootThreads) shoot_adjoint_kernel(const __gr
     double ax = 0.0, ay = 0.0;
     if (valid) {
       cost += norm_in * (Q.kvel * dv * dv + Q.kbank * phi * phi);
+      if constexpr (EXTRA) {
       if (use_obs) {
         for (int o = 0; o < Q.n_obs; ++o) {
           const double dx = x - Q.obs[o][0], dy = y - Q.obs[o][1], r = Q.obs[o][2];
@@ -150,9 +153,11 @@ __global__ void __launch_bounds__(kShootThreads) shoot_adjoint_kernel(const __gr
           ax += Q.kcol * sN * -2.0 * col_kr * col_kr * dx * es; ay += Q.kcol * sN * -2.0 * col_kr * col_kr * dy * es;
         }
       }
+      }
     }
     if (!moves) { ax = 0.0; ay = 0.0; }                                         // node 0 is fixed
-    const double Gx = Gx_c + warp_suffix(ax, lane), Gy = Gy_c + warp_suffix(ay, lane);
+    double Gx = Gx_c, Gy = Gy_c;                                                // without position costs Gx, Gy are the terminal multipliers
+    if constexpr (EXTRA) { Gx += warp_suffix(ax, lane); Gy += warp_suffix(ay, lane); }
     double s, c, sp, cp;
     sincos_any(psi, s, c);
     sincos_any(phi, sp, cp);
@@ -231,7 +236,9 @@ extern "C" int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p, 
   a.p = *p; a.P = P; a.u = u; a.xs = const_cast<double*>(xs); a.c = const_cast<double*>(c); a.lam = lam;
   a.rho = rho; a.cost = cost; a.lagr = lagr; a.grad = grad;
   D2DX_CUDA(cudaSetDevice(h->device));
-  shoot_adjoint_kernel<<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
+  const bool extra = (on(p->kobs) && p->n_obs > 0) || (on(p->kcol) && p->n_ac > 1);
+  if (extra) shoot_adjoint_kernel<true><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
+  else shoot_adjoint_kernel<false><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
   D2DX_LAUNCH_CHECK("shoot_adjoint_kernel");
   return D2DX_OK;
 }

@@ -32,6 +32,8 @@ class _PlannerBase:
         phi = np.stack([guess[sl] for sl in self._phi_slices()])[None]
         v = np.stack([guess[sl] for sl in self._v_slices()])[None]
         phi_b, v_b = self._bounds["phi"], self._bounds["v"]
+        if phi_b is None or v_b is None:
+            raise ValueError("run() needs phi_constraint and v_constraint (lo, hi) on the experiment / scenario")
         if n_starts > 1:
             rng = np.random.default_rng(seed)
             k = np.concatenate([[0.], np.ones(n_starts - 1)])[:, None, None]      # start 0 is the caller's guess
@@ -154,7 +156,7 @@ class MultiPlanner(_PlannerBase):
         n1 = _node_of(scen.t1, scen.t0, self.time_step, N)
         self._instance_constraints = [(3 * i + k, n0, p[k]) for i, p in enumerate(scen.p0s) for k in range(3)] + \
                                      [(3 * i + k, n1, p[k]) for i, p in enumerate(scen.p1s) for k in range(3)]   # :53-56
-        self._bounds = {"phi": scen.phi_constraint, "v": scen.v_constraint}           # :58-64
+        self._bounds = {"phi": getattr(scen, "phi_constraint", None), "v": getattr(scen, "v_constraint", None)}   # :58-64
         if getattr(scen, "x_constraint", None) is not None: self._bounds["x"] = scen.x_constraint
         if getattr(scen, "y_constraint", None) is not None: self._bounds["y"] = scen.y_constraint
         if initialize:

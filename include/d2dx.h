@@ -340,7 +340,7 @@ int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_
  * termination tests are per problem, on the device).  [evaluate, tick] has no host decision inside and can be captured
  * in a CUDA graph; *n_running (device) holds the number of problems still iterating after each tick. */
 typedef struct {
-  int32_t m;            /* history pairs (1..64) */
+  int32_t m;            /* history pairs (1..32) */
   int32_t max_inner;    /* accepted steps per multiplier update */
   int32_t max_outer;    /* multiplier updates */
   int32_t ls_max;       /* halvings per line search */

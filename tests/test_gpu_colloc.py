@@ -220,8 +220,12 @@ def test_planner_front_ends_and_cost_classes(golden):
     np.testing.assert_allclose(mp.prob.obj(free), g["m3/cost/composit/cost"], rtol=1e-10)
     np.testing.assert_allclose(mscen.cost.cost_grad(free, mp), g["m3/cost/composit/grad"], rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(d2mou.CostCollision(r=10.).cost(free, mp), g["m3/cost/collision/cost"], rtol=1e-10)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                             # this scenario carries no input bounds
         mp.run()
+    mscen.phi_constraint, mscen.v_constraint = (-0.6, 0.6), (9., 15.)
+    mp = planner.MultiPlanner(mscen)
+    info = mp.run()                                             # solved on the engine (tests/test_gpu_shooting.py covers the solver)
+    assert np.abs(mp.prob.con(mp.solution)[:3 * 3 * 19]).max() < 1e-9 and info["outer"] >= 1
 
 
 def test_cuda_graph_replay_matches_direct_evaluation(golden):
@@ -272,5 +276,8 @@ def test_reference_csv_solutions_are_feasible_and_round_trip(golden, tmp_path):
              sol_v=sol[4 * N:], wind=np.zeros((N, 2)))
     planner.compute_or_load(p, filename=str(npz))
     assert np.abs(p.prob.con(p.solution)).max() < 1e-6
-    with pytest.raises(NotImplementedError):
-        planner.compute_or_load(p, force_recompute=True, filename=str(tmp_path / "new.npz"))
+    planner.compute_or_load(p, force_recompute=True, filename=str(tmp_path / "new.npz"))     # solves on the engine and caches
+    q = planner.Planner(exp)
+    planner.compute_or_load(q, filename=str(tmp_path / "new.npz"))
+    np.testing.assert_array_equal(q.solution, p.solution)
+    assert np.abs(q.prob.con(q.solution)).max() < 1e-6

@@ -91,19 +91,20 @@ def test_shoot_unbounded_gradient():
             assert abs(g[p, k, a, i] - fd) <= 1e-7 * max(1., abs(fd)) + 2e-11 * abs(L[p])
 
 
-def test_device_driver_on_analytic_problems():
+@pytest.mark.parametrize("n", [40, 5000])
+def test_device_driver_on_analytic_problems(n):
     """d2dx_al_lbfgs_tick alone, fed by torch-evaluated functions: min |x - a|^2 s.t. sum x = 1 and x_0 - x_1 = 0.5
-    (closed-form KKT solution), one problem per block, different data per problem."""
+    (closed-form KKT solution), different data per problem; n = 40 runs one warp per problem, n = 5000 one block."""
     import torch
     from d2d_b200 import _lib
     from d2d_b200.engine import get_engine
     e = get_engine()
-    P, n, n_con = 5, 40, 2
+    P, n_con = 5, 2
     rng = np.random.default_rng(3)
     a = torch.as_tensor(rng.normal(0, 1, (P, n)), device=e.device)
     A = torch.zeros(n_con, n, dtype=torch.float64, device=e.device); A[0] = 1.0; A[1, 0], A[1, 1] = 1.0, -1.0
     b = torch.tensor([1.0, 0.5], dtype=torch.float64, device=e.device)
-    o = _lib.LbfgsOptions(m=10, max_inner=200, max_outer=40, ls_max=30, window=10, gtol=1e-12, ftol=1e-15, ctol=1e-10, rho0=10., rho_max=1e6)
+    o = _lib.LbfgsOptions(m=10, max_inner=200, max_outer=40, ls_max=30, window=10, gtol=1e-12, ftol=1e-15, ctol=1e-10 if n < 100 else 1e-8, rho0=10., rho_max=1e6)
     off = e.lbfgs_layout(P, n, n_con, o)
     state, lam, rho, nrun = e.empty(off[0]), e.empty(P, n_con), e.empty(P), e.zeros(1, dtype=torch.int32)
     e.lbfgs_init(P, n, n_con, o, state, lam, rho)
@@ -121,7 +122,7 @@ def test_device_driver_on_analytic_problems():
     # KKT: x = a - A' mu / 2 with A x = b
     Ah, ah = A.cpu().numpy(), a.cpu().numpy()
     mu = np.linalg.solve(Ah @ Ah.T / 2, (ah @ Ah.T - b.cpu().numpy()).T).T
-    np.testing.assert_allclose(xt.cpu().numpy(), ah - mu @ Ah / 2, atol=1e-8)
+    np.testing.assert_allclose(xt.cpu().numpy(), ah - mu @ Ah / 2, atol=1e-8 if n < 100 else 1e-6)
 
 
 def test_device_and_host_drivers_agree_and_population_solves():
