@@ -55,3 +55,28 @@ def test_batched_lbfgs_independent_columns():
     np.testing.assert_allclose(x[:, 1].numpy(), 1.0, atol=1e-6)
     np.testing.assert_allclose(x[:, 2].numpy(), 1.0, atol=1e-6)
     assert torch.equal(x[:, 3], x0[:, 3]) and g.abs().max() < 1e-8
+
+
+def test_mission_host_logic():
+    """Stop rules and the symmetric extension of 11_full_sim_case1.py / 12_full_sim_case2.py (pure host code)."""
+    from d2d_b200 import mission
+    T, n_ac = 12, 2
+    X = np.zeros((T, n_ac, 5)); X[:, :, 0] = 100.
+    X0f = np.zeros((n_ac, 5))
+    assert mission.first_stop_index(X, X0f) is None
+    X[7:, 0, 0] = 1.0; X[5:, 1, 0] = 2.9                      # both inside (3, 3, 0.5 deg) from row 7 on
+    assert mission.first_stop_index(X, X0f) == 8               # seen at the top of iteration 8 -> rows [:8]
+    X[0, :, 0] = 0.                                            # row 0 (initial state) is never tested by the loop
+    assert mission.first_stop_index(X, X0f) == 8
+    X[7:, 0, 2] = np.deg2rad(0.6)                              # heading outside 0.5 deg
+    assert mission.first_stop_index(X, X0f) is None
+    eth = np.full((T, 1), 5.0); eth[0] = 0.; eth[4:] = 0.4
+    assert mission.first_stop_index(None, e_theta=eth) == 4     # inside iteration 4 -> rows [:5]
+    # symmetric extension: aircraft 0 ends where aircraft 1 starts and vice versa
+    t = np.arange(3) * 0.1
+    x = np.array([[0., 10.], [5., 5.], [10., 0.]]); y = np.array([[1., -1.], [2., -2.], [-1., 1.]])
+    t2, x2, y2, psi2 = mission.ExtendTraj_symm(2, x, y, np.zeros_like(x), t)
+    assert len(t2) == 6 and x2.shape == (6, 2)
+    np.testing.assert_array_equal(x2[3:, 0], x[:, 1]); np.testing.assert_array_equal(y2[3:, 1], y[:, 0])
+    np.testing.assert_allclose(t2[3:], t + t[-1])
+    assert mission.ConstructBMatrix(3).tolist() == [[-1, 0], [1, -1], [0, 1]]
