@@ -82,6 +82,12 @@ class D2dxError(RuntimeError):
     pass
 
 
+class Pursuit(C.Structure):
+    """d2dx_pursuit (include/d2dx.h)."""
+    _fields_ = [("n_pts", C.c_int32), ("px", C.c_void_p), ("py", C.c_void_p), ("lookahead", C.c_int32),
+                ("K", C.c_double), ("sat_phi", C.c_double), ("v_sp", C.c_double)]
+
+
 class LbfgsOptions(C.Structure):
     """d2dx_lbfgs_options (include/d2dx.h)."""
     _fields_ = [("m", C.c_int32), ("max_inner", C.c_int32), ("max_outer", C.c_int32), ("ls_max", C.c_int32), ("window", C.c_int32),
@@ -132,6 +138,8 @@ def _load():
         "d2dx_lbfgs_layout": (C.c_int, [i32, i32, i32, P(LbfgsOptions), P(i64)]),
         "d2dx_lbfgs_init": (C.c_int, [H, i32, i32, i32, P(LbfgsOptions), c_dp, c_dp, c_dp, c_dp]),
         "d2dx_al_lbfgs_tick": (C.c_int, [H, i32, i32, i32, P(LbfgsOptions), c_dp, c_dp, c_dp, c_dp, i32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_pursuit_control": (C.c_int, [H, P(Pursuit), i32, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_rollout_pursuit": (C.c_int, [H, P(Pursuit), i32, c_dp, c_dp, c_dp, dbl, i32, i32, i32, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_dfma_burn": (C.c_int, [H, i32, i32, i32, c_dp, c_dp]),
         "d2dx_math_probe": (C.c_int, [H, i32, c_dp, c_dp, c_dp, c_dp]),
     }

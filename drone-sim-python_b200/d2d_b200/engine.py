@@ -308,6 +308,26 @@ class Engine:
                                      n_parts, _ptr(grad), _ptr(c), _ptr(lam), _ptr(rho), _ptr(n_running), self.stream_ptr()),
               "d2dx_al_lbfgs_tick")
 
+    # ---- pure pursuit ------------------------------------------------------------------------------------
+    def pursuit(self, pts, lookahead=100, K=1., sat_phi=np.deg2rad(45.), v_sp=10.):
+        """device copy of a sampled path (n_pts, 2) + the controller constants -> (struct, keep-alive tensors)"""
+        px = self.to_device(np.ascontiguousarray(np.asarray(pts, np.float64)[:, 0]))
+        py = self.to_device(np.ascontiguousarray(np.asarray(pts, np.float64)[:, 1]))
+        return _lib.Pursuit(len(pts), px.data_ptr(), py.data_ptr(), int(lookahead), float(K), float(sat_phi), float(v_sp)), (px, py)
+
+    def pursuit_control(self, pp, X):
+        B = X.shape[1]
+        U, idx = self.empty(2, B), self.zeros(B, dtype=torch.int32)
+        check(lib.d2dx_pursuit_control(self.h, C.byref(pp), B, _ptr(X), _ptr(U), _ptr(idx), self.stream_ptr()), "d2dx_pursuit_control")
+        return U, idx
+
+    def rollout_pursuit(self, pp, X0, wind, ac, dt, i_begin, i_end, nsub=1, X_log=None, U_log=None, idx_log=None):
+        B = X0.shape[1]
+        Xf = self.empty(5, B)
+        check(lib.d2dx_rollout_pursuit(self.h, C.byref(pp), B, _ptr(X0), _ptr(wind), _ptr(ac), float(dt), i_begin, i_end, nsub,
+                                       _ptr(X_log), _ptr(U_log), _ptr(idx_log), _ptr(Xf), self.stream_ptr()), "d2dx_rollout_pursuit")
+        return Xf
+
     def math_probe(self, x, y):
         """Engine elementary functions on device arrays x, y -> [7][n] (sin, cos, atan2(y,x), atan x, y/x, sqrt|x|, rsqrt|x|)."""
         n = x.numel(); out = self.empty(7, n)

@@ -125,3 +125,49 @@ class GVFcontroller:
         out = eng.gvf(eng.to_device(X.reshape(5, 1)), eng.to_device(c.reshape(2, 1)), eng.to_device(np.array([r])), ke, kd)
         U, U1, U2 = out.cpu().numpy()[:, 0]
         return U, U1, U2
+
+
+class VelControler:
+    """Timing PI loop of d2d/guidance.py:188-202 (host arithmetic; unused upstream: control_vel is False)."""
+
+    def __init__(self):
+        self.Kp, self.Ki = 2., 0.001
+        self.sat_err, self.sat_vel, self.ref_vel, self.sum_err = 10., 4, 10., 0.
+
+    def get(self, tself, tref):
+        timing_error = np.clip(tself - tref, -self.sat_err, self.sat_err)
+        self.sum_err += timing_error
+        return self.ref_vel - np.clip(self.Kp * timing_error + self.Ki * self.sum_err, -self.sat_vel, self.sat_vel)
+
+
+class PurePursuitControler:
+    """Pure pursuit on the trajectory sampled every 0.01 s (d2d/guidance.py:204-245): carrot 100 samples (10 m at 10 m/s)
+    ahead of the nearest sample, phi_sp = clip(-wrap(psi - bearing to the carrot), +-45 deg), v_sp = 10.  `get(X, t)` and
+    the closed loop (simulation.run_simulation / simulation.pursuit_rollout) run on the engine."""
+
+    def __init__(self, traj):
+        self.traj = traj
+        self.time = np.arange(0, traj.duration, 0.01)
+        self.pts_2d = np.asarray(traj.get_many(self.time))[:, 0, :]
+        self.sat_phi = np.deg2rad(45.)
+        self.ref_pos, self.carrot = [], []
+        self.vel_ctl = VelControler()
+        self.control_vel = False
+        self._pp = None
+
+    def device_path(self):
+        if self._pp is None:
+            self._pp = get_engine().pursuit(self.pts_2d, lookahead=int(10 / 10 / 0.01), K=1., sat_phi=self.sat_phi, v_sp=10.)
+        return self._pp[0]
+
+    def get(self, X, t):
+        eng = get_engine()
+        U, idx = eng.pursuit_control(self.device_path(), eng.to_device(np.asarray(X, dtype=np.float64).reshape(5, 1)))
+        i = int(idx.item())
+        ic = i + 100
+        self.ref_pos.append(self.pts_2d[i])
+        self.carrot.append(self.pts_2d[ic - len(self.pts_2d) if ic >= len(self.pts_2d) else ic])
+        U = U.cpu().numpy()[:, 0]
+        if self.control_vel:
+            U[1] = self.vel_ctl.get(self.time[i], t)
+        return U

@@ -10,7 +10,7 @@ import torch
 from . import trajectory as ddt
 from .dynamic import Aircraft
 from .engine import get_engine
-from .guidance import DFFFController, WindField
+from .guidance import DFFFController, PurePursuitControler, WindField
 
 
 def _perts_csr(eng, perts_list, T):
@@ -138,9 +138,19 @@ def rollout(time, trajs, wind, X0, perts=None, tau_phi=0.01, tau_v=1., nsub=1, l
 def run_simulation(time, aircraft, windfield, ctl, X0, perts):
     """Drop-in for run_simulation(time, aircraft, windfield, ctl, X0, perts) -> X (T,5), U (T,2), Yref (T,4,2)
     (05_test_simulation.py:21-34).  `ctl` must be a DFFFController; its Xref / K logs are filled as upstream."""
-    if not isinstance(ctl, DFFFController):
-        raise TypeError("the engine implements the DFFF controller (scen.ppctl is False in every reference scenario)")
     time = np.asarray(time, dtype=np.float64)
+    if isinstance(ctl, PurePursuitControler):
+        if np.any(np.asarray(perts)):
+            raise ValueError("the pure-pursuit rollout takes no state perturbations")
+        W = windfield.sample(time[0], None)
+        X, U, idx = pursuit_rollout(ctl, time, np.asarray(X0, dtype=np.float64).reshape(1, 5), W, aircraft.tau_phi, aircraft.tau_v,
+                                    nsub=getattr(aircraft, "nsub", 1))
+        n = len(ctl.pts_2d)
+        ctl.ref_pos += list(ctl.pts_2d[idx[:, 0]])
+        ctl.carrot += list(ctl.pts_2d[(idx[:, 0] + 100) % n])
+        return X[:, 0], U[:, 0], ctl.traj.get_many(time)
+    if not isinstance(ctl, DFFFController):
+        raise TypeError("run_simulation takes a DFFFController or a PurePursuitControler")
     W = windfield.sample(time[0], None)
     res = rollout(time, [ctl.traj], W, np.asarray(X0, dtype=np.float64).reshape(1, 5), perts=[perts],
                   tau_phi=aircraft.tau_phi, tau_v=aircraft.tau_v, nsub=getattr(aircraft, "nsub", 1), log_ref=True)
@@ -150,11 +160,35 @@ def run_simulation(time, aircraft, windfield, ctl, X0, perts):
     return res.X[0], res.U[0], Yref
 
 
+def pursuit_rollout(ctl, time, X0, wind, tau_phi=0.01, tau_v=1., nsub=1):
+    """B aircraft chasing the path of one PurePursuitControler in one launch: X0 (B,5), wind (2,) or (B,2).
+    Returns X (T,B,5), U (T,B,2) (last row = control at the final state, 05_test_simulation.py:33), idx (T,B)."""
+    eng = get_engine()
+    time = np.asarray(time, dtype=np.float64)
+    X0 = np.asarray(X0, dtype=np.float64).reshape(-1, 5)
+    B, T = len(X0), len(time)
+    wind = np.broadcast_to(np.asarray(wind, dtype=np.float64).reshape(-1, 2), (B, 2))
+    ac = np.stack([np.full(B, tau_phi, dtype=np.float64), np.full(B, tau_v, dtype=np.float64)])
+    X_log, U_log, idx_log = eng.empty(T, 5, B), eng.empty(T, 2, B), eng.zeros(T, B, dtype=torch.int32)
+    pp = ctl.device_path()
+    Xf = eng.rollout_pursuit(pp, eng.to_device(np.ascontiguousarray(X0.T)), eng.to_device(np.ascontiguousarray(wind.T)),
+                             eng.to_device(ac), time[1] - time[0], 0, T - 1, nsub, X_log=X_log, U_log=U_log, idx_log=idx_log)
+    U_last, idx_last = eng.pursuit_control(pp, Xf)
+    U_log[T - 1], idx_log[T - 1] = U_last, idx_last
+    return X_log.permute(0, 2, 1).cpu().numpy(), U_log.permute(0, 2, 1).cpu().numpy(), idx_log.cpu().numpy()
+
+
 def test_simulation(scen, **_ignored):
     """Every aircraft of a scenario in ONE launch (the loop of 05_test_simulation.py:37-53).
     Returns Xs, Us, Yrefs lists like the upstream loop accumulates."""
     n = len(scen.trajs)
     W = scen.windfield.sample(scen.time[0], None)
+    if getattr(scen, "ppctl", False):                        # 05_test_simulation.py:40-41: one pure-pursuit controller per trajectory
+        Xs, Us = [], []
+        for tr, ac, X0 in zip(scen.trajs, scen.aircrafts, scen.X0s):
+            X, U, _ = pursuit_rollout(PurePursuitControler(tr), scen.time, np.asarray(X0, dtype=np.float64).reshape(1, 5), W, ac.tau_phi, ac.tau_v)
+            Xs.append(X[:, 0]); Us.append(U[:, 0])
+        return Xs, Us, [tr.get_many(scen.time) for tr in scen.trajs]
     res = rollout(scen.time, scen.trajs, W, np.asarray([np.asarray(x, dtype=np.float64) for x in scen.X0s[:n]]),
                   perts=list(scen.perts), tau_phi=[a.tau_phi for a in scen.aircrafts], tau_v=[a.tau_v for a in scen.aircrafts])
     Yrefs = [tr.get_many(scen.time) for tr in scen.trajs]

@@ -361,6 +361,27 @@ int d2dx_al_lbfgs_tick(d2dx_handle* h, int32_t P, int32_t n, int32_t n_con, cons
                        double* x_trial, const double* f_parts, const double* cost_parts, int32_t n_parts, const double* grad,
                        const double* c, double* lam, double* rho, int32_t* n_running, void* stream);
 
+/* -------- pure-pursuit guidance on a sampled path (PurePursuitControler, d2d/guidance.py:204-245) --------
+ * nearest sample of the path to the aircraft (first minimum of the Euclidean distance, as np.argmin), carrot `lookahead`
+ * samples further (wrapping at the end), phi_c = clip(-K wrap(psi - atan2(carrot - position)), +-sat_phi), v_c = v_sp.
+ * Upstream: path = traj.get(t)[0] for t in arange(0, traj.duration, 0.01), lookahead = 100, K = 1, sat 45 deg, v_sp 10. */
+typedef struct {
+  int32_t n_pts;
+  const double* px;      /* [n_pts] device */
+  const double* py;
+  int32_t lookahead;
+  double K, sat_phi, v_sp;
+} d2dx_pursuit;
+/* X[5][B] -> U[2][B] (and the index of the nearest sample, nullable) */
+int d2dx_pursuit_control(d2dx_handle* h, const d2dx_pursuit* p, int32_t B, const double* X, double* U, int32_t* idx_closest,
+                         void* stream);
+/* closed loop (run_simulation, 05_test_simulation.py:21-34, with this controller): steps i_begin .. i_end-1 of `dt` (RK4,
+ * nsub sub-steps, heading wrapped per step); X_log[T][5][B] rows i_begin..i_end, U_log[T][2][B] / idx_log[T][B] rows
+ * i_begin..i_end-1 (all nullable); X_final[5][B]. */
+int d2dx_rollout_pursuit(d2dx_handle* h, const d2dx_pursuit* p, int32_t B, const double* X0, const double* wind, const double* ac,
+                         double dt, int32_t i_begin, int32_t i_end, int32_t nsub, double* X_log, double* U_log, int32_t* idx_log,
+                         double* X_final, void* stream);
+
 /* -------- diagnostics -------- */
 /* FP64 roofline probe: every thread runs `iters` rounds of 16 independent DFMA chains (32*iters flop per
  * thread); the caller times it with CUDA events.  sink: device double[1] (keeps the chains alive). */

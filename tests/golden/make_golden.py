@@ -572,8 +572,26 @@ def golden_tracker():
         use_rk4(1)
 
 
+def golden_pursuit(sim):
+    """PurePursuitControler (d2d/guidance.py:204-245) in the run_simulation loop, on the square patrol (composite of lines
+    and arcs, 3.3 k path samples) and on a circle; wind on the second case.  RK4 nsub 1 stands in for LSODA as everywhere."""
+    out = {}
+    use_rk4(1)
+    for tag, traj, w, X0, T in (("square", ddtf.TrajSquare(), [0., 0.], [5., -3., 0.3, 0., 10.], 1500),
+                                ("circle", ddtf.TrajCircle(), [2., -1.], [25., 5., 1.2, 0., 9.], 1200)):
+        ctl = ddg.PurePursuitControler(traj)
+        ac, wind = ddyn.Aircraft(), ddg.WindField(w)
+        time = np.arange(T) * 0.01
+        X, U, _ = sim.run_simulation(time, ac, wind, ctl, np.array(X0, dtype=float), np.zeros((T, 5)))
+        idx = np.array([int(np.argmin(np.linalg.norm(ctl.pts_2d - r, axis=1))) for r in np.array(ctl.ref_pos)])
+        out[f"{tag}/pts"], out[f"{tag}/time"], out[f"{tag}/wind"], out[f"{tag}/X0"] = ctl.pts_2d, time, np.array(w), np.array(X0)
+        out[f"{tag}/X"], out[f"{tag}/U"], out[f"{tag}/idx"], out[f"{tag}/carrot"] = X, U, idx, np.array(ctl.carrot)
+        print(f"pursuit {tag}: {len(ctl.pts_2d)} path samples, final state {X[-1]}")
+    np.savez_compressed(os.path.join(HERE, "pursuit.npz"), **out)
+
+
 def main():
-    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc", "tab", "tracker"]
+    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc", "tab", "tracker", "pursuit"]
     sim = load_script("05_test_simulation.py", "ref05")
     if "c1" in what: golden_c1(sim)
     if "scen" in what: golden_scenarios(sim)
@@ -582,6 +600,7 @@ def main():
     if "colloc" in what: golden_colloc()
     if "tab" in what: golden_tabulated(sim)
     if "tracker" in what: golden_tracker()
+    if "pursuit" in what: golden_pursuit(sim)
 
 
 if __name__ == "__main__":
