@@ -248,6 +248,44 @@ def secondary_metrics(eng, hbm_peak):
         out[tag] = {"seconds": dt_solve, "lbfgs_iterations": int(info["iterations"]), "evaluations": int(info["nfev"]), "ticks": int(info.get("ticks", 0)),
                     "feasible_starts": int((info["c_max"] < 1e-6).sum()), "cost": float(info["cost"][info["best"]]),
                     "constraint_residual_max": float(np.abs(p.prob.con(p.solution)).max())}
+    # a population of planner problems (exp_0 grid, N = 101) with random terminal targets, solved together
+    Pp = 4096
+    pe = pl.Planner(pl.exp_0)
+    p1 = np.stack([rng.uniform(-10, 10, Pp), rng.uniform(28, 40, Pp), np.pi + rng.uniform(-0.5, 0.5, Pp)], 1).reshape(Pp, 3, 1)
+    nlp = ShootingNLP(pe.prob, np.zeros((3, 1)), p1, pl.exp_0.phi_constraint, pl.exp_0.v_constraint, P=Pp)
+    th0 = nlp.theta_of(np.full((1, pe.num_nodes), 0.1), np.full((1, pe.num_nodes), 12.))
+    torch.cuda.synchronize(); t0 = _time.perf_counter()
+    _, info = shoot_solve(nlp, th0, ctol=1e-8)
+    torch.cuda.synchronize(); dt_pop = _time.perf_counter() - t0
+    out["planner_population_4096"] = {"seconds": dt_pop, "solved": int((info["flag"] == 2).sum()), "problems": Pp, "ticks": int(info["ticks"]),
+                                      "solved_problems_per_s": float((info["flag"] == 2).sum() / dt_pop),
+                                      "median_iterations": float(np.median(info["iterations_each"]))}
+    del nlp
+    # pure-pursuit closed loop: 4096 aircraft on the square patrol, 1500 steps, 2000 path samples searched per step
+    from d2d_b200 import guidance as ddg, trajectory_factory as ddtf
+    from d2d_b200.simulation import pursuit_rollout
+    ctl = ddg.PurePursuitControler(ddtf.TrajSquare())
+    Bq, Tq = 4096, 1500
+    X0q = np.tile(np.array([5., -3., 0.3, 0., 10.]), (Bq, 1)); X0q[:, 0] += rng.uniform(-5, 5, Bq)
+    ppd = ctl.device_path()
+    X0d, wd, acd = eng.to_device(np.ascontiguousarray(X0q.T)), eng.zeros(2, Bq), eng.to_device(np.stack([np.full(Bq, 0.01), np.full(Bq, 1.)]))
+    dtq = timed(lambda: eng.rollout_pursuit(ppd, X0d, wd, acd, 0.01, 0, Tq, 1), 3)
+    out["pursuit_square_batch4096"] = {"aircraft_steps_per_s": Bq * Tq / dtq, "path_samples": len(ctl.pts_2d), "ms_per_launch": dtq * 1e3,
+                                       "distance_evaluations_per_s": Bq * Tq * len(ctl.pts_2d) / dtq}
+    # the three-phase mission of 11_full_sim_case1.py (formation until the stop rule, plan, track, two laps of phase 3)
+    try:
+        import pandas as pd
+        from d2d_b200 import mission
+        gt = np.load(os.path.join(ROOT, "tests", "golden", "tracker.npz"))
+        cols = {"time": gt["inf/time"]}
+        for i in range(4):
+            cols[f"x_{i + 1}"], cols[f"y_{i + 1}"], cols[f"psi_{i + 1}"] = gt["inf/x_ref"][:, i], gt["inf/y_ref"][:, i], 0 * gt["inf/time"]
+        t0 = _time.perf_counter()
+        om = mission.full_sim(pd.DataFrame(cols), t_sim_end=150)
+        out["mission_case1"] = {"seconds": _time.perf_counter() - t0, "phase1_end_s": float(om["phase1"][5]), "simulated_s": float(om["time"][-1]),
+                                "rows": int(len(om["time"]))}
+    except Exception as e:                                    # the fixture is test data; the bench line does not depend on it
+        out["mission_case1"] = {"error": str(e)}
     return out
 
 

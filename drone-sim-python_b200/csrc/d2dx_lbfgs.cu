@@ -370,12 +370,7 @@ extern "C" int d2dx_al_lbfgs_tick(d2dx_handle* h, int32_t P, int32_t n, int32_t 
   lbfgs_count_reset<<<1, 1, 0, as_stream(stream)>>>(n_running);
   if (n <= kLbWarpMaxN) {
     al_lbfgs_tick_kernel<32><<<P, 32, lb_smem_bytes(o->m, 32, a.gram), as_stream(stream)>>>(a);
-  } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      D2DX_CUDA(cudaFuncSetAttribute(al_lbfgs_tick_kernel<kLbWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb_smem_bytes(32, kLbWide, 1)));
-      attr_set = true;
-    }
+  } else {                                                  // at most 47 kB of dynamic shared memory (m = 32): no opt-in needed
     al_lbfgs_tick_kernel<kLbWide><<<P, kLbWide, lb_smem_bytes(o->m, kLbWide, a.gram), as_stream(stream)>>>(a);
   }
   D2DX_LAUNCH_CHECK("al_lbfgs_tick_kernel");
