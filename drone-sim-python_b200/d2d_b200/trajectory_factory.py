@@ -131,6 +131,71 @@ class TrajTabulated(ddt.Trajectory):                         # d2d/trajectory_fa
         return [(_lib.SEG_TABLE, np.zeros(_lib.SEG_NPAR))]
 
 
+def _spline_pieces(xs, ys, k=4):
+    """Quartic interpolating spline (FITPACK through scipy, as upstream: host-side setup) -> break points and
+    per-interval polynomial coefficients in ascending powers of (t - break point), padded to 8."""
+    import scipy.interpolate as interpolate
+    spl = interpolate.InterpolatedUnivariateSpline(xs, ys, k=k)
+    pp = interpolate.PPoly.from_spline(spl._eval_args)
+    keep = np.nonzero(np.diff(pp.x) > 0)[0]                   # repeated end knots give empty intervals
+    coefs = np.zeros((len(keep), 8))
+    coefs[:, :k + 1] = pp.c[::-1, keep].T
+    return pp.x[keep], pp.x[keep + 1], coefs, spl
+
+
+@register
+class TrajSpline(ddt.Trajectory):                            # d2d/trajectory_factory.py:189-211
+    """Quartic spline through way points, periodic in time.  The spline's polynomial pieces become SEG_POLY segments of a
+    composite trajectory, so `get` and the rollouts evaluate them on the device (FITPACK's de Boor recursion and the
+    piecewise polynomial agree to ~1e-13)."""
+    name, desc = "spline", "spline dev"
+
+    def __init__(self, waypoints=None, duration=None):
+        self.waypoints = np.array([[0., 0.], [50, 50], [100, 0], [150, 50], [200, 0]]) if waypoints is None else np.asarray(waypoints, dtype=float)
+        if duration is None:
+            v = 10.
+            duration = np.sum(np.linalg.norm(self.waypoints[1:] - self.waypoints[:-1], axis=1)) / v
+        self.duration = duration
+        lam = np.linspace(0, self.duration, len(self.waypoints))
+        x0, x1, cx, sx = _spline_pieces(lam, self.waypoints[:, 0])
+        _, _, cy, sy = _spline_pieces(lam, self.waypoints[:, 1])
+        self.splines = [sx, sy]
+        self._starts, self.steps_end, self._cx, self._cy = x0, x1, cx, cy
+        self.extends = [0, 200, -20, 80]
+        self.t0 = 0.
+
+    def is_composite(self):
+        return True
+
+    def segments(self):
+        segs = []
+        for t_i, cx, cy in zip(self._starts, self._cx, self._cy):
+            p = np.zeros(_lib.SEG_NPAR)
+            p[0], p[1:9], p[9:17] = t_i, cx, cy
+            segs.append((_lib.SEG_POLY, p))
+        return segs
+
+
+class SplineOne:                                             # d2d/trajectory_factory.py:213-221
+    """Scalar quartic spline; `get(t)` -> value and three derivatives, evaluated on the device."""
+
+    def __init__(self, xs, ys):
+        self.nder = 3
+        self.duration = xs[-1]
+        self._starts, self._ends, self._c, self.dyn = _spline_pieces(np.asarray(xs, float), np.asarray(ys, float))
+
+    def get(self, t):
+        from .engine import PackedTrajectories, get_engine
+        eng = get_engine()
+        n = len(self._starts)
+        par = np.zeros((_lib.SEG_NPAR, n))
+        par[0], par[1:9] = self._starts, self._c.T
+        ends = self._ends.copy(); ends[-1] = np.inf             # no wrap: the last piece extends (upstream extrapolates too)
+        tab = eng.table(PackedTrajectories([0], [n], [0.], [np.inf], [_lib.SEG_POLY] * n, ends, par))
+        Y = eng.traj_eval(tab, eng.to_device(np.array([float(t)])))
+        return Y.cpu().numpy().reshape(4, 2)[:, 0].copy()
+
+
 def print_available():
     print("Available trajectories:")
     for i, n in enumerate(list_available()):

@@ -590,8 +590,29 @@ def golden_pursuit(sim):
     np.savez_compressed(os.path.join(HERE, "pursuit.npz"), **out)
 
 
+def golden_spline(sim):
+    """TrajSpline (d2d/trajectory_factory.py:189-211, default way points: the only ones its constructor accepts) sampled
+    over two periods, SplineOne samples, and the DFFF closed loop on it."""
+    traj = ddtf.TrajSpline()
+    ts = np.concatenate([np.linspace(0., 2.2 * traj.duration, 400), [0., traj.duration * 0.5, traj.duration - 1e-9]])
+    Y = np.array([traj.get(t) for t in ts])
+    xs = np.arange(0, 30.5, 0.5); ys = np.sin(xs / 30. * np.pi / 2)
+    one = ddtf.SplineOne(xs, ys)
+    t1 = np.linspace(0., 30., 77)
+    Y1 = np.array([one.get(t) for t in t1])
+    use_rk4(1)
+    time = np.arange(0, 20, 0.01)
+    wind = ddg.WindField([1., 0.5])
+    ac = ddyn.Aircraft()
+    X0 = ddg.DiffFlatness.state_and_input_from_output(traj.get(0.), wind.sample(0, None), ac)[0] + np.array([2., -2., 0.1, 0., 0.])
+    X, U, Yref, Xref, K = run_dfff(sim, time, traj, wind, X0, np.zeros((len(time), 5)))
+    print("spline: duration", traj.duration, "X[-1]", X[-1])
+    np.savez_compressed(os.path.join(HERE, "spline.npz"), duration=traj.duration, ts=ts, Y=Y, one_xs=xs, one_ys=ys, one_t=t1, one_Y=Y1,
+                        time=time, wind=np.array([1., 0.5]), X0=X0, X=X, U=U)
+
+
 def main():
-    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc", "tab", "tracker", "pursuit"]
+    what = sys.argv[1:] or ["c1", "scen", "units", "form", "colloc", "tab", "tracker", "pursuit", "spline"]
     sim = load_script("05_test_simulation.py", "ref05")
     if "c1" in what: golden_c1(sim)
     if "scen" in what: golden_scenarios(sim)
@@ -601,6 +622,7 @@ def main():
     if "tab" in what: golden_tabulated(sim)
     if "tracker" in what: golden_tracker()
     if "pursuit" in what: golden_pursuit(sim)
+    if "spline" in what: golden_spline(sim)
 
 
 if __name__ == "__main__":
