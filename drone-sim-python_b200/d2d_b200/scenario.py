@@ -194,6 +194,37 @@ class ScenCircularFormation(Scenario):                       # :254-264
         self.windfield = WindField([0, 5.])                  # set after X0s were derived with zero wind, as upstream
 
 
+@register
+class ScenOval(Scenario):                                    # :268-279
+    """Upstream never calls Scenario.__init__ here, so `aircrafts` / `perts` are missing and test_simulation raises
+    AttributeError; the defaults are filled in (one trajectory -> the first of the two X0s is used)."""
+    name, desc = "oval", "oval"
+
+    def __init__(self):
+        self.trajs = [ddtf.TrajLineWithIntro(Y0=[0., 100.], Y1=[0., 50.], Y2=[200., 50.], r=25.)]
+        self.X0s = [[0, 100, -np.pi, 0, 10], [0, 0, -np.pi, 0, 10]]
+        self.extends = (-30, 110, -10, 110)
+        self.windfield = WindField([0, 2.5])
+        self.time = np.arange(0, 20, 0.01)
+        super().__init__()
+
+
+@register
+class ScenDualOpty(Scenario):                                # :283-290 (planner outputs as tabulated references)
+    name, desc = "dual opty", "dual opty"
+    files = ("optyplan_exp6_0.npz", "optyplan_exp6_1.npz", "optyplan_exp6_2.npz")
+
+    def __init__(self, files=None):
+        self.trajs = [ddtf.TrajTabulated(f) for f in (files or self.files)]      # the .npz files are not shipped upstream either
+        super().__init__()
+
+
+@register
+class ScenOpty2(ScenDualOpty):                               # :294-303
+    name, desc = "opty2", "opty2"
+    files = tuple(f"optyplan_exp7_{i}.npz" for i in range(5))
+
+
 def print_available():
     print("Available scenarios:")
     for i, n in enumerate(list_available()):

@@ -317,6 +317,33 @@ def test_tabulated_trajectory_against_reference_golden(d2d, golden, tag, tmp_pat
     np.testing.assert_allclose(res.X_final[1], g[f"{tag}/Xlast"], rtol=0, atol=TOL)
 
 
+def test_remaining_registry_scenarios(d2d, golden, tmp_path):
+    """`oval` (d2d/scenario.py:268-279; upstream forgets Scenario.__init__, so the oracle is the checker) and the tabulated
+    scenarios `dual opty` / `opty2` (:283-303) fed with planner files made from the golden solutions."""
+    from oracle import d2d_oracle as orc
+    from d2d_b200 import scenario, simulation
+    scen, desc = scenario.get("oval")
+    Xs, Us, _ = simulation.test_simulation(scen)
+    Xo, Uo = orc.run_simulation(scen.time[:600], orc.traj_line_with_intro(Y0=(0., 100.), Y1=(0., 50.), Y2=(200., 50.), r=25.), [0., 2.5],
+                                np.array(scen.X0s[0], float))[:2]
+    np.testing.assert_allclose(Xs[0][:600], Xo, rtol=0, atol=TOL)
+    np.testing.assert_allclose(Us[0][:599], Uo[:599], rtol=0, atol=TOL)
+    g = golden["tabulated"]
+    files = []
+    for tag in ("exp0", "exp13", "exp0"):
+        fn = tmp_path / f"plan_{len(files)}.npz"
+        np.savez(fn, **{k: g[f"{tag}/{k}"] for k in ("sol_time", "sol_x", "sol_y", "sol_psi", "sol_phi", "sol_v", "wind")})
+        files.append(str(fn))
+    assert set(("oval", "dual opty", "opty2")) <= {e.split(":")[0] for e in scenario.list_available()}
+    sc = scenario.ScenDualOpty(files)
+    assert len(sc.trajs) == 3 and len(sc.X0s) == 3
+    Xs, Us, Yrefs = simulation.test_simulation(sc)
+    solo = simulation.rollout(sc.time, [sc.trajs[1]], sc.windfield.sample(0, None), np.asarray(sc.X0s[1], float)[None])
+    np.testing.assert_allclose(Xs[1], solo.X[0], rtol=0, atol=1e-12)
+    with pytest.raises(FileNotFoundError):                      # the upstream default files are not shipped
+        scenario.get("opty2")
+
+
 def test_step_by_step_duck_typed_api_under_d2d_alias(d2d, golden):
     """A caller written in the reference's style (`import d2d.dynamic as ddyn`, one controller call and one disc_dyn
     call per step, as the loop body of 05_test_simulation.py:28-32) runs against the package aliased as `d2d`."""
