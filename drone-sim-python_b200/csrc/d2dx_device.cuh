@@ -134,15 +134,42 @@ __device__ __forceinline__ void segment_eval(int type, LD P, double t, FlatOut& 
       Y.y2x = poly_row<2>(cx, dt); Y.y2y = poly_row<2>(cy, dt);
       if (WANT3) { Y.y3x = poly_row<3>(cx, dt); Y.y3y = poly_row<3>(cy, dt); }
     } break;
-    default: {                       // D2DX_SEG_SI_LINE: SpaceIndexedTraj.get, d2d/trajectory.py:231-241
-      auto cl = [&](int k) { return P(5 + k); };
-      const double l0 = clip(poly_row<0>(cl, t), 0.0, 1.0);
-      const double l1 = poly_row<1>(cl, t), l2 = poly_row<2>(cl, t);
-      const double gx = P(3), gy = P(4);      // dg/dlambda of the line geometry; higher ones vanish
-      Y.y0x = __dadd_rn(P(1), __dmul_rn(gx, l0)); Y.y0y = __dadd_rn(P(2), __dmul_rn(gy, l0));
-      Y.y1x = l1 * gx; Y.y1y = l1 * gy;
-      Y.y2x = l2 * gx; Y.y2y = l2 * gy;
-      if (WANT3) { const double l3 = poly_row<3>(cl, t); Y.y3x = l3 * gx; Y.y3y = l3 * gy; }
+    default: {                       // D2DX_SEG_SI_LINE / D2DX_SEG_SI_CIRCLE: SpaceIndexedTraj.get, d2d/trajectory.py:231-241
+      double l0, l1, l2, l3 = 0.0;   // lambda(t) and its derivatives: polynomial (PolynomialOne / AffineOne / CstOne) or SinOne (:26-38)
+      if (P(16) == 0.0) {
+        auto cl = [&](int k) { return P(5 + k); };
+        l0 = poly_row<0>(cl, t); l1 = poly_row<1>(cl, t); l2 = poly_row<2>(cl, t);
+        if (WANT3) l3 = poly_row<3>(cl, t);
+      } else {
+        const double a = P(6), om = P(7);
+        double sa, ca;
+        sincos_any(__dmul_rn(om, t - P(8)), sa, ca);
+        const double asa = __dmul_rn(a, sa), aca = __dmul_rn(a, ca);
+        l0 = __dadd_rn(P(5), asa); l1 = __dmul_rn(om, aca); l2 = -(om * om) * asa;
+        if (WANT3) l3 = -(om * om * om) * aca;
+      }
+      l0 = clip(l0, 0.0, 1.0);       // :233 "protect ourself against unruly dynamics"
+      if (type == D2DX_SEG_SI_LINE) {
+        const double gx = P(3), gy = P(4);      // dg/dlambda of the line geometry; higher ones vanish
+        Y.y0x = __dadd_rn(P(1), __dmul_rn(gx, l0)); Y.y0y = __dadd_rn(P(2), __dmul_rn(gy, l0));
+        Y.y1x = l1 * gx; Y.y1y = l1 * gy;
+        Y.y2x = l2 * gx; Y.y2y = l2 * gy;
+        if (WANT3) { Y.y3x = l3 * gx; Y.y3y = l3 * gy; }
+      } else {                        // circle geometry g(lambda) = TrajectoryCircle.get(lambda), chain rule of :235-238
+        const double r = P(3), om = P(4);
+        double sa, ca;
+        sincos_any(__dadd_rn(__dmul_rn(l0 - P(0), om), P(13)), sa, ca);
+        const double w1 = __dmul_rn(om, r), w2 = __dmul_rn(__dmul_rn(om, om), r), w3 = __dmul_rn(om * om * om, r);
+        const double g1x = -w1 * sa, g1y = w1 * ca, g2x = -w2 * ca, g2y = -w2 * sa, g3x = w3 * sa, g3y = -w3 * ca;
+        Y.y0x = __dadd_rn(P(1), __dmul_rn(r, ca)); Y.y0y = __dadd_rn(P(2), __dmul_rn(r, sa));
+        Y.y1x = l1 * g1x; Y.y1y = l1 * g1y;
+        const double l1s = l1 * l1;
+        Y.y2x = l2 * g1x + l1s * g2x; Y.y2y = l2 * g1y + l1s * g2y;
+        if (WANT3) {
+          const double m = 3.0 * l1 * l2, l1c = l1s * l1;
+          Y.y3x = l3 * g1x + m * g2x + l1c * g3x; Y.y3y = l3 * g1y + m * g2y + l1c * g3y;
+        }
+      }
     } break;
   }
 }

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("D2DX_LIB") or os.path.join(_HERE, "libd2dx.so")     # D2DX_LIB: A/B builds of the same ABI
 
-SEG_LINE, SEG_CIRCLE, SEG_SLALOM, SEG_POLY, SEG_SI_LINE, SEG_TABLE = range(6)
+SEG_LINE, SEG_CIRCLE, SEG_SLALOM, SEG_POLY, SEG_SI_LINE, SEG_TABLE, SEG_SI_CIRCLE = range(7)
 SEG_NPAR = 17
 JAC_COMPACT, JAC_OPTY_DENSE = 0, 1
 EVAL_RESIDUAL, EVAL_JAC, EVAL_COST, EVAL_GRAD = 1, 2, 4, 8

@@ -92,6 +92,38 @@ def arr(k, n):
     return a
 
 
+class CstOne:                                                # d2d/trajectory.py:13-17
+    """Constant scalar trajectory; as a SpaceIndexedTraj dynamic it is a degree-0 polynomial."""
+
+    def __init__(self, c=-1., duration=1.):
+        self.c, self.duration = c, duration
+        self.coefs = np.zeros((4, 8)); self.coefs[0, 0] = c
+
+    def get(self, t):
+        return np.array([self.c, 0, 0, 0])
+
+
+class AffineOne:                                             # d2d/trajectory.py:19-24
+    def __init__(self, c1=-1., c2=0, duration=1.):
+        self.c1, self.c2, self.duration = c1, c2, duration
+        self.coefs = np.zeros((4, 8)); self.coefs[0, 0], self.coefs[0, 1] = c2, c1
+
+    def get(self, t):
+        return np.array([self.c1 * t + self.c2, self.c1, 0, 0])
+
+
+class SinOne:                                                # d2d/trajectory.py:26-38
+    def __init__(self, c=0., a=1., om=1., duration=2 * np.pi):
+        self.duration = duration
+        self.c, self.a, self.om = c, a, om
+        self.t0 = 0.
+
+    def get(self, t):
+        alpha = self.om * (t - self.t0)
+        asa, aca = self.a * np.sin(alpha), self.a * np.cos(alpha)
+        return np.array([self.c + asa, self.om * aca, -self.om ** 2 * asa, -self.om ** 3 * aca])
+
+
 class PolynomialOne:
     """Scalar min-snap polynomial through boundary values and derivatives (d2d/trajectory.py:47-82).
     Coefficients are solved on the host exactly as the reference does (setup, not hot path); evaluation
@@ -175,9 +207,9 @@ class CompositeTraj(Trajectory):
 
 
 class SpaceIndexedTraj(Trajectory):
-    """Geometry g(lambda) driven by a scalar dynamic lambda(t) (d2d/trajectory.py:220-241).  The engine
-    supports the combination the reference instantiates: TrajectoryLine geometry + PolynomialOne dynamic
-    (TrajSiDemo, d2d/trajectory_factory.py:177-185)."""
+    """Geometry g(lambda) driven by a scalar dynamic lambda(t) (d2d/trajectory.py:220-241).  On the engine: line or
+    circle geometry with polynomial (PolynomialOne, AffineOne, CstOne) or sinusoidal (SinOne) dynamics -- TrajSiDemo
+    (d2d/trajectory_factory.py:177-185) and the first stage of TrajSiSpline (:246-247)."""
 
     def __init__(self, geometry, dynamic):
         self.duration = dynamic.duration
@@ -190,16 +222,24 @@ class SpaceIndexedTraj(Trajectory):
         self.duration = dyn.duration
 
     def segments(self):
-        if not isinstance(self._geom, TrajectoryLine) or not isinstance(self._dyn, PolynomialOne):
-            raise NotImplementedError("SpaceIndexedTraj: only line geometry with polynomial dynamics runs on the engine")
-        g = self._geom
-        if g.t0 != 0.:
-            raise NotImplementedError("SpaceIndexedTraj geometry must have t0 = 0")
-        uv = g.un * g.v
+        g, dyn = self._geom, self._dyn
         p = np.zeros(_lib.SEG_NPAR)
-        p[1], p[2], p[3], p[4] = g.p1[0], g.p1[1], uv[0], uv[1]
-        p[5:13] = self._dyn.coefs[0]
-        return [(_lib.SEG_SI_LINE, p)]
+        if isinstance(dyn, SinOne):
+            p[5], p[6], p[7], p[8], p[16] = dyn.c, dyn.a, dyn.om, dyn.t0, 1.
+        elif hasattr(dyn, "coefs") and np.shape(dyn.coefs) == (4, 8):
+            p[5:13] = dyn.coefs[0]
+        else:
+            raise NotImplementedError(f"SpaceIndexedTraj: {type(dyn).__name__} dynamics do not run on the engine "
+                                      "(polynomial or SinOne dynamics do)")
+        if isinstance(g, TrajectoryLine):
+            uv = g.un * g.v
+            p1 = np.asarray(g.p1, dtype=float) - uv * g.t0          # geometry evaluated at lambda: p1 + un v (lambda - t0)
+            p[1], p[2], p[3], p[4] = p1[0], p1[1], uv[0], uv[1]
+            return [(_lib.SEG_SI_LINE, p)]
+        if isinstance(g, TrajectoryCircle):
+            p[0], p[1], p[2], p[3], p[4], p[13] = g.t0, g.c[0], g.c[1], g.r, g.omega, g.alpha0
+            return [(_lib.SEG_SI_CIRCLE, p)]
+        raise NotImplementedError("SpaceIndexedTraj: only line and circle geometries run on the engine")
 
 
 class CircleBatch:

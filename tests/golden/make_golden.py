@@ -607,8 +607,27 @@ def golden_spline(sim):
     X0 = ddg.DiffFlatness.state_and_input_from_output(traj.get(0.), wind.sample(0, None), ac)[0] + np.array([2., -2., 0.1, 0., 0.])
     X, U, Yref, Xref, K = run_dfff(sim, time, traj, wind, X0, np.zeros((len(time), 5)))
     print("spline: duration", traj.duration, "X[-1]", X[-1])
+    # SpaceIndexedTraj beyond TrajSiDemo: circle geometry (TrajSiSpline's, trajectory_factory.py:246-247) and the scalar
+    # dynamics of d2d/trajectory.py:13-38
+    si = {}
+    circ = ddt.TrajectoryCircle(c=[30., 30.], r=30., v=2 * np.pi * 30., t0=0., alpha0=0, dalpha=3 * np.pi / 2)
+    line = ddt.TrajectoryLine([0., 0.], [80., 40.], v=np.hypot(80., 40.), t0=0.)
+    cases = {"circle_affine": (circ, ddt.AffineOne(1. / 30., 0., duration=30.)),
+             "circle_poly": (circ, ddt.PolynomialOne([0, 0, 0, 0], [1, 0, 0, 0], 25.)),
+             "line_sin": (line, ddt.SinOne(c=0.5, a=0.6, om=0.4, duration=2 * np.pi / 0.4)),
+             "circle_sin": (circ, ddt.SinOne(c=0.4, a=0.3, om=0.7, duration=2 * np.pi / 0.7))}
+    for tag, (geom, dyn) in cases.items():
+        tr = ddt.SpaceIndexedTraj(geom, dyn)
+        tsi = np.linspace(0., tr.duration, 200)
+        si[f"si/{tag}/t"], si[f"si/{tag}/Y"] = tsi, np.array([tr.get(t) for t in tsi])
+    tr = ddt.SpaceIndexedTraj(*cases["circle_poly"])
+    time2 = np.arange(0, 25, 0.01)
+    wind2 = ddg.WindField([0.5, -0.5])
+    X0b = ddg.DiffFlatness.state_and_input_from_output(tr.get(0.5), wind2.sample(0, None), ac)[0] + np.array([1., 1., 0., 0., 1.])
+    Xb, Ub, _, _, _ = run_dfff(sim, time2[50:], tr, wind2, X0b, np.zeros((len(time2) - 50, 5)))
+    si["si/run/time"], si["si/run/wind"], si["si/run/X0"], si["si/run/X"], si["si/run/U"] = time2[50:], np.array([0.5, -0.5]), X0b, Xb, Ub
     np.savez_compressed(os.path.join(HERE, "spline.npz"), duration=traj.duration, ts=ts, Y=Y, one_xs=xs, one_ys=ys, one_t=t1, one_Y=Y1,
-                        time=time, wind=np.array([1., 0.5]), X0=X0, X=X, U=U)
+                        time=time, wind=np.array([1., 0.5]), X0=X0, X=X, U=U, **si)
 
 
 def main():

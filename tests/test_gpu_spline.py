@@ -47,3 +47,34 @@ def test_spline_one_and_custom_waypoints():
     Y = tr.get_many(ts)
     scale = np.abs(ref).max(axis=(0, 2))[None, :, None]
     np.testing.assert_allclose(Y / scale, ref / scale, rtol=0, atol=1e-11)
+
+
+def test_space_indexed_geometries_and_dynamics():
+    """SpaceIndexedTraj (d2d/trajectory.py:220-241) with circle / line geometry and polynomial, affine, sinusoidal dynamics
+    against the unmodified reference (samples over a full duration; a DFFF closed loop on circle + min-snap dynamics)."""
+    from d2d_b200 import dynamic as ddyn, guidance as ddg, trajectory as ddt
+    from d2d_b200.simulation import run_simulation
+    g = np.load(os.path.join(HERE, "golden", "spline.npz"))
+    circ = ddt.TrajectoryCircle(c=[30., 30.], r=30., v=2 * np.pi * 30., t0=0., alpha0=0, dalpha=3 * np.pi / 2)
+    line = ddt.TrajectoryLine([0., 0.], [80., 40.], v=np.hypot(80., 40.), t0=0.)
+    cases = {"circle_affine": (circ, ddt.AffineOne(1. / 30., 0., duration=30.)),
+             "circle_poly": (circ, ddt.PolynomialOne([0, 0, 0, 0], [1, 0, 0, 0], 25.)),
+             "line_sin": (line, ddt.SinOne(c=0.5, a=0.6, om=0.4, duration=2 * np.pi / 0.4)),
+             "circle_sin": (circ, ddt.SinOne(c=0.4, a=0.3, om=0.7, duration=2 * np.pi / 0.7))}
+    for tag, (geom, dyn) in cases.items():
+        tr = ddt.SpaceIndexedTraj(geom, dyn)
+        ref = g[f"si/{tag}/Y"]
+        Y = tr.get_many(g[f"si/{tag}/t"])
+        scale = np.maximum(np.abs(ref).max(axis=(0, 2)), 1e-3)[None, :, None]
+        np.testing.assert_allclose(Y / scale, ref / scale, rtol=0, atol=1e-11, err_msg=tag)
+    for dyn in (ddt.CstOne(0.3), ddt.AffineOne(0.1, 0.2, 5.), ddt.SinOne(0.5, 0.2, 1.3)):
+        tr = ddt.SpaceIndexedTraj(circ, dyn)                      # host get() of the scalar classes vs the device evaluation
+        lam = dyn.get(0.7)
+        gl = circ.get(float(np.clip(lam[0], 0, 1)))
+        np.testing.assert_allclose(tr.get(0.7)[1], lam[1] * gl[1], atol=1e-10)
+    tr = ddt.SpaceIndexedTraj(*cases["circle_poly"])
+    time = g["si/run/time"]
+    ctl = ddg.DFFFController(tr, ddyn.Aircraft(), ddg.WindField(list(g["si/run/wind"])))
+    X, U, _ = run_simulation(time, ddyn.Aircraft(), ddg.WindField(list(g["si/run/wind"])), ctl, g["si/run/X0"], np.zeros((len(time), 5)))
+    np.testing.assert_allclose(X, g["si/run/X"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(U, g["si/run/U"], rtol=0, atol=1e-8)
