@@ -18,6 +18,8 @@ struct ShootArgs {
   int P;
   const double *u, *p0, *p1, *lam, *rho;
   double *uphys, *xs, *c, *cost, *lagr, *grad;
+  int boxed;              // soft state box: weight/N * sum_i (excess of x_i, y_i over [lo, hi])^2 added to the cost
+  double box[5];          // x_lo, x_hi, y_lo, y_hi, weight
   int bounded;            // inputs are theta with phi = mid + half sin(theta) (same for v): box constraints by substitution
   double mid[2], half[2];
 };
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __gr
 
 // EXTRA = obstacle and/or collision terms present; the input-cost-only instance keeps the position-gradient code out
 template <bool EXTRA>
-__global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 6) shoot_adjoint_kernel(const __grid_constant__ ShootArgs a) {
+__global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 8) shoot_adjoint_kernel(const __grid_constant__ ShootArgs a) {
   const d2dx_colloc_problem& Q = a.p;
   const int N = Q.N, n_ac = Q.n_ac, lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5);
@@ -127,6 +129,13 @@ __global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 6) shoot_adjoint_ke
     if (valid) {
       cost += norm_in * (Q.kvel * dv * dv + Q.kbank * phi * phi);
       if constexpr (EXTRA) {
+      if (a.boxed) {                                                             // x/y_constraint of the planners as a soft box
+        const double wN = a.box[4] * sN;
+        const double ex = x > a.box[1] ? x - a.box[1] : (x < a.box[0] ? x - a.box[0] : 0.0);
+        const double ey = y > a.box[3] ? y - a.box[3] : (y < a.box[2] ? y - a.box[2] : 0.0);
+        cost += wN * (ex * ex + ey * ey);
+        ax += 2.0 * wN * ex; ay += 2.0 * wN * ey;
+      }
       if (use_obs) {
         for (int o = 0; o < Q.n_obs; ++o) {
           const double dx = x - Q.obs[o][0], dy = y - Q.obs[o][1], r = Q.obs[o][2];
@@ -225,8 +234,8 @@ extern "C" int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p, 
 }
 
 extern "C" int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t P, const double* u, const double* bounds,
-                                  const double* u_phys, const double* xs, const double* c, const double* lam, const double* rho,
-                                  double* cost, double* lagr, double* grad, void* stream) {
+                                  const double* state_box, const double* u_phys, const double* xs, const double* c, const double* lam,
+                                  const double* rho, double* cost, double* lagr, double* grad, void* stream) {
   if (int rc = check(p, P, "d2dx_shoot_adjoint")) return rc;
   D2DX_CHECK_ARG(h && u && xs && c && lam && rho && cost && lagr && grad, "d2dx_shoot_adjoint: null array");
   D2DX_CHECK_ARG(!bounds || u_phys, "d2dx_shoot_adjoint: bounds need u_phys (from d2dx_shoot_forward)");
@@ -236,7 +245,12 @@ extern "C" int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p, 
   a.p = *p; a.P = P; a.u = u; a.xs = const_cast<double*>(xs); a.c = const_cast<double*>(c); a.lam = lam;
   a.rho = rho; a.cost = cost; a.lagr = lagr; a.grad = grad;
   D2DX_CUDA(cudaSetDevice(h->device));
-  const bool extra = (on(p->kobs) && p->n_obs > 0) || (on(p->kcol) && p->n_ac > 1);
+  a.boxed = state_box != nullptr;
+  if (state_box) {
+    D2DX_CHECK_ARG(state_box[1] >= state_box[0] && state_box[3] >= state_box[2] && state_box[4] >= 0.0, "d2dx_shoot_adjoint: state_box lo > hi or weight < 0");
+    for (int k = 0; k < 5; ++k) a.box[k] = state_box[k];
+  }
+  const bool extra = a.boxed || (on(p->kobs) && p->n_obs > 0) || (on(p->kcol) && p->n_ac > 1);
   if (extra) shoot_adjoint_kernel<true><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
   else shoot_adjoint_kernel<false><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
   D2DX_LAUNCH_CHECK("shoot_adjoint_kernel");

@@ -134,7 +134,7 @@ def _load():
         "d2dx_colloc_eval_shard": (C.c_int, [H, P(CollocProblem), i32, i32, c_dp, c_dp, u32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_colloc_pack_positions": (C.c_int, [H, i32, i32, c_dp, c_dp, c_dp]),
         "d2dx_shoot_forward": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
-        "d2dx_shoot_adjoint": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_shoot_adjoint": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_lbfgs_layout": (C.c_int, [i32, i32, i32, P(LbfgsOptions), P(i64)]),
         "d2dx_lbfgs_init": (C.c_int, [H, i32, i32, i32, P(LbfgsOptions), c_dp, c_dp, c_dp, c_dp]),
         "d2dx_al_lbfgs_tick": (C.c_int, [H, i32, i32, i32, P(LbfgsOptions), c_dp, c_dp, c_dp, c_dp, i32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),

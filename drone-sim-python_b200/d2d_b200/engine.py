@@ -290,9 +290,10 @@ class Engine:
         check(lib.d2dx_shoot_forward(self.h, C.byref(prob), P, _ptr(u), b, _ptr(p0), _ptr(p1), _ptr(u_phys), _ptr(xs), _ptr(c),
                                      self.stream_ptr()), "d2dx_shoot_forward")
 
-    def shoot_adjoint(self, prob, P, u, bounds, u_phys, xs, c, lam, rho, cost, lagr, grad):
+    def shoot_adjoint(self, prob, P, u, bounds, u_phys, xs, c, lam, rho, cost, lagr, grad, state_box=None):
         b = (C.c_double * 4)(*bounds) if bounds is not None else None
-        check(lib.d2dx_shoot_adjoint(self.h, C.byref(prob), P, _ptr(u), b, _ptr(u_phys), _ptr(xs), _ptr(c), _ptr(lam), _ptr(rho),
+        sb = (C.c_double * 5)(*state_box) if state_box is not None else None
+        check(lib.d2dx_shoot_adjoint(self.h, C.byref(prob), P, _ptr(u), b, sb, _ptr(u_phys), _ptr(xs), _ptr(c), _ptr(lam), _ptr(rho),
                                      _ptr(cost), _ptr(lagr), _ptr(grad), self.stream_ptr()), "d2dx_shoot_adjoint")
 
     def lbfgs_layout(self, P, n, n_con, opts):

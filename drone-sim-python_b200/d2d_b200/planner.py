@@ -21,12 +21,13 @@ class _PlannerBase:
     def configure(self, tol=1e-8, max_iter=3000):
         self.tol, self.max_iter = tol, max_iter
 
-    def run(self, initial_guess=None, n_starts=1, seed=0, verbose=False, **_):
+    def run(self, initial_guess=None, n_starts=1, seed=0, verbose=False, state_weight=100., **_):
         """`self.solution, info = prob.solve(initial_guess)` of 06_optyplan.py:117-125 / 07_multioptyplan.py:80-88,
         solved by single shooting + augmented Lagrangian (shooting.solve).  Only the input part of `initial_guess`
         seeds the solve (the states follow from the inputs).  n_starts > 1 adds randomly perturbed starts solved in the
-        same launches; the feasible one of least cost is kept.  State bounds (x/y_constraint) are not enforced: they are
-        checked on the result and reported in `self.info["state_bounds_ok"]`."""
+        same launches; the feasible one of least cost is kept.  State bounds (x/y_constraint) enter as a soft box
+        (`state_weight` x squared excess, averaged over the nodes); `self.info["state_bounds_ok"]` tells whether the result
+        respects them strictly."""
         guess = self.get_initial_guess() if initial_guess is None else np.asarray(initial_guess, dtype=float)
         n, N = self._n_ac, self.num_nodes
         phi = np.stack([guess[sl] for sl in self._phi_slices()])[None]
@@ -40,7 +41,11 @@ class _PlannerBase:
             phi = phi + k * rng.normal(0., 0.25 * (phi_b[1] - phi_b[0]), (n_starts, n, 1))
             v = v + k * rng.normal(0., 0.25 * (v_b[1] - v_b[0]), (n_starts, n, 1))
         p0, p1 = self._boundary_states()
-        nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts)
+        box = None
+        if "x" in self._bounds or "y" in self._bounds:
+            bx, by = self._bounds.get("x", (-np.inf, np.inf)), self._bounds.get("y", (-np.inf, np.inf))
+            box = (max(bx[0], -1e300), min(bx[1], 1e300), max(by[0], -1e300), min(by[1], 1e300), state_weight)
+        nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts, state_box=box)
         tol = getattr(self, "tol", 1e-8)
         driver = shooting.solve_host if _.get("driver") == "host" else shooting.solve
         theta, info = driver(nlp, nlp.theta_of(np.clip(phi, *phi_b), np.clip(v, *v_b)), ctol=min(tol, 1e-6),

@@ -19,7 +19,7 @@ class ShootingNLP:
     and the cost).  p0, p1: (3, n_ac) or (P, 3, n_ac) initial states / terminal targets (x, y, psi).
     Device arrays are problem-major (include/d2dx.h): theta/u_phys/grad (P, 2, n_ac, N), xs (P, 3, n_ac, N)."""
 
-    def __init__(self, prob, p0, p1, phi_bounds, v_bounds, P=1, engine=None):
+    def __init__(self, prob, p0, p1, phi_bounds, v_bounds, P=1, engine=None, state_box=None):
         self.eng = e = engine or prob.eng
         self.prob, self.c_prob = prob, prob.c
         self.n_ac, self.N, self.P = prob.n_ac, prob.N, int(P)
@@ -36,6 +36,7 @@ class ShootingNLP:
         self.lam, self.rho = e.zeros(self.P, 3, n_ac), e.zeros(self.P) + 10.
         self.cost_ac, self.lagr_ac, self.grad = e.empty(self.P, n_ac), e.empty(self.P, n_ac), e.empty(self.P, 2, n_ac, N)
         self.nfev = 0
+        self.state_box = None if state_box is None else tuple(float(v) for v in state_box)      # x_lo, x_hi, y_lo, y_hi, weight
 
     # ---- variables ------------------------------------------------------------------------------------
     def theta_of(self, phi, v):
@@ -50,7 +51,7 @@ class ShootingNLP:
         e = self.eng
         e.shoot_forward(self.c_prob, self.P, theta, self.bounds, self.p0, self.p1, self.u_phys, self.xs, self.c)
         e.shoot_adjoint(self.c_prob, self.P, theta, self.bounds, self.u_phys, self.xs, self.c, self.lam, self.rho,
-                        self.cost_ac, self.lagr_ac, self.grad)
+                        self.cost_ac, self.lagr_ac, self.grad, state_box=self.state_box)
         self.nfev += 1
 
     def evaluate(self, theta):

@@ -328,12 +328,15 @@ int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const do
  * ignored: the terminal targets come from p1, gradients are always exact).
  * Box constraints by substitution: with `bounds` = {phi_lo, phi_hi, v_lo, v_hi} (HOST array; NULL = none) `u` holds
  * angles theta with phi = mid + half sin(theta) (likewise v); forward writes the physical inputs to u_phys (same shape
- * as u), adjoint reads them and returns the gradient with respect to theta. */
+ * as u), adjoint reads them and returns the gradient with respect to theta.
+ * Soft state box: with `state_box` = {x_lo, x_hi, y_lo, y_hi, weight} (HOST array; NULL = none) the cost gains
+ * weight * obj_scale / N * sum over aircraft and nodes of the squared excess of x_i, y_i over the box (the planners'
+ * x/y_constraint, which IPOPT treats as variable bounds). */
 int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t P, const double* u, const double* bounds,
                        const double* p0, const double* p1, double* u_phys, double* xs, double* c, void* stream);
 int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t P, const double* u, const double* bounds,
-                       const double* u_phys, const double* xs, const double* c, const double* lam, const double* rho,
-                       double* cost, double* lagr, double* grad, void* stream);
+                       const double* state_box, const double* u_phys, const double* xs, const double* c, const double* lam,
+                       const double* rho, double* cost, double* lagr, double* grad, void* stream);
 
 /* -------- batched augmented-Lagrangian L-BFGS driver (the solver behind Planner.run; replaces prob.solve -> IPOPT,
  * 06_optyplan.py:117-125, 07_multioptyplan.py:80-88) --------

@@ -752,12 +752,16 @@ def shoot_free(phi, v, p0, h, wind):
     return np.concatenate([np.concatenate([x[a], y[a], psi[a]]) for a in range(x.shape[0])] + [np.ravel(phi), np.ravel(v)])
 
 
-def shoot_lagrangian(phi, v, p0, p1, h, wind, spec, lam, rho, multi=None):
-    """cost (reference cost classes, exact value), c = terminal state - p1 (3, n_ac), and
-    cost + sum lam c + rho/2 |c|^2."""
+def shoot_lagrangian(phi, v, p0, p1, h, wind, spec, lam, rho, multi=None, state_box=None):
+    """cost (reference cost classes, exact value; plus the soft state box weight * obj_scale / N * sum of squared excesses
+    when state_box = (x_lo, x_hi, y_lo, y_hi, weight)), c = terminal state - p1 (3, n_ac), and cost + sum lam c + rho/2 |c|^2."""
     phi, v = np.atleast_2d(phi), np.atleast_2d(v)
     n_ac, N = phi.shape
     x, y, psi = shoot_states(phi, v, p0, h, wind)
     cost, _ = cost_and_grad(shoot_free(phi, v, p0, h, wind), N, n_ac, spec, multi)
+    if state_box is not None:
+        xl, xh, yl, yh, wgt = state_box
+        ex, ey = np.maximum(x - xh, 0) + np.minimum(x - xl, 0), np.maximum(y - yh, 0) + np.minimum(y - yl, 0)
+        cost += wgt * spec.get("obj_scale", 1.) / N * np.sum(ex ** 2 + ey ** 2)
     c = np.stack([x[:, -1], y[:, -1], psi[:, -1]]) - np.asarray(p1, float).reshape(3, -1)
     return cost, c, cost + np.sum(np.asarray(lam) * c) + 0.5 * rho * np.sum(c * c)

@@ -16,7 +16,7 @@ def timed(fn, reps=200):
     e1.record(); e1.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps
 
-for (P, n_ac, N, h) in ((1, 1, 101, 0.1), (1, 1, 1001, 0.02), (1, 16, 500, 0.02), (2048, 1, 101, 0.1), (16384, 1, 101, 0.1), (1024, 1, 1001, 0.02)):
+for (P, n_ac, N, h) in ((1, 1, 101, 0.1), (1, 1, 1001, 0.02), (1, 16, 500, 0.02), (2048, 1, 101, 0.1), (16384, 1, 101, 0.1), (1024, 1, 1001, 0.02), (16384, 1, 1001, 0.02), (512, 16, 500, 0.02)):
     prob = CollocationProblem(n_ac, N, h, cost=CostSpec(vsp=12., kvel=1., kbank=1.), multi=n_ac > 1)
     rng = np.random.default_rng(1)
     p1 = np.stack([rng.uniform(-10, 10, (P, n_ac)), rng.uniform(28, 40, (P, n_ac)), np.pi + rng.uniform(-0.5, 0.5, (P, n_ac))], 1)

@@ -154,6 +154,44 @@ def test_device_and_host_drivers_agree_and_population_solves():
     assert np.abs(term[ok]).max() < 1e-8
 
 
+def test_soft_state_box_gradient_and_effect():
+    """state_box: value and gradient against the oracle, and a planner whose y_constraint cuts the unconstrained optimum."""
+    import torch
+    from d2d_b200 import planner as pl
+    prob, nlp, spec, h, wind, p0, p1, phi, v, rng = _setup(2, 30, 2)
+    box = (-2., 6., -4., 3., 7.5)
+    nlp.state_box = box
+    nlp.rho.fill_(3.0)
+    theta = nlp.theta_of(phi, v)
+    L, g = nlp.evaluate(theta)
+    L, g, th = L.cpu().numpy(), g.cpu().numpy().reshape(2, 2, 2, 30), theta.cpu().numpy().reshape(2, 2, 2, 30)
+    mid, half = nlp.mid, nlp.half
+    lag = lambda thp, p: orc.shoot_lagrangian(mid[0] + half[0] * np.sin(thp[0]), mid[1] + half[1] * np.sin(thp[1]), p0[p], p1[p], h, wind,
+                                              spec, np.zeros((3, 2)), 3.0, multi=True, state_box=box)
+    for p in range(2):
+        co, cc, Lo = lag(th[p], p)
+        assert abs(nlp.cost.cpu().numpy()[p] - co) <= 1e-12 * abs(co) and abs(L[p] - Lo) <= 1e-11 * abs(Lo)
+        assert co > orc.shoot_lagrangian(mid[0] + half[0] * np.sin(th[p][0]), mid[1] + half[1] * np.sin(th[p][1]), p0[p], p1[p], h, wind,
+                                         spec, np.zeros((3, 2)), 3.0, multi=True)[0]            # the box is active at this point
+        for (k, a, i) in ((0, 0, 2), (1, 1, 9), (0, 1, 20), (1, 0, 29)):
+            e = np.zeros_like(th[p]); e[k, a, i] = 1e-4
+            fd = _fd(lambda s_: lag(th[p] + s_ * e, p)[2])
+            assert abs(g[p, k, a, i] - fd) <= 1e-7 * max(1., abs(fd)) + 2e-11 * abs(Lo)
+    p = pl.Planner(pl.exp_0)
+    p.configure(tol=1e-8)
+    p.run()
+    y_free = p.sol_y.max()
+
+    class exp_box(pl.exp_0):
+        y_constraint = (-50., y_free - 3.)
+    q = pl.Planner(exp_box)
+    q.configure(tol=1e-8)
+    info = q.run(state_weight=1e3)
+    assert info["feasible"] and np.abs(q.prob.con(q.solution)).max() < 1e-7
+    assert q.sol_y.max() < y_free - 2.5                       # pushed inside (soft: a small excess over the bound remains)
+    assert info["state_bounds_ok"] == bool(q.sol_y.max() <= y_free - 3. + 1e-9)
+
+
 def test_planner_run_single_aircraft():
     """Planner.run() on exp_0 (06_optyplan.py) and on the C3 grid: feasible to 1e-7 by the reference's constraints; on
     the C3 grid the cost is not above the cached IPOPT solution's (golden c3/sol, cost 8.09e-8)."""
