@@ -13,7 +13,7 @@ SEG_NPAR = 17
 JAC_COMPACT, JAC_OPTY_DENSE = 0, 1
 EVAL_RESIDUAL, EVAL_JAC, EVAL_COST, EVAL_GRAD = 1, 2, 4, 8
 EVAL_ALL = 15
-MAX_OBSTACLES = 8
+MAX_OBSTACLES = 16
 
 c_dp = C.c_void_p      # device pointers travel as integers
 

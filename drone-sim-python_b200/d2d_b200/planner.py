@@ -21,7 +21,7 @@ class _PlannerBase:
     def configure(self, tol=1e-8, max_iter=3000):
         self.tol, self.max_iter = tol, max_iter
 
-    def run(self, initial_guess=None, n_starts=1, seed=0, verbose=False, state_weight=100., **_):
+    def run(self, initial_guess=None, n_starts=1, seed=0, verbose=False, state_weight=1000., **_):
         """`self.solution, info = prob.solve(initial_guess)` of 06_optyplan.py:117-125 / 07_multioptyplan.py:80-88,
         solved by single shooting + augmented Lagrangian (shooting.solve).  Only the input part of `initial_guess`
         seeds the solve (the states follow from the inputs).  n_starts > 1 adds randomly perturbed starts solved in the

@@ -253,7 +253,7 @@ int d2dx_rollout_formation(d2dx_handle* h, const d2dx_formations* f, double dt, 
  * d2d/multiopty_utils.py:29-174. */
 enum { D2DX_JAC_COMPACT = 0, D2DX_JAC_OPTY_DENSE = 1 };
 enum { D2DX_EVAL_RESIDUAL = 1, D2DX_EVAL_JAC = 2, D2DX_EVAL_COST = 4, D2DX_EVAL_GRAD = 8 };
-#define D2DX_MAX_OBSTACLES 8
+#define D2DX_MAX_OBSTACLES 16
 
 typedef struct {
   int32_t n_ac, N;           /* aircraft, collocation nodes                                      */

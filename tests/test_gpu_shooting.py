@@ -242,3 +242,46 @@ def test_planner_run_multi_aircraft_multistart(tmp_path):
     q = pl.MultiPlanner(scen4)
     q.load_csv(f)
     np.testing.assert_allclose(q.solution, p.solution, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["exp_1", "exp_2", "exp_4", "exp_4_1", "exp_4_2", "exp_5", "exp_14"])
+def test_reference_planner_experiments_solve(name):
+    """The single-vehicle experiments of d2d/optyplan_scenarios.py (input costs, obstacles incl. the 12-obstacle checker board,
+    state boxes) through Planner.run: feasible at the experiment's own tolerance under the reference's constraints."""
+    from d2d_b200 import optyplan_scenarios as S, planner as pl
+    exp = getattr(S, name)
+    exp.set_case(0)
+    p = pl.Planner(exp)
+    p.configure(tol=exp.tol, max_iter=exp.max_iter)
+    info = p.run(n_starts=4)
+    assert info["feasible"] and np.abs(p.prob.con(p.solution)).max() < 10 * exp.tol
+    lo, hi = exp.phi_constraint
+    assert p.sol_phi.min() >= lo - 1e-12 and p.sol_phi.max() <= hi + 1e-12
+    assert p.sol_v.min() >= exp.v_constraint[0] - 1e-12 and p.sol_v.max() <= exp.v_constraint[1] + 1e-12
+    if exp.x_constraint is not None:                              # soft box: at most a few centimetres outside
+        assert p.sol_x.min() > exp.x_constraint[0] - 0.2 and p.sol_x.max() < exp.x_constraint[1] + 0.2
+        assert p.sol_y.min() > exp.y_constraint[0] - 0.2 and p.sol_y.max() < exp.y_constraint[1] + 0.2
+    if len(exp.obstacles) and name != "exp_4_1":                  # obstacle costs keep the path out of the disc cores
+        for (ox, oy, r) in exp.obstacles:
+            assert np.hypot(p.sol_x - ox, p.sol_y - oy).min() > 0.3 * r
+
+
+def test_infeasible_experiment_is_reported():
+    """exp_13 asks for a quarter turn of radius 20 m at 12 m/s in 3 s: 37 deg of bank against a 30 deg limit."""
+    from d2d_b200 import optyplan_scenarios as S, planner as pl
+    p = pl.Planner(S.exp_13)
+    p.configure(tol=S.exp_13.tol, max_iter=S.exp_13.max_iter)
+    info = p.run(n_starts=4)
+    assert not info["feasible"] and (info["flag"] == 3).all()
+    assert np.abs(p.prob.con(p.solution)[:3 * (p.num_nodes - 1)]).max() < 1e-10     # the defects still hold by construction
+
+
+def test_experiment_table_matches_upstream_values():
+    from d2d_b200 import optyplan_scenarios as S
+    assert len(S.scens) == 15 and S.exp_0.t1 == 15.                # building exp_6 sets exp_0.t1 as upstream's class body does
+    S.exp_0.t1 = 10.
+    assert S.exp_5.cost.spec().obstacles[0] == (0., 20., 10.) and len(S.exp_5.obstacles) == 12
+    S.exp_0_2.set_case(3); assert S.exp_0.wind.w == [5., 0.]; S.exp_0_2.set_case(0)
+    S.exp_6.set_case(2); assert S.exp_0.p0 == (10, 10, np.pi / 2, 0., 10.) and S.exp_6.label(2) == "2"
+    S.exp_0.p0, S.exp_0.p1 = (0., 0., 0., 0., 10.), (0., 30., np.pi, 0., 10.)
+    assert S.desc_one(4).startswith("exp_1 combined phi/vel objective\ninitial state 0.0 (0.0, 0.0, 0.0, 0.0, 12.0)")
