@@ -285,3 +285,28 @@ def test_experiment_table_matches_upstream_values():
     S.exp_6.set_case(2); assert S.exp_0.p0 == (10, 10, np.pi / 2, 0., 10.) and S.exp_6.label(2) == "2"
     S.exp_0.p0, S.exp_0.p1 = (0., 0., 0., 0., 10.), (0., 30., np.pi, 0., 10.)
     assert S.desc_one(4).startswith("exp_1 combined phi/vel objective\ninitial state 0.0 (0.0, 0.0, 0.0, 0.0, 12.0)")
+
+
+def test_multi_aircraft_experiments_solve_and_collision_cost_separates():
+    """Experiments of 07_multioptyplan.py:170-435 through MultiPlanner.run: face-to-face pair without / with the collision
+    cost (exp_5 cases 0 / 1), the meeting pair, the obstacle slalom and the four-aircraft formation entry."""
+    from d2d_b200 import multiopty_scenarios as S, planner as pl
+
+    def solve(exp, case=0):
+        exp.set_case(case)
+        p = pl.MultiPlanner(exp)
+        p.configure(tol=exp.tol, max_iter=exp.max_iter)
+        info = p.run(initial_guess=p.get_initial_guess("tri"), n_starts=4)
+        assert info["feasible"] and np.abs(p.prob.con(p.solution)).max() < 10 * exp.tol, exp.name
+        n = p.acs.nb_aicraft
+        sep = min([np.hypot(p.sol_x[a] - p.sol_x[b], p.sol_y[a] - p.sol_y[b]).min() for a in range(n) for b in range(a)] or [np.inf])
+        return p, sep
+    _, sep_ref = solve(S.exp_5, 0)
+    _, sep_col = solve(S.exp_5, 1)
+    S.exp_5.set_case(0)
+    assert sep_ref < 1.0 and sep_col > 4.0                        # head-on pair: the collision cost opens a gap (rcol = 10)
+    for exp in (S.exp_1_0, S.exp_4, S.gvf_trial_3ac):
+        p, _ = solve(exp)
+        for a, p1 in enumerate(exp.p1s):
+            np.testing.assert_allclose([p.sol_x[a][-1], p.sol_y[a][-1], p.sol_psi[a][-1]], p1[:3], atol=1e-4)
+    assert len(S.scens) == 15 and S.get_scen(13) is S.gvf_trial_3ac and "exp_2 4 aicraft" in S.desc_all_scens()
