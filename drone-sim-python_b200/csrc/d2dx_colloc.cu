@@ -165,20 +165,23 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 5 : 8) colloc_kernel(c
     const int n = n_ac, half = n / 2;
     const bool even = (n % 2) == 0;
     const double f = P.exact_grad ? col_kr * col_kr : 1.0;
+    const double cw = P.kcol * sN * -2.0 * f;                     // weight of dx * es in the gradient
+    const int row = 2 * TN;                                       // doubles per aircraft in the staged arrays
     for (int k = 1; k <= half; ++k) {
       __syncthreads();
       if (i < N) {
         for (int a_l = al; a_l < n; a_l += a.APP) {
           if (even && k == half && a_l >= half) continue;         // the antipodal pair is visited from its lower member only
           int b = a_l + k; if (b >= n) b -= n;
-          const double dx = spos[(a_l * 2) * TN + il] - spos[(b * 2) * TN + il];
-          const double dy = spos[(a_l * 2 + 1) * TN + il] - spos[(b * 2 + 1) * TN + il];
+          const int oa = a_l * row + il, ob = b * row + il;
+          const double dx = spos[oa] - spos[ob];
+          const double dy = spos[oa + TN] - spos[ob + TN];
           const double ux = dx * col_kr, uy = dy * col_kr;
           const double es = fm::exp_neg(-(ux * ux + uy * uy));
           s_col += es;
-          const double wx = P.kcol * (sN * -2.0 * dx * es) * f, wy = P.kcol * (sN * -2.0 * dy * es) * f;
-          sown[(a_l * 2) * TN + il] += wx; sown[(a_l * 2 + 1) * TN + il] += wy;
-          sacc[(b * 2) * TN + il] -= wx; sacc[(b * 2 + 1) * TN + il] -= wy;
+          const double wx = cw * dx * es, wy = cw * dy * es;
+          sown[oa] += wx; sown[oa + TN] += wy;
+          sacc[ob] -= wx; sacc[ob + TN] -= wy;
         }
       }
     }

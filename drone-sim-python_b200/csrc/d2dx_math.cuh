@@ -14,7 +14,7 @@ namespace d2dx {
 namespace fm {
 
 // layout chosen so that consecutive uses are adjacent (16-byte pairs)
-static __constant__ __align__(16) double kTab[60] = {
+static __constant__ __align__(16) double kTab[76] = {
     /* 0*/ 0.6366197723675814, 6755399441055744.0,                    // 2/pi, 1.5*2^52
     /* 2*/ -1.5707963267948966, -6.123233995736766e-17,               // -pi/2 split in three
     /* 4*/ 1.4973849048591698e-33, 0.0,
@@ -47,6 +47,15 @@ static __constant__ __align__(16) double kTab[60] = {
     /*54*/ 2.48015873015873e-05, -1.3888888888888889e-03,             // 1/8!, -1/6!
     /*56*/ 4.1666666666666664e-02, -0.5,                              // 1/4!, -1/2!
     /*58*/ 0.0, 0.0,
+    // exp_neg: log2 e, -ln2 hi, -ln2 lo, then the Taylor coefficients 1/13! .. 1/3! (the magic constant is kTab[1])
+    /*60*/ 1.4426950408889634, -6.93147180369123816490e-01,
+    /*62*/ -1.90821492927058770002e-10, 1.6059043836821613e-10,
+    /*64*/ 2.08767569878681e-09, 2.505210838544172e-08,
+    /*66*/ 2.755731922398589e-07, 2.7557319223985893e-06,
+    /*68*/ 2.48015873015873e-05, 1.984126984126984e-04,
+    /*70*/ 1.3888888888888889e-03, 8.333333333333333e-03,
+    /*72*/ 4.1666666666666664e-02, 1.6666666666666666e-01,
+    /*74*/ 0.0, 0.0,
 };
 
 // 1/b to ~1 ulp: MUFU.RCP64H seed (relative error e0 <= 2^-20), then y0 (1 + e0 + e0^2 + e0^3 + e0^4)-style
@@ -136,22 +145,22 @@ __device__ __forceinline__ void sincos_small(double d, double& s, double& c) {
 // exp(y) for y <= 0 (Gaussian-type penalties): k = rint(y log2 e), r = y - k ln2 (two-term), degree-13 Taylor polynomial
 // on |r| <= ln2/2 (truncation 4e-18 relative), scaling through the exponent field; flushes to 0 below 2^-1000.
 __device__ __forceinline__ double exp_neg(double y) {
-  const double t = fma(y, 1.4426950408889634, 6755399441055744.0);
+  const double t = fma(y, kTab[60], kTab[1]);
   const int k = __double2loint(t);
-  const double j = t - 6755399441055744.0;
-  double r = fma(j, -6.93147180369123816490e-01, y);
-  r = fma(j, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;                 // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);               // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);              // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);              // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);             // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);               // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);              // 1/7!
-  p = fma(p, r, 1.3888888888888889e-03);             // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);              // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);             // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);             // 1/3!
+  const double j = t - kTab[1];
+  double r = fma(j, kTab[61], y);
+  r = fma(j, kTab[62], r);
+  double p = kTab[63];                               // 1/13!
+  p = fma(p, r, kTab[64]);                           // 1/12!
+  p = fma(p, r, kTab[65]);                           // 1/11!
+  p = fma(p, r, kTab[66]);                           // 1/10!
+  p = fma(p, r, kTab[67]);                           // 1/9!
+  p = fma(p, r, kTab[68]);                           // 1/8!
+  p = fma(p, r, kTab[69]);                           // 1/7!
+  p = fma(p, r, kTab[70]);                           // 1/6!
+  p = fma(p, r, kTab[71]);                           // 1/5!
+  p = fma(p, r, kTab[72]);                           // 1/4!
+  p = fma(p, r, kTab[73]);                           // 1/3!
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);

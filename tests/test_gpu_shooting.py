@@ -276,17 +276,6 @@ def test_infeasible_experiment_is_reported():
     assert np.abs(p.prob.con(p.solution)[:3 * (p.num_nodes - 1)]).max() < 1e-10     # the defects still hold by construction
 
 
-def test_experiment_table_matches_upstream_values():
-    from d2d_b200 import optyplan_scenarios as S
-    assert len(S.scens) == 15 and S.exp_0.t1 == 15.                # building exp_6 sets exp_0.t1 as upstream's class body does
-    S.exp_0.t1 = 10.
-    assert S.exp_5.cost.spec().obstacles[0] == (0., 20., 10.) and len(S.exp_5.obstacles) == 12
-    S.exp_0_2.set_case(3); assert S.exp_0.wind.w == [5., 0.]; S.exp_0_2.set_case(0)
-    S.exp_6.set_case(2); assert S.exp_0.p0 == (10, 10, np.pi / 2, 0., 10.) and S.exp_6.label(2) == "2"
-    S.exp_0.p0, S.exp_0.p1 = (0., 0., 0., 0., 10.), (0., 30., np.pi, 0., 10.)
-    assert S.desc_one(4).startswith("exp_1 combined phi/vel objective\ninitial state 0.0 (0.0, 0.0, 0.0, 0.0, 12.0)")
-
-
 def test_multi_aircraft_experiments_solve_and_collision_cost_separates():
     """Experiments of 07_multioptyplan.py:170-435 through MultiPlanner.run: face-to-face pair without / with the collision
     cost (exp_5 cases 0 / 1), the meeting pair, the obstacle slalom and the four-aircraft formation entry."""

@@ -80,3 +80,25 @@ def test_mission_host_logic():
     np.testing.assert_array_equal(x2[3:, 0], x[:, 1]); np.testing.assert_array_equal(y2[3:, 1], y[:, 0])
     np.testing.assert_allclose(t2[3:], t + t[-1])
     assert mission.ConstructBMatrix(3).tolist() == [[-1, 0], [1, -1], [0, 1]]
+
+
+def test_experiment_table_matches_upstream_values():
+    from d2d_b200 import optyplan_scenarios as S
+    assert len(S.scens) == 15 and S.exp_0.t1 == 15.                # building exp_6 sets exp_0.t1 as upstream's class body does
+    S.exp_0.t1 = 10.
+    assert S.exp_5.cost.spec().obstacles[0] == (0., 20., 10.) and len(S.exp_5.obstacles) == 12
+    S.exp_0_2.set_case(3); assert S.exp_0.wind.w == [5., 0.]; S.exp_0_2.set_case(0)
+    S.exp_6.set_case(2); assert S.exp_0.p0 == (10, 10, np.pi / 2, 0., 10.) and S.exp_6.label(2) == "2"
+    S.exp_0.p0, S.exp_0.p1 = (0., 0., 0., 0., 10.), (0., 30., np.pi, 0., 10.)
+    assert S.desc_one(4).startswith("exp_1 combined phi/vel objective\ninitial state 0.0 (0.0, 0.0, 0.0, 0.0, 12.0)")
+
+
+def test_multi_experiment_table():
+    from d2d_b200 import multiopty_scenarios as S
+    assert len(S.scens) == 15 and S.get_scen(13) is S.gvf_trial_3ac and "exp_2 4 aicraft" in S.desc_all_scens()
+    assert abs(S.exp_2.d - 22.0) < 1e-12 and S.exp_2.p0s[2] == (0., 22.0, -np.pi / 2, 0., 12.)
+    S.exp_5.set_case(1); assert S.exp_5.cost.kcol == 10. and S.exp_5.cost.rcol == 10. and S.exp_5.label(1) == "obj AntiCol"
+    S.exp_5.set_case(0); assert np.isnan(S.exp_5.cost.kcol) and S.exp_5.cost.rcol == 3.
+    S.exp_4_1.set_case(2); assert S.exp_4_1.obstacles == ((70, -10, 15), (70, 25, 15)) and S.exp_4_1.cost.vsp == 14.
+    S.exp_3_1.set_case(1); assert S.exp_3_1.cost.c == (25, -10)
+    assert S.trap_4.cost.kvel == 70. and S.trap_4.x_constraint == (-150, 150)
