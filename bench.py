@@ -248,6 +248,36 @@ def secondary_metrics(eng, hbm_peak):
         out[tag] = {"seconds": dt_solve, "lbfgs_iterations": int(info["iterations"]), "evaluations": int(info["nfev"]), "ticks": int(info.get("ticks", 0)),
                     "feasible_starts": int((info["c_max"] < 1e-6).sum()), "cost": float(info["cost"][info["best"]]),
                     "constraint_residual_max": float(np.abs(p.prob.con(p.solution)).max())}
+    # CPU figure for the planner solve: the oracle's shooting adjoint under SciPy's L-BFGS-B with the same augmented-Lagrangian
+    # schedule, one core, exp_0 on the C3 grid (what planner_solve_c3_single does on the GPU)
+    try:
+        import scipy.optimize as so
+        from oracle import d2d_oracle as orc
+        Nc, hc = 1001, 0.02
+        p0c, p1c = np.zeros((3, 1)), np.array([0., 30., np.pi]).reshape(3, 1)
+        lamc, rhoc, uc = np.zeros((3, 1)), 10., np.concatenate([np.full(Nc, 0.1), np.full(Nc, 12.)])
+        bnds = [(-np.deg2rad(30.), np.deg2rad(30.))] * Nc + [(9., 14.)] * Nc
+        spec_c = dict(vsp=12., kvel=1.)
+
+        def fun(u_):
+            L_, dphi_, dv_, _, _ = orc.shoot_value_and_grad(u_[None, :Nc], u_[None, Nc:], p0c, p1c, hc, (0., 0.), spec_c, lamc, rhoc, multi=False)
+            return L_, np.concatenate([dphi_[0], dv_[0]])
+        t0 = _time.perf_counter(); nit = 0; cprev = None
+        for _outer in range(30):
+            r_ = so.minimize(fun, uc, jac=True, method="L-BFGS-B", bounds=bnds, options=dict(maxiter=500, ftol=1e-15, gtol=1e-10, maxcor=20))
+            uc, nit = r_.x, nit + r_.nit
+            _, _, _, cost_c, cc = orc.shoot_value_and_grad(uc[None, :Nc], uc[None, Nc:], p0c, p1c, hc, (0., 0.), spec_c, lamc, rhoc, multi=False)
+            cm = np.abs(cc).max()
+            if cm < 1e-8:
+                break
+            lamc = lamc + rhoc * cc
+            if cprev is None or cm > 0.25 * cprev:
+                rhoc = min(rhoc * 3, 1e6)
+            cprev = cm
+        out["planner_solve_c3_cpu_scipy_1core"] = {"seconds": _time.perf_counter() - t0, "lbfgs_iterations": int(nit), "cost": float(cost_c),
+                                                   "constraint_residual_max": float(cm), "kind": "port", "cores": 1}
+    except Exception as e:
+        out["planner_solve_c3_cpu_scipy_1core"] = {"error": str(e)}
     # a population of planner problems (exp_0 grid, N = 101) with random terminal targets, solved together
     Pp = 4096
     pe = pl.Planner(pl.exp_0)

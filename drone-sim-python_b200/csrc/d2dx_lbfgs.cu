@@ -245,24 +245,24 @@ __global__ void __launch_bounds__(kLbThreads) al_lbfgs_tick_kernel(const __grid_
       auto vec_index = [&](int v) { const int k = (head - cnt + (v >> 1) + 2 * m) % m; return v == nvec - 1 ? 2 * m : ((v & 1) ? m + k : k); };
       auto vec_ptr = [&](int idx) -> const double* { return idx == 2 * m ? g : (idx >= m ? Y + (size_t)(idx - m) * n : S + (size_t)idx * n); };
       if (accepted) {                                          // g changed (and maybe a new pair): refresh their Gram rows
+        // each warp streams whole basis vectors (all lanes, coalesced, independent accumulators) and finishes their three dot
+        // products with shuffles: no cross-warp reduction
         const double* sn = S + (size_t)slot * n; const double* yn = Y + (size_t)slot * n;
-        for (int v = 0; v < nvec; ++v) {
-          const double* b = vec_ptr(vec_index(v));
+        for (int v = wid; v < nvec; v += kLbThreads / 32) {
+          const int row = vec_index(v);
+          const double* b = vec_ptr(row);
           double tg = 0.0, ts = 0.0, ty = 0.0;
-          if (new_pair) for (int i = tid; i < n; i += kLbThreads) { const double bi = b[i]; tg += bi * g[i]; ts += bi * sn[i]; ty += bi * yn[i]; }
-          else for (int i = tid; i < n; i += kLbThreads) tg += b[i] * g[i];
-          tg = warp_sum(tg); ts = warp_sum(ts); ty = warp_sum(ty);
-          if (lane == 0) { double* q = part + (wid * B + v) * 3; q[0] = tg; q[1] = ts; q[2] = ty; }
-        }
-        team_sync<kLbThreads>();
-        for (int e = tid; e < nvec * 3; e += kLbThreads) {
-          const int v = e / 3, w = e % 3;
-          if (w > 0 && !new_pair) continue;
-          double t = 0.0;
-          for (int r = 0; r < kLbThreads / 32; ++r) t += part[(r * B + v) * 3 + w];
-          const int row = vec_index(v), col = w == 0 ? 2 * m : (w == 1 ? slot : m + slot);
-          Gs[row * B + col] = t; Gs[col * B + row] = t;
-          Gg[row * B + col] = t; Gg[col * B + row] = t;
+          if (new_pair) for (int i = lane; i < n; i += 32) { const double bi = b[i]; tg += bi * g[i]; ts += bi * sn[i]; ty += bi * yn[i]; }
+          else for (int i = lane; i < n; i += 32) tg += b[i] * g[i];
+          tg = warp_sum(tg);
+          if (new_pair) { ts = warp_sum(ts); ty = warp_sum(ty); }
+          if (lane == 0) {
+            Gs[row * B + 2 * m] = tg; Gs[2 * m * B + row] = tg; Gg[row * B + 2 * m] = tg; Gg[2 * m * B + row] = tg;
+            if (new_pair) {
+              Gs[row * B + slot] = ts; Gs[slot * B + row] = ts; Gg[row * B + slot] = ts; Gg[slot * B + row] = ts;
+              Gs[row * B + m + slot] = ty; Gs[(m + slot) * B + row] = ty; Gg[row * B + m + slot] = ty; Gg[(m + slot) * B + row] = ty;
+            }
+          }
         }
       }
       team_sync<kLbThreads>();
@@ -300,9 +300,17 @@ __global__ void __launch_bounds__(kLbThreads) al_lbfgs_tick_kernel(const __grid_
         gd = -scale * Gs[2 * m * B + 2 * m];
         for (int i = tid; i < n; i += kLbThreads) { const double di = -scale * g[i]; d[i] = di; xt[i] = x[i] + di; }
       } else {
+        double* vcoef = part;                                  // coefficient of basis vector v, in the order of the loop below
+        for (int v = tid; v < nvec; v += kLbThreads) vcoef[v] = dl[vec_index(v)];
+        team_sync<kLbThreads>();
+        const int k0 = (head - cnt + 2 * m) % m;               // oldest valid slot
         for (int i = tid; i < n; i += kLbThreads) {
-          double di = 0.0;
-          for (int v = 0; v < nvec; ++v) { const int idx = vec_index(v); di -= dl[idx] * vec_ptr(idx)[i]; }
+          double di = -vcoef[nvec - 1] * g[i];
+          int k = k0;
+          for (int v = 0; v + 1 < nvec; v += 2) {              // (s_k, y_k) pairs, oldest to newest
+            di -= vcoef[v] * S[(size_t)k * n + i] + vcoef[v + 1] * Y[(size_t)k * n + i];
+            k = k + 1 == m ? 0 : k + 1;
+          }
           d[i] = di; xt[i] = x[i] + di;
         }
       }
@@ -365,7 +373,7 @@ extern "C" int d2dx_al_lbfgs_tick(d2dx_handle* h, int32_t P, int32_t n, int32_t 
   a.P = P; a.n = n; a.n_con = n_con; a.n_parts = n_parts; a.o = *o; a.L = lb_layout(P, n, n_con, o->m, o->window);
   a.state = state; a.xt = x_trial; a.fparts = f_parts; a.cparts = cost_parts; a.gt = grad; a.c = c; a.lam = lam; a.rho = rho;
   a.n_running = n_running;
-  a.gram = (n >= 1024 && n <= 8192 && P <= 64) ? 1 : 0;   // measured: the Gram form wins only where the tick is latency-bound (profiles/README)
+  a.gram = (n >= 1024 && P <= 64) ? 1 : 0;   // measured: the Gram form wins only where the tick is latency-bound (profiles/README)
   D2DX_CUDA(cudaSetDevice(h->device));
   lbfgs_count_reset<<<1, 1, 0, as_stream(stream)>>>(n_running);
   if (n <= kLbWarpMaxN) {

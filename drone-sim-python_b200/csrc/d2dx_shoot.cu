@@ -45,9 +45,47 @@ __device__ __forceinline__ double warp_suffix(double v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __grid_constant__ ShootArgs a) {
-  const int N = a.p.N, n_ac = a.p.n_ac, lane = threadIdx.x & 31;
-  const long w = (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5);
+// One unit = one (problem, aircraft), run by W threads: W = 32 (a warp; kShootWarps units per block) when there are
+// enough units to fill the machine, W = kShootWide (a whole block; scans go through shared memory) for few, long problems.
+constexpr int kShootWide = 256;
+
+template <int W> struct UnitScan {
+  // inclusive prefix / suffix over the unit's threads; `total` = sum over the unit (same in every thread)
+  static __device__ __forceinline__ double prefix(double v, double& total, double* red) {
+    const int lane = threadIdx.x & 31;
+    const double w = warp_prefix(v, lane);
+    if (W == 32) { total = __shfl_sync(0xffffffffu, w, 31); return w; }
+    const int wid = threadIdx.x >> 5;
+    __syncthreads();                                 // the previous scan's readers are done with `red`
+    if (lane == 31) red[wid] = w;
+    __syncthreads();
+    double off = 0.0, tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < W / 32; ++k) { const double r = red[k]; tot += r; if (k < wid) off += r; }
+    total = tot;
+    return off + w;
+  }
+  static __device__ __forceinline__ double suffix(double v, double& total, double* red) {
+    const int lane = threadIdx.x & 31;
+    const double w = warp_suffix(v, lane);
+    if (W == 32) { total = __shfl_sync(0xffffffffu, w, 0); return w; }
+    const int wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = w;
+    __syncthreads();
+    double off = 0.0, tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < W / 32; ++k) { const double r = red[k]; tot += r; if (k > wid) off += r; }
+    total = tot;
+    return off + w;
+  }
+};
+
+template <int W>
+__global__ void __launch_bounds__(W == 32 ? kShootThreads : W) shoot_forward_kernel(const __grid_constant__ ShootArgs a) {
+  __shared__ double red[3][kShootWide / 32];
+  const int N = a.p.N, n_ac = a.p.n_ac, lane = W == 32 ? (threadIdx.x & 31) : threadIdx.x;
+  const long w = W == 32 ? (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5) : (long)blockIdx.x;
   if (w >= (long)a.P * n_ac) return;
   const long p = w / n_ac;
   const int ac = (int)(w % n_ac);
@@ -59,10 +97,10 @@ __global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __gr
   double* yo = a.xs + ox + (size_t)(1 * n_ac + ac) * N;
   double* po = a.xs + ox + (size_t)(2 * n_ac + ac) * N;
   double cx = a.p0[ob + 0 * n_ac + ac], cy = a.p0[ob + 1 * n_ac + ac], cpsi = a.p0[ob + 2 * n_ac + ac];   // carries
-  for (int base = 0; base < N; base += 32) {
+  for (int base = 0; base < N; base += W) {
     const int i = base + lane;
     const bool valid = i < N;
-    double ph = 0.0, vv = 1.0, s, c;
+    double ph = 0.0, vv = 1.0, s, c, tot;
     if (valid) {
       ph = phi_in[i]; vv = v_in[i];
       if (a.bounded) {
@@ -75,12 +113,14 @@ __global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __gr
     double sp, cp;
     sincos_any(ph, sp, cp);
     const double dpsi = moves ? h * kG * sp * rcp_f(cp * vv) : 0.0;
-    const double psi = cpsi + warp_prefix(dpsi, lane);
+    const double psi = cpsi + UnitScan<W>::prefix(dpsi, tot, red[0]);
+    cpsi += tot;
     sincos_any(psi, s, c);
-    const double x = cx + warp_prefix(moves ? h * (vv * c - wx) : 0.0, lane);
-    const double y = cy + warp_prefix(moves ? h * (vv * s - wy) : 0.0, lane);
+    const double x = cx + UnitScan<W>::prefix(moves ? h * (vv * c - wx) : 0.0, tot, red[1]);
+    cx += tot;
+    const double y = cy + UnitScan<W>::prefix(moves ? h * (vv * s - wy) : 0.0, tot, red[2]);
+    cy += tot;
     if (valid) { xo[i] = x; yo[i] = y; po[i] = psi; }
-    cpsi = __shfl_sync(0xffffffffu, psi, 31); cx = __shfl_sync(0xffffffffu, x, 31); cy = __shfl_sync(0xffffffffu, y, 31);
   }
   if (lane == 0) {
     a.c[ob + 0 * n_ac + ac] = cx - a.p1[ob + 0 * n_ac + ac];
@@ -90,11 +130,12 @@ __global__ void __launch_bounds__(kShootThreads) shoot_forward_kernel(const __gr
 }
 
 // EXTRA = obstacle and/or collision terms present; the input-cost-only instance keeps the position-gradient code out
-template <bool EXTRA>
-__global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 8) shoot_adjoint_kernel(const __grid_constant__ ShootArgs a) {
+template <bool EXTRA, int W>
+__global__ void __launch_bounds__(W == 32 ? kShootThreads : W, W == 32 ? (EXTRA ? 4 : 8) : 1) shoot_adjoint_kernel(const __grid_constant__ ShootArgs a) {
+  __shared__ double red[3][kShootWide / 32];
   const d2dx_colloc_problem& Q = a.p;
-  const int N = Q.N, n_ac = Q.n_ac, lane = threadIdx.x & 31;
-  const long w = (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5);
+  const int N = Q.N, n_ac = Q.n_ac, lane = W == 32 ? (threadIdx.x & 31) : threadIdx.x;
+  const long w = W == 32 ? (long)blockIdx.x * kShootWarps + (threadIdx.x >> 5) : (long)blockIdx.x;
   if (w >= (long)a.P * n_ac) return;
   const long p = w / n_ac;
   const int ac = (int)(w % n_ac);
@@ -116,8 +157,9 @@ __global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 8) shoot_adjoint_ke
   }
   double Gx_c = gl[0], Gy_c = gl[1], Gp_c = gl[2];                              // carries: sums over the rows already done
   double cost = 0.0;
-  for (int base = ((N - 1) / 32) * 32; base >= 0; base -= 32) {
+  for (int base = ((N - 1) / W) * W; base >= 0; base -= W) {
     const int i = base + lane;
+    double tot;
     const bool valid = i < N, moves = valid && i > 0;
     double x = 0, y = 0, psi = 0, phi = 0, v = 1;
     if (valid) {
@@ -166,12 +208,16 @@ __global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 8) shoot_adjoint_ke
     }
     if (!moves) { ax = 0.0; ay = 0.0; }                                         // node 0 is fixed
     double Gx = Gx_c, Gy = Gy_c;                                                // without position costs Gx, Gy are the terminal multipliers
-    if constexpr (EXTRA) { Gx += warp_suffix(ax, lane); Gy += warp_suffix(ay, lane); }
+    if constexpr (EXTRA) {
+      Gx += UnitScan<W>::suffix(ax, tot, red[0]); Gx_c += tot;
+      Gy += UnitScan<W>::suffix(ay, tot, red[1]); Gy_c += tot;
+    }
     double s, c, sp, cp;
     sincos_any(psi, s, c);
     sincos_any(phi, sp, cp);
     const double m = moves ? Gx * (-h * v * s) + Gy * (h * v * c) : 0.0;        // x_i, y_i depend on psi_i
-    const double Gp = Gp_c + warp_suffix(m, lane);
+    const double Gp = Gp_c + UnitScan<W>::suffix(m, tot, red[2]);
+    Gp_c += tot;
     if (valid) {
       double jphi = 1.0, jv = 1.0;                                              // d(phi, v) / d theta
       if (a.bounded) {
@@ -189,9 +235,16 @@ __global__ void __launch_bounds__(kShootThreads, EXTRA ? 4 : 8) shoot_adjoint_ke
       a.grad[ou + (size_t)ac * N + i] = gphi * jphi;
       a.grad[ou + (size_t)(n_ac + ac) * N + i] = gv * jv;
     }
-    Gx_c = __shfl_sync(0xffffffffu, Gx, 0); Gy_c = __shfl_sync(0xffffffffu, Gy, 0); Gp_c = __shfl_sync(0xffffffffu, Gp, 0);
   }
   cost = warp_sum(cost);
+  if (W != 32) {                                                                // unit = block: add the warps' shares in order
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = cost;
+    __syncthreads();
+    cost = 0.0;
+#pragma unroll
+    for (int k = 0; k < W / 32; ++k) cost += red[0][k];
+  }
   if (lane == 0) {
     double lg = cost;
 #pragma unroll
@@ -214,6 +267,8 @@ static int check(const d2dx_colloc_problem* p, int P, const char* who) {
 }
 
 static unsigned shoot_grid(const d2dx_colloc_problem* p, int P) { return (unsigned)(((long)P * p->n_ac + kShootWarps - 1) / kShootWarps); }
+// few, long units: one block each (latency of one evaluation of a single problem: 32 serial row steps -> 4)
+static bool shoot_wide(const d2dx_colloc_problem* p, int P) { return (long)P * p->n_ac <= 296 && p->N > 96; }
 
 }  // namespace d2dx
 
@@ -228,7 +283,8 @@ extern "C" int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p, 
   set_bounds(a, bounds);
   a.p = *p; a.P = P; a.u = u; a.p0 = p0; a.p1 = p1; a.uphys = u_phys; a.xs = xs; a.c = c;
   D2DX_CUDA(cudaSetDevice(h->device));
-  shoot_forward_kernel<<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
+  if (shoot_wide(p, P)) shoot_forward_kernel<kShootWide><<<(unsigned)((long)P * p->n_ac), kShootWide, 0, as_stream(stream)>>>(a);
+  else shoot_forward_kernel<32><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
   D2DX_LAUNCH_CHECK("shoot_forward_kernel");
   return D2DX_OK;
 }
@@ -251,8 +307,14 @@ extern "C" int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p, 
     for (int k = 0; k < 5; ++k) a.box[k] = state_box[k];
   }
   const bool extra = a.boxed || (on(p->kobs) && p->n_obs > 0) || (on(p->kcol) && p->n_ac > 1);
-  if (extra) shoot_adjoint_kernel<true><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
-  else shoot_adjoint_kernel<false><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
+  if (shoot_wide(p, P)) {
+    const unsigned grid = (unsigned)((long)P * p->n_ac);
+    if (extra) shoot_adjoint_kernel<true, kShootWide><<<grid, kShootWide, 0, as_stream(stream)>>>(a);
+    else shoot_adjoint_kernel<false, kShootWide><<<grid, kShootWide, 0, as_stream(stream)>>>(a);
+  } else {
+    if (extra) shoot_adjoint_kernel<true, 32><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
+    else shoot_adjoint_kernel<false, 32><<<shoot_grid(p, P), kShootThreads, 0, as_stream(stream)>>>(a);
+  }
   D2DX_LAUNCH_CHECK("shoot_adjoint_kernel");
   return D2DX_OK;
 }

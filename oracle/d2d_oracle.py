@@ -765,3 +765,30 @@ def shoot_lagrangian(phi, v, p0, p1, h, wind, spec, lam, rho, multi=None, state_
         cost += wgt * spec.get("obj_scale", 1.) / N * np.sum(ex ** 2 + ey ** 2)
     c = np.stack([x[:, -1], y[:, -1], psi[:, -1]]) - np.asarray(p1, float).reshape(3, -1)
     return cost, c, cost + np.sum(np.asarray(lam) * c) + 0.5 * rho * np.sum(c * c)
+
+
+def shoot_value_and_grad(phi, v, p0, p1, h, wind, spec, lam, rho, multi=None, g=G):
+    """Lagrangian of `shoot_lagrangian` and its exact gradient with respect to the inputs by the adjoint recursion,
+    vectorised with cumulative sums -- for the input-cost terms only (kvel, kbank; no obstacle / collision / box terms).
+    phi, v: (n_ac, N).  Returns L, dL/dphi (n_ac, N), dL/dv (n_ac, N), cost, c."""
+    phi, v = np.atleast_2d(np.asarray(phi, float)), np.atleast_2d(np.asarray(v, float))
+    n_ac, N = phi.shape
+    multi = (n_ac > 1) if multi is None else multi
+    x, y, psi = shoot_states(phi, v, p0, h, wind)
+    s = spec.get("obj_scale", 1.)
+    vsp, kvel, kbank = spec.get("vsp", 10.), spec.get("kvel", 0.), spec.get("kbank", 0.)
+    norm_in = s / N / n_ac if multi else s / N
+    cost = norm_in * (kvel * np.sum(np.square(v - vsp)) + kbank * np.sum(np.square(phi)))
+    c = np.stack([x[:, -1], y[:, -1], psi[:, -1]]) - np.asarray(p1, float).reshape(3, -1)
+    lam = np.asarray(lam, float).reshape(3, -1)
+    L = cost + np.sum(lam * c) + 0.5 * rho * np.sum(c * c)
+    gl = lam + rho * c                                            # dL / d terminal state, (3, n_ac)
+    # x_N = x_0 + sum_j h (v_j cos psi_j - w): d x_N / d psi_j = -h v_j sin psi_j, and psi_j depends on (phi_i, v_i) for i <= j
+    sx, sy = -h * v[:, 1:] * np.sin(psi[:, 1:]), h * v[:, 1:] * np.cos(psi[:, 1:])
+    Gpsi = np.cumsum((gl[0][:, None] * sx + gl[1][:, None] * sy)[:, ::-1], axis=1)[:, ::-1] + gl[2][:, None]
+    dphi, dv = np.zeros_like(phi), np.zeros_like(v)
+    dphi[:, 1:] = Gpsi * h * g / (np.cos(phi[:, 1:]) ** 2 * v[:, 1:])
+    dv[:, 1:] = Gpsi * (-h * g * np.tan(phi[:, 1:]) / v[:, 1:] ** 2) + gl[0][:, None] * h * np.cos(psi[:, 1:]) + gl[1][:, None] * h * np.sin(psi[:, 1:])
+    dphi += norm_in * kbank * 2 * phi
+    dv += norm_in * kvel * 2 * (v - vsp)
+    return L, dphi, dv, cost, c

@@ -91,6 +91,33 @@ def test_shoot_unbounded_gradient():
             assert abs(g[p, k, a, i] - fd) <= 1e-7 * max(1., abs(fd)) + 2e-11 * abs(L[p])
 
 
+def test_shoot_gradient_against_the_oracle_adjoint():
+    """Whole gradient arrays (not samples) against the oracle's own adjoint: input costs, three aircraft, 300 nodes."""
+    import torch
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    from d2d_b200.shooting import ShootingNLP
+    rng = np.random.default_rng(9)
+    n_ac, N, P, h, wind = 3, 300, 3, 0.05, (1.0, -0.5)
+    spec = dict(vsp=12., kvel=3., kbank=2., obj_scale=0.5)
+    prob = CollocationProblem(n_ac, N, h, wind=wind, cost=CostSpec(vsp=12., kvel=3., kbank=2.), obj_scale=0.5, multi=True)
+    p0, p1 = rng.uniform(-5, 5, (P, 3, n_ac)), rng.uniform(-5, 60, (P, 3, n_ac))
+    nlp = ShootingNLP(prob, p0, p1, (-0.6, 0.6), (9., 15.), P=P)
+    phi, v = rng.uniform(-0.4, 0.4, (P, n_ac, N)), rng.uniform(9.5, 14.5, (P, n_ac, N))
+    e = nlp.eng
+    u = e.to_device(np.ascontiguousarray(np.stack([phi, v], 1)))
+    nlp.lam.copy_(torch.as_tensor(rng.normal(0, 1, (P, 3, n_ac)))); nlp.rho.copy_(torch.as_tensor(rng.uniform(1, 50, P)))
+    e.shoot_forward(prob.c, P, u, None, nlp.p0, nlp.p1, None, nlp.xs, nlp.c)
+    e.shoot_adjoint(prob.c, P, u, None, None, nlp.xs, nlp.c, nlp.lam, nlp.rho, nlp.cost_ac, nlp.lagr_ac, nlp.grad)
+    g, L = nlp.grad.cpu().numpy(), nlp.lagr_ac.sum(1).cpu().numpy()
+    lam, rho = nlp.lam.cpu().numpy(), nlp.rho.cpu().numpy()
+    for p in range(P):
+        Lo, dphi, dv, _, _ = orc.shoot_value_and_grad(phi[p], v[p], p0[p], p1[p], h, wind, spec, lam[p], rho[p], multi=True)
+        assert abs(L[p] - Lo) <= 1e-12 * abs(Lo)
+        scale = max(np.abs(dphi).max(), np.abs(dv).max())
+        np.testing.assert_allclose(g[p, 0], dphi, rtol=0, atol=1e-11 * scale)
+        np.testing.assert_allclose(g[p, 1], dv, rtol=0, atol=1e-11 * scale)
+
+
 @pytest.mark.parametrize("n", [40, 5000])
 def test_device_driver_on_analytic_problems(n):
     """d2dx_al_lbfgs_tick alone, fed by torch-evaluated functions: min |x - a|^2 s.t. sum x = 1 and x_0 - x_1 = 0.5

@@ -102,3 +102,20 @@ def test_multi_experiment_table():
     S.exp_4_1.set_case(2); assert S.exp_4_1.obstacles == ((70, -10, 15), (70, 25, 15)) and S.exp_4_1.cost.vsp == 14.
     S.exp_3_1.set_case(1); assert S.exp_3_1.cost.c == (25, -10)
     assert S.trap_4.cost.kvel == 70. and S.trap_4.x_constraint == (-150, 150)
+
+
+def test_oracle_adjoint_gradient_against_finite_differences():
+    rng = np.random.default_rng(4)
+    n_ac, N, h, wind = 2, 40, 0.1, (0.7, -0.4)
+    phi, v = rng.uniform(-0.4, 0.4, (n_ac, N)), rng.uniform(9.5, 14.5, (n_ac, N))
+    p0, p1 = rng.uniform(-5, 5, (3, n_ac)), rng.uniform(0, 30, (3, n_ac))
+    spec, lam, rho = dict(vsp=12., kvel=3., kbank=2., obj_scale=1.5), rng.normal(0, 1, (3, n_ac)), 4.0
+    L, dphi, dv, cost, c = orc.shoot_value_and_grad(phi, v, p0, p1, h, wind, spec, lam, rho, multi=True)
+    co, cc, Lo = orc.shoot_lagrangian(phi, v, p0, p1, h, wind, spec, lam, rho, multi=True)
+    assert abs(L - Lo) < 1e-12 * abs(Lo) and abs(cost - co) < 1e-14 and np.abs(c - cc).max() == 0
+    for (k, a, i) in ((0, 0, 1), (0, 1, 39), (1, 0, 17), (1, 1, 0), (0, 0, 0), (1, 1, 39)):
+        d = np.zeros((2, n_ac, N)); d[k, a, i] = 1e-4
+        F = lambda s_: orc.shoot_lagrangian(phi + s_ * d[0], v + s_ * d[1], p0, p1, h, wind, spec, lam, rho, multi=True)[2]
+        fd = (8 * (F(1) - F(-1)) - (F(2) - F(-2))) / 12e-4
+        an = (dphi if k == 0 else dv)[a, i]
+        assert abs(an - fd) <= 1e-7 * max(1., abs(fd)) + 2e-11 * abs(Lo), (k, a, i, an, fd)
