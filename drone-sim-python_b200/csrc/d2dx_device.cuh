@@ -283,7 +283,12 @@ __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c
     phi += h6 * (k1f + 2.0 * k2f + 2.0 * k3f + k4f);
     v += h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
   }
-  if (!fast_ok) { rk4_step_generic(a, X, phi_c, v_c, dt, nsub); return; }   // NaN compares false: also caught
+  if (!fast_ok) {                            // NaN compares false: also caught.  The generic path works on a copy, so that
+    double T[5] = {X[0], X[1], X[2], X[3], X[4]};   // the caller's state stays in registers (only T has its address taken)
+    rk4_step_generic(a, T, phi_c, v_c, dt, nsub);
+    X[0] = T[0]; X[1] = T[1]; X[2] = T[2]; X[3] = T[3]; X[4] = T[4];
+    return;
+  }
   X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
 }
 #endif
