@@ -239,6 +239,7 @@ def secondary_metrics(eng, hbm_peak):
 
     class exp_c3(pl.exp_0):
         t1, hz = 20., 50.
+    _w = pl.Planner(pl.exp_0); _w.configure(tol=1e-8); _w.run()      # untimed: first CUDA-graph capture / module load of the process
     for tag, n_starts in (("planner_solve_c3_single", 1), ("planner_solve_c3_64starts", 64)):
         p = pl.Planner(exp_c3)
         p.configure(tol=1e-8)

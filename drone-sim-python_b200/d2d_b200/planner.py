@@ -21,11 +21,11 @@ class _PlannerBase:
     def configure(self, tol=1e-8, max_iter=3000):
         self.tol, self.max_iter = tol, max_iter
 
-    def run(self, initial_guess=None, n_starts=1, seed=0, verbose=False, state_weight=1000., **_):
+    def run(self, initial_guess=None, n_starts=1, seed=0, verbose=False, state_weight=1000., min_solved=None, **_):
         """`self.solution, info = prob.solve(initial_guess)` of 06_optyplan.py:117-125 / 07_multioptyplan.py:80-88,
         solved by single shooting + augmented Lagrangian (shooting.solve).  Only the input part of `initial_guess`
         seeds the solve (the states follow from the inputs).  n_starts > 1 adds randomly perturbed starts solved in the
-        same launches; the feasible one of least cost is kept.  State bounds (x/y_constraint) enter as a soft box
+        same launches; the feasible one of least cost is kept (`min_solved=k` returns as soon as k starts have converged).  State bounds (x/y_constraint) enter as a soft box
         (`state_weight` x squared excess, averaged over the nodes); `self.info["state_bounds_ok"]` tells whether the result
         respects them strictly."""
         guess = self.get_initial_guess() if initial_guess is None else np.asarray(initial_guess, dtype=float)
@@ -48,8 +48,9 @@ class _PlannerBase:
         nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts, state_box=box)
         tol = getattr(self, "tol", 1e-8)
         driver = shooting.solve_host if _.get("driver") == "host" else shooting.solve
+        kw = {} if driver is shooting.solve_host else {"min_solved": min_solved}
         theta, info = driver(nlp, nlp.theta_of(np.clip(phi, *phi_b), np.clip(v, *v_b)), ctol=min(tol, 1e-6),
-                             max_inner=min(getattr(self, "max_iter", 3000), 500), verbose=verbose)
+                             max_inner=min(getattr(self, "max_iter", 3000), 500), verbose=verbose, **kw)
         frees = nlp.free_vectors()
         if self.prob.c.perm_phi:                                                  # opty input order: place the input blocks by rank
             frees = self._to_opty_order(frees)

@@ -161,10 +161,11 @@ def solve_host(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_
 
 
 def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner=500, rho0=10., rho_max=1e6, m=20,
-          window=10, ls_max=30, ticks_per_check=64, max_ticks=None, use_graph=True, verbose=False):
+          window=10, ls_max=30, ticks_per_check=64, max_ticks=None, use_graph=True, min_solved=None, verbose=False):
     """Device-resident solve: every tick = [d2dx_shoot_forward, d2dx_shoot_adjoint, d2dx_al_lbfgs_tick]; `ticks_per_check`
     ticks are captured in one CUDA graph and replayed until no problem is iterating (one host read per replay).
-    Problems advance independently (own line search, multipliers, termination).  Returns theta (P, n) at the solutions
+    Problems advance independently (own line search, multipliers, termination); `min_solved` stops the replays as soon as
+    that many problems have converged (multi-start: the stragglers are usually the infeasible starts).  Returns theta (P, n) at the solutions
     and an info dict; `nlp.free_vectors()` then gives the planner-layout solutions."""
     from . import _lib
     e, P, n, n_con = nlp.eng, nlp.P, nlp.n, nlp.n_con
@@ -193,16 +194,15 @@ def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner
         replay = g.replay
     max_ticks = max_ticks or int(1.5 * max_outer * max_inner)
     done_ticks = 1
+    meta = state[off[5]:off[5] + P * off[7] // 2].view(torch.int32).view(P, off[7])
     while done_ticks < max_ticks:
         replay()
         done_ticks += ticks_per_check
         running = int(n_running.item())
         if verbose:
             print(f"ticks {done_ticks}: {running} of {P} problems iterating")
-        if running == 0:
+        if running == 0 or (min_solved is not None and int((meta[:, 0] == 2).sum().item()) >= min_solved):
             break
-    sc = state[off[3]:off[3] + P * off[6]].view(P, off[6])
-    meta = state[off[5]:off[5] + P * off[7] // 2].view(torch.int32).view(P, off[7])
     theta = state[off[1]:off[1] + P * n].view(P, n).clone()
     nlp.launch(theta)                                                            # buffers (states, physical inputs, c) at the solutions
     meta_h = meta.cpu().numpy()

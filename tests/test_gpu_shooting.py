@@ -172,6 +172,9 @@ def test_device_and_host_drivers_agree_and_population_solves():
     N = p.num_nodes
     theta, info = shooting.solve(nlp, nlp.theta_of(np.full((1, N), 0.1), np.full((1, N), 12.)), ctol=1e-8)
     assert (info["flag"] == 2).sum() >= 0.8 * P, info["flag"]      # some targets need a turn tighter than the bank limit allows
+    _, info_early = shooting.solve(nlp, nlp.theta_of(np.full((1, N), 0.1), np.full((1, N), 12.)), ctol=1e-8, min_solved=10)
+    assert 10 <= (info_early["flag"] == 2).sum() and info_early["ticks"] <= info["ticks"]      # early exit of a multi-start style run
+    theta, info = shooting.solve(nlp, nlp.theta_of(np.full((1, N), 0.1), np.full((1, N), 12.)), ctol=1e-8)
     frees = nlp.free_vectors()
     ok = info["flag"] == 2
     N3 = 3 * (N - 1)
