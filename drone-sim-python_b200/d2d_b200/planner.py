@@ -17,6 +17,23 @@ def _node_of(t, t0, h, N):
     return int(min(max(round((t - t0) / h), 0), N - 1))
 
 
+def inputs_from_path(x, y, h, phi_b, v_b, smooth_s=1.0, g=9.81):
+    """Inputs that roughly fly a guessed path (x, y per node): airspeed from the node spacing, bank from the heading rate
+    (phi = atan(v psi_dot / g)) after a moving average of `smooth_s` seconds, both clipped inside the bounds.  A shooting
+    solve cannot use a state guess directly; this turns the planners' `tri` / straight-line guesses into an input guess
+    that bends the same way."""
+    x, y = np.asarray(x, float), np.asarray(y, float)
+    dx, dy = np.gradient(x), np.gradient(y)
+    v = np.clip(np.hypot(dx, dy) / h, v_b[0] + 0.05 * (v_b[1] - v_b[0]), v_b[1] - 0.05 * (v_b[1] - v_b[0]))
+    psi = np.unwrap(np.arctan2(dy, dx))
+    w = max(int(round(smooth_s / h)) | 1, 1)
+    psid = np.gradient(psi) / h
+    if w > 1 and len(psid) > w:
+        psid = np.convolve(np.pad(psid, w // 2, mode="edge"), np.ones(w) / w, mode="valid")
+    phi = np.arctan(v * psid / g)
+    return np.clip(phi, 0.9 * phi_b[0], 0.9 * phi_b[1]), v
+
+
 class _PlannerBase:
     def configure(self, tol=1e-8, max_iter=3000):
         self.tol, self.max_iter = tol, max_iter
@@ -30,11 +47,16 @@ class _PlannerBase:
         respects them strictly."""
         guess = self.get_initial_guess() if initial_guess is None else np.asarray(initial_guess, dtype=float)
         n, N = self._n_ac, self.num_nodes
-        phi = np.stack([guess[sl] for sl in self._phi_slices()])[None]
-        v = np.stack([guess[sl] for sl in self._v_slices()])[None]
         phi_b, v_b = self._bounds["phi"], self._bounds["v"]
         if phi_b is None or v_b is None:
             raise ValueError("run() needs phi_constraint and v_constraint (lo, hi) on the experiment / scenario")
+        phi = np.stack([guess[sl] for sl in self._phi_slices()])
+        v = np.stack([guess[sl] for sl in self._v_slices()])
+        if _.get("guess_from_path", False):                       # opt-in: bend the input guess like the guessed path (measured: no gain on upstream's experiments)
+            for a, (sx, sy) in enumerate(zip(self._x_slices(), self._y_slices())):
+                if np.ptp(guess[sx]) + np.ptp(guess[sy]) > 1e-9 and not np.any(phi[a]):
+                    phi[a], v[a] = inputs_from_path(guess[sx], guess[sy], self.time_step, phi_b, v_b)
+        phi, v = phi[None], v[None]
         if n_starts > 1:
             rng = np.random.default_rng(seed)
             k = np.concatenate([[0.], np.ones(n_starts - 1)])[:, None, None]      # start 0 is the caller's guess

@@ -119,3 +119,13 @@ def test_oracle_adjoint_gradient_against_finite_differences():
         fd = (8 * (F(1) - F(-1)) - (F(2) - F(-2))) / 12e-4
         an = (dphi if k == 0 else dv)[a, i]
         assert abs(an - fd) <= 1e-7 * max(1., abs(fd)) + 2e-11 * abs(Lo), (k, a, i, an, fd)
+
+
+def test_inputs_from_path_on_a_circle():
+    """A circle of radius 40 m flown at 12 m/s needs tan(phi) = v^2 / (g r)."""
+    from d2d_b200.planner import inputs_from_path
+    h, r, v = 0.1, 40., 12.
+    a = np.arange(200) * h * v / r
+    phi, vv = inputs_from_path(r * np.cos(a), r * np.sin(a), h, (-0.7, 0.7), (9., 15.))
+    np.testing.assert_allclose(vv[5:-5], v, rtol=1e-3)
+    np.testing.assert_allclose(np.tan(phi[20:-20]), v * v / (9.81 * r), rtol=2e-3)
