@@ -187,14 +187,16 @@ __global__ void __launch_bounds__(kLbThreads) al_lbfgs_tick_kernel(const __grid_
       for (int i = tid; i < n; i += kLbThreads) xt[i] = x[i];
     } else {
       const double rho = a.rho[p], cprev = sc[SC_CPREV];
+      const bool raise = (cprev < 0.0 || cm > 0.25 * cprev) && rho < a.o.rho_max;
       for (int k = tid; k < a.n_con; k += kLbThreads) lam[k] += rho * cacc[k];
       team_sync<kLbThreads>();
       if (tid == 0) {
-        if (cprev < 0.0 || cm > 0.25 * cprev) a.rho[p] = fmin(rho * 3.0, a.o.rho_max);
+        if (raise) a.rho[p] = fmin(rho * 3.0, a.o.rho_max);
         sc[SC_CPREV] = cm;
       }
       for (int i = tid; i < n; i += kLbThreads) xt[i] = x[i];
-      flag = LB_EVAL0; cnt = 0; have = 0; head = 0;
+      flag = LB_EVAL0;
+      if (raise || !a.o.keep_history) { cnt = 0; have = 0; head = 0; }   // a multiplier update alone changes the Hessian little: keep the pairs
     }
     if (tid == 0) { sc[SC_CMAX] = cm; mi[MI_OUTER] = outer; }
   }

@@ -91,7 +91,8 @@ class Pursuit(C.Structure):
 class LbfgsOptions(C.Structure):
     """d2dx_lbfgs_options (include/d2dx.h)."""
     _fields_ = [("m", C.c_int32), ("max_inner", C.c_int32), ("max_outer", C.c_int32), ("ls_max", C.c_int32), ("window", C.c_int32),
-                ("gtol", C.c_double), ("ftol", C.c_double), ("ctol", C.c_double), ("rho0", C.c_double), ("rho_max", C.c_double)]
+                ("gtol", C.c_double), ("ftol", C.c_double), ("ctol", C.c_double), ("rho0", C.c_double), ("rho_max", C.c_double),
+                ("keep_history", C.c_int32)]
 
 
 def _load():

@@ -161,7 +161,8 @@ def solve_host(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_
 
 
 def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner=500, rho0=10., rho_max=1e6, m=20,
-          window=10, ls_max=30, ticks_per_check=64, max_ticks=None, use_graph=True, min_solved=None, verbose=False):
+          window=10, ls_max=30, ticks_per_check=64, max_ticks=None, use_graph=True, min_solved=None, keep_history=False,
+          verbose=False):
     """Device-resident solve: every tick = [d2dx_shoot_forward, d2dx_shoot_adjoint, d2dx_al_lbfgs_tick]; `ticks_per_check`
     ticks are captured in one CUDA graph and replayed until no problem is iterating (one host read per replay).
     Problems advance independently (own line search, multipliers, termination); `min_solved` stops the replays as soon as
@@ -170,7 +171,7 @@ def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner
     from . import _lib
     e, P, n, n_con = nlp.eng, nlp.P, nlp.n, nlp.n_con
     o = _lib.LbfgsOptions(m=m, max_inner=max_inner, max_outer=max_outer, ls_max=ls_max, window=window, gtol=gtol, ftol=ftol,
-                          ctol=ctol, rho0=rho0, rho_max=rho_max)
+                          ctol=ctol, rho0=rho0, rho_max=rho_max, keep_history=int(keep_history))
     off = e.lbfgs_layout(P, n, n_con, o)
     state = e.empty(off[0])
     n_running = e.zeros(1, dtype=torch.int32)

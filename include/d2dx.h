@@ -355,6 +355,7 @@ typedef struct {
   double ftol;
   double ctol;          /* a problem is solved when max|c| < ctol after an inner loop */
   double rho0, rho_max; /* penalty: starts at rho0, x3 (up to rho_max) when max|c| did not fall to a quarter */
+  int32_t keep_history; /* 1: keep the L-BFGS pairs across multiplier updates that leave rho unchanged; 0: restart every time */
 } d2dx_lbfgs_options;
 /* offsets (in doubles) into the state buffer: [0] total size, [1] x[P][n], [2] g[P][n], [3] scalars[P][offsets[6]]
  * (0 L, 4 previous max|c|, 5 max|c|, 6 cost), [4] c at x [P][n_con], [5] int32 meta[P][offsets[7]]
