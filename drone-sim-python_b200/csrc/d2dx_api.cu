@@ -315,6 +315,7 @@ int d2dx_dfff_control(d2dx_handle* h, const d2dx_traj_table* tt, const double* X
   if (int rc = check_table(tt, "d2dx_dfff_control")) return rc;
   d2dx_dfff_gains g;
   if (gains_host) g = *gains_host; else d2dx_dfff_default_gains(&g);
+  D2DX_CHECK_ARG(g.err_sat[0] >= 0 && g.err_sat[1] >= 0 && g.err_sat[2] >= 0, "gains: err_sat must be >= 0 (symmetric saturation)");
   D2DX_CUDA(cudaSetDevice(h->device));
   dfff_control_kernel<<<grid_for(tt->n_traj), kThreads, 0, as_stream(stream)>>>(*tt, X, t, W, ac, g, U, Xr, K, care_state);
   D2DX_LAUNCH_CHECK("dfff_control_kernel");

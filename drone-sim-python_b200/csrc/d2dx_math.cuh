@@ -112,10 +112,11 @@ __device__ __forceinline__ void sincos(double x, double& s, double& c) {
   pc = fma(pc, z, kTab[18]);
   const double sn = fma(ps * z, r, r);
   const double cs = fma(pc, z, 1.0);
-  double a = (q & 1) ? cs : sn;
-  double b = (q & 1) ? sn : cs;
-  s = (q & 2) ? -a : a;
-  c = ((q + 1) & 2) ? -b : b;
+  const double a = (q & 1) ? cs : sn;
+  const double b = (q & 1) ? sn : cs;
+  // quadrant signs straight into the sign bit (one integer op each instead of a negate and two selects)
+  s = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
+  c = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
 }
 
 // tan(x) as a ratio: tan x = tn / td with tn = x P(x^2), td = Q(x^2); valid for |x| <= 1.15 (bank angles).  The caller

@@ -228,6 +228,7 @@ extern "C" int d2dx_rollout_dfff(d2dx_handle* h, const d2dx_scenarios* s, const 
   a.s = *s; a.o = *out; a.time = time;
   a.i_begin = i_begin; a.i_end = i_end; a.nsub = nsub; a.final_control = final_control;
   if (gains_host) a.g = *gains_host; else d2dx_dfff_default_gains(&a.g);
+  D2DX_CHECK_ARG(a.g.err_sat[0] >= 0 && a.g.err_sat[1] >= 0 && a.g.err_sat[2] >= 0, "gains: err_sat must be >= 0 (symmetric saturation)");
   a.cc = care_const(a.g);
   D2DX_CHECK_ARG(a.g.q_pos > 0 && a.g.q_psi > 0 && a.g.r_phi > 0 && a.g.r_v > 0, "d2dx_rollout_dfff: Q, R must be positive");
   D2DX_CUDA(cudaSetDevice(h->device));
