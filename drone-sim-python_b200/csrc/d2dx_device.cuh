@@ -229,6 +229,7 @@ static __device__ __noinline__ void rk4_step_generic(const AcPar& a, double* X, 
 }
 
 #ifdef D2DX_USE_LIBM
+template <bool ONE = false>
 __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
   rk4_step_generic(a, X, phi_c, v_c, dt, nsub);
 }
@@ -253,13 +254,17 @@ __device__ __forceinline__ void stage_heading(double s0, double c0, double d, do
 // one full sincos (stages 2-4 by angle addition of the increment h psi_dot), tan(phi) is a Pade ratio folded into
 // the 1/v reciprocal.  Validity (|increment| < 0.1, |phi| <= 1.15) is accumulated in one flag; if it is ever violated
 // the control step is redone with rk4_step_generic.
+// ONE = the caller guarantees nsub == 1 (the Monte-Carlo rollouts): no sub-step loop, so no loop-carried register copies.
+template <bool ONE = false>
 __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
   // h = dt / nsub and h / 6 as written in the oracle cost two IEEE divisions (~40 instructions) per control step; the
   // reciprocal forms differ by at most one ulp of h (1e-16 relative on one step length), far inside the 1e-9 parity bound
-  const double h = nsub == 1 ? dt : dt * (1.0 / nsub), hh = 0.5 * h, h6 = h * (1.0 / 6.0);
+  const double h = (ONE || nsub == 1) ? dt : dt * (1.0 / nsub), hh = 0.5 * h, h6 = h * (1.0 / 6.0);
   double x = X[0], y = X[1], psi = X[2], phi = X[3], v = X[4];
   bool fast_ok = true;                       // every stage increment < 0.1 rad and every bank angle <= 1.15 rad
-  for (int sub = 0; sub < nsub; ++sub) {
+  const int n_sub = ONE ? 1 : nsub;
+#pragma unroll
+  for (int sub = 0; sub < n_sub; ++sub) {
     double s1, c1, s, c, d;
     sincos_b(psi, s1, c1);
     // stage 1

@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
     // (computing the next reference here, one step ahead and interleaved with the RK4 stages, was tried in round 1:
     //  the extra live state pushed the kernel over 128 registers and it ran 7 % slower)
     const double t1 = a.time[i + 1];
-    rk4_step(load_ac(), X, u_phi, u_v, t1 - t, a.nsub);
+    if (a.nsub == 1) rk4_step<true>(load_ac(), X, u_phi, u_v, t1 - t, 1);        // uniform branch on a kernel argument
+    else rk4_step(load_ac(), X, u_phi, u_v, t1 - t, a.nsub);
     t = t1;
     if (i + 1 == ev_next) {            // perturbation event (05_test_simulation.py:32)
 #pragma unroll
