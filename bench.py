@@ -27,11 +27,11 @@ METRIC = "closed-loop aircraft-steps/s"
 UNIT = "aircraft-steps/s"
 # Executed fp64 flop per aircraft-step of rollout_dfff_kernel<CIRCLE> (DADD + DMUL + 2 x DFMA thread-instructions
 # from the ncu capture under profiles/, divided by scenarios x steps); see DESIGN.md "Roofline accounting".
-FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "716"))
+FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "704"))
 # From the same capture (profiles/r1_final_rollout_dfff_circle.md, one launch of 1e6 scenarios x 1000 steps, log x100):
 # dram__bytes_read.sum + dram__bytes_write.sum, and the fp64 pipe's active fraction.
-NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 183.78e6 + 618.77e6 
-NCU_FP64_PIPE_ACTIVE = 0.750
+NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 185.17e6 + 628.88e6
+NCU_FP64_PIPE_ACTIVE = 0.757
 LOG_BYTES_PER_LOGGED_SAMPLE = 56          # 5 state + 2 input doubles
 
 
