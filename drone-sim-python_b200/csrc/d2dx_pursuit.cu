@@ -19,14 +19,19 @@ struct PursuitArgs {
   int32_t* idx_log;
 };
 
-// nearest sample: np.argmin(np.linalg.norm(pts - X[:2], axis=1)) -- sqrt(dx*dx + dy*dy) without contraction, first minimum
+// nearest sample: np.argmin(np.linalg.norm(pts - X[:2], axis=1)) -- sqrt(dx*dx + dy*dy) without contraction, first minimum.
+// The square root (correctly rounded, as NumPy's) is only taken for candidates: a point can only beat the running minimum
+// if its squared distance is within a few ulp of, or below, the squared distance of the current best.
 __device__ __forceinline__ int nearest_point(const d2dx_pursuit& p, double x, double y, int lane) {
-  double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+  double best = __longlong_as_double(0x7ff0000000000000LL), lim = best;   // +inf
   int bi = 0x7fffffff;
   for (int j = lane; j < p.n_pts; j += 32) {
     const double dx = p.px[j] - x, dy = p.py[j] - y;
-    const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-    if (d < best) { best = d; bi = j; }                      // ascending j per lane: strict < keeps the first
+    const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    if (d2 <= lim) {
+      const double d = sqrt(d2);
+      if (d < best) { best = d; bi = j; lim = d2 * (1.0 + 8.9e-16); }    // ascending j per lane: strict < keeps the first
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -34,7 +39,7 @@ __device__ __forceinline__ int nearest_point(const d2dx_pursuit& p, double x, do
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
-  return bi;
+  return bi == 0x7fffffff ? 0 : bi;                  // non-finite position: np.argmin of an all-NaN array is 0
 }
 
 __device__ __forceinline__ void pursuit_law(const d2dx_pursuit& p, const double* X, int idx, double& phi_sp, double& v_sp) {
