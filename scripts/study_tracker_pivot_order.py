@@ -4,6 +4,7 @@ Jacobian (sympy) of the same six equations in the same unknowns as the kernel, 2
 kernel's cold start for tau_phi in {0.01, 0.1, 0.9667}, v in [4, 30] m/s, |phi| <= 1.1; exhaustive search over the 720
 row orders.  Result (printed): order (2, 0, 3, 1, 4, 5), worst relative error 1.6e-15; identity order 1.8e-11.
 CPU only (numpy, scipy, sympy); takes about two minutes."""
+import itertools
 import numpy as np, scipy.linalg, sympy as sp
 g=9.81
 q1,q3,q4,q5=1.,0.1,0.01,0.01; r1,r2=8.,1.
