@@ -129,3 +129,26 @@ def test_inputs_from_path_on_a_circle():
     phi, vv = inputs_from_path(r * np.cos(a), r * np.sin(a), h, (-0.7, 0.7), (9., 15.))
     np.testing.assert_allclose(vv[5:-5], v, rtol=1e-3)
     np.testing.assert_allclose(np.tan(phi[20:-20]), v * v / (9.81 * r), rtol=2e-3)
+
+
+def test_opty_input_block_order_mapping():
+    """MultiPlanner._to_opty_order: numeric input blocks [phi_0..phi_{n-1} | v_0..v_{n-1}] -> opty's name-sorted blocks
+    (phi0, phi1, phi10, phi11, phi2, ... then v0, v1, v10, ...), states untouched."""
+    from d2d_b200 import planner as pl, multiopty_scenarios as S
+
+    class scen12(S.exp_0):
+        p0s = tuple((float(i), 0., 0., 0., 10.) for i in range(12))
+        p1s = tuple((float(i), 50., 0., 0., 10.) for i in range(12))
+        hz, t1 = 1., 3.
+    p = pl.MultiPlanner(scen12, initialize=False)
+    n, N = 12, p.num_nodes
+    free = np.arange(5 * n * N, dtype=float)[None]
+    out = p._to_opty_order(free)
+    np.testing.assert_array_equal(out[:, :3 * n * N], free[:, :3 * n * N])
+    names = sorted([f"phi{i}" for i in range(n)] + [f"v{i}" for i in range(n)])
+    o = 3 * n * N
+    for rank, nm in enumerate(names):
+        i = int(nm.lstrip("phiv"))
+        src = o + (i if nm.startswith("phi") else n + i) * N
+        np.testing.assert_array_equal(out[0, o + rank * N:o + (rank + 1) * N], free[0, src:src + N])
+    assert names[:4] == ["phi0", "phi1", "phi10", "phi11"]
