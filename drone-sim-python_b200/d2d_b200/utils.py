@@ -1,15 +1,14 @@
-"""Small helpers of `d2d.utils` (d2d/utils.py:7-18) kept for import compatibility."""
-from .guidance import norm_mpi_pi  # noqa: F401  (d2d/utils.py:7; evaluated by the engine)
+"""Import-compatible stand-in for `d2d.utils` (d2d/utils.py:7-18): the angle wrap is evaluated by the engine, the wind
+field is the constant one of the planners with this module's (x, y, t) argument order."""
+from .guidance import norm_mpi_pi  # noqa: F401  (d2d/utils.py:7)
+from . import opty_utils as _d2ou
 
 
-class WindField:
-    """Constant wind with the numeric / symbolic sampling names of d2d/utils.py:10-18."""
+class WindField(_d2ou.WindField):
+    """d2d/utils.py:10-18 samples with (x, y, t); d2d/opty_utils.py:18-27 with (t, x, y).  The wind is constant, so both
+    return the stored vector; only the signatures differ."""
 
-    def __init__(self, w=[0., 0.]):
-        self.w = w
-
-    def sample_num(self, _x, _y, _t):
+    def _constant(self, *_position_and_time):
         return self.w
 
-    def sample_sym(self, _x, _y, _t):
-        return self.w
+    sample_num = sample_sym = _constant
