@@ -1,8 +1,9 @@
 """Prototype 2: primal log-barrier Newton (interior point) on the full collocation NLP, physical inputs with bounds,
 exact Lagrangian Hessian + barrier Hessian, sparse KKT, fraction-to-boundary, l1 merit.  CPU / SciPy -- R&D for round 2."""
 import sys, time, numpy as np, sympy as sp, scipy.sparse as ss, scipy.sparse.linalg as sl
-sys.path.insert(0, '/root/repo')
-from oracle import d2d_oracle as orc
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..', 'drone-sim-python_b200'))
+from d2d_b200 import opty_utils as orc      # triangle() initial guess only
 g = 9.81
 psi, phi, v, lx, ly, lp, h, kvel, kbank, vsp, nrm = sp.symbols('psi phi v lx ly lp h kvel kbank vsp nrm')
 fx, fy, fp = h * v * sp.cos(psi), h * v * sp.sin(psi), h * g * sp.tan(phi) / v

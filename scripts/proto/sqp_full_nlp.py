@@ -108,8 +108,9 @@ if __name__ == "__main__":
              "bank": (201, 0.05, (0, 0, 0), (80, 30, 0), (-np.deg2rad(40), np.deg2rad(40)), (9., 15.), 1., 1., 12.)}
     for nm, (N, hh, p0, p1, pb, vb, kv, kb, vspv) in cases.items():
         # start: straight line between the end points, heading along it, mid inputs
-        sys.path.insert(0, '/root/repo')
-        from oracle import d2d_oracle as orc
+        import os
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..', 'drone-sim-python_b200'))
+        from d2d_b200 import opty_utils as orc      # triangle() initial guess only
         xg, yg, psig, phig, vg = orc.triangle(p0[:2], p1[:2], 12., (N - 1) * hh, N, go_left=-1.)
         z0 = np.zeros((N, 5)); z0[:, 0], z0[:, 1], z0[:, 2] = xg, yg, np.unwrap(psig)
         z0[:, 3] = 0.0; z0[:, 4] = np.arcsin(np.clip((12. - (vb[0] + vb[1]) / 2) / ((vb[1] - vb[0]) / 2), -0.99, 0.99))
