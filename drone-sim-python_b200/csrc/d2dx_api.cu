@@ -215,9 +215,6 @@ int d2dx_create(int device, d2dx_handle** out) {
   d2dx_handle* h = new d2dx_handle;
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  h->done_counter = nullptr;
-  D2DX_CUDA(cudaMalloc(&h->done_counter, 64 * sizeof(int32_t)));
-  D2DX_CUDA(cudaMemset(h->done_counter, 0, 64 * sizeof(int32_t)));
   *out = h;
   return D2DX_OK;
 }
@@ -225,7 +222,6 @@ int d2dx_create(int device, d2dx_handle** out) {
 int d2dx_destroy(d2dx_handle* h) {
   if (!h) return D2DX_OK;
   cudaSetDevice(h->device);
-  if (h->done_counter) cudaFree(h->done_counter);
   delete h;
   return D2DX_OK;
 }

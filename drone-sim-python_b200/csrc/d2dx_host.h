@@ -9,7 +9,6 @@
 struct d2dx_handle {
   int device;
   int sm_count;
-  int32_t* done_counter;   // device: ticket for "last block reduces" in the collocation kernel
 };
 
 namespace d2dx {

@@ -14,6 +14,7 @@ JAC_COMPACT, JAC_OPTY_DENSE = 0, 1
 EVAL_RESIDUAL, EVAL_JAC, EVAL_COST, EVAL_GRAD = 1, 2, 4, 8
 EVAL_ALL = 15
 MAX_OBSTACLES = 16
+PEER_MAX_WORLD, IPC_HANDLE_BYTES = 16, 64
 
 c_dp = C.c_void_p      # device pointers travel as integers
 
@@ -134,6 +135,13 @@ def _load():
         "d2dx_colloc_eval": (C.c_int, [H, P(CollocProblem), i32, c_dp, i32, u32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_colloc_eval_shard": (C.c_int, [H, P(CollocProblem), i32, i32, c_dp, c_dp, u32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_colloc_pack_positions": (C.c_int, [H, i32, i32, c_dp, c_dp, c_dp]),
+        "d2dx_peer_create": (C.c_int, [H, i32, i32, i32, i32, i32, P(H)]),
+        "d2dx_peer_ipc_handle": (C.c_int, [H, C.c_char_p]),
+        "d2dx_peer_connect_ipc": (C.c_int, [H, C.c_char_p]),
+        "d2dx_peer_connect_local": (C.c_int, [H, P(H)]),
+        "d2dx_peer_status": (C.c_int, [H, P(i32)]),
+        "d2dx_peer_destroy": (C.c_int, [H]),
+        "d2dx_colloc_eval_peer": (C.c_int, [H, H, P(CollocProblem), i32, i32, c_dp, u32, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_shoot_forward": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_shoot_adjoint": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_lbfgs_layout": (C.c_int, [i32, i32, i32, P(LbfgsOptions), P(i64)]),

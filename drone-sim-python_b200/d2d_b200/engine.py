@@ -283,7 +283,15 @@ class Engine:
         self.launches += 1
 
 
-    # ---- diagnostics -------------------------------------------------------------------------------
+    # ---- peer exchange (aircraft-sharded collocation over NVLink peer memory) -------------------------------
+    def peer_create(self, world, rank, max_prob, n_ac_total, N):
+        return PeerExchange(self, world, rank, max_prob, n_ac_total, N)
+
+    def colloc_eval_peer(self, peer, prob_local, n_prob, a_lo, free_local, what, residual, jac, cost, grad):
+        check(lib.d2dx_colloc_eval_peer(self.h, peer.p, C.byref(prob_local), n_prob, a_lo, _ptr(free_local), what, _ptr(residual),
+                                        _ptr(jac), _ptr(cost), _ptr(grad), self.stream_ptr()), "d2dx_colloc_eval_peer")
+        self.launches += 1
+
     # ---- single shooting (planner NLP solve) ------------------------------------------------------------
     def shoot_forward(self, prob, P, u, bounds, p0, p1, u_phys, xs, c):
         b = (C.c_double * 4)(*bounds) if bounds is not None else None
@@ -348,6 +356,48 @@ class Engine:
             e1.record(); e1.synchronize()
             best = max(best, blocks * threads * iters * 32.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
         return best
+
+
+class PeerExchange:
+    """One rank's exchange buffer of the fused aircraft-sharded evaluation (d2dx_peer_*, include/d2dx.h)."""
+
+    def __init__(self, eng, world, rank, max_prob, n_ac_total, N):
+        self.eng, self.world, self.rank = eng, int(world), int(rank)
+        p = C.c_void_p()
+        check(lib.d2dx_peer_create(eng.h, self.world, self.rank, int(max_prob), int(n_ac_total), int(N), C.byref(p)), "d2dx_peer_create")
+        self.p = p
+
+    def ipc_handle(self):
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        check(lib.d2dx_peer_ipc_handle(self.p, buf), "d2dx_peer_ipc_handle")
+        return buf.raw
+
+    def connect_ipc(self, handles):
+        """handles: list of `world` 64-byte blobs in rank order (all_gather_object of ipc_handle())."""
+        blob = b"".join(bytes(h_) for h_ in handles)
+        assert len(blob) == self.world * _lib.IPC_HANDLE_BYTES
+        check(lib.d2dx_peer_connect_ipc(self.p, blob), "d2dx_peer_connect_ipc")
+
+    def connect_local(self, peers):
+        """peers: the `world` PeerExchange objects of one process, rank order."""
+        arr = (C.c_void_p * self.world)(*[q.p for q in peers])
+        check(lib.d2dx_peer_connect_local(self.p, arr), "d2dx_peer_connect_local")
+
+    def status(self):
+        s = (C.c_int32 * 4)()
+        check(lib.d2dx_peer_status(self.p, s), "d2dx_peer_status")
+        return {"timeouts": s[0], "evaluations": s[1], "resident_blocks": s[2], "buffer_kib": s[3]}
+
+    def close(self):
+        if getattr(self, "p", None):
+            lib.d2dx_peer_destroy(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default = None

@@ -294,6 +294,8 @@ int d2dx_colloc_init_dense(d2dx_handle* h, const d2dx_colloc_problem* p_host, in
 /* Evaluates n_prob problems sharing one description: free[n_prob][n_free] ->
  * residual[n_prob][n_con], jac[n_prob][nnz], cost[n_prob], grad[n_prob][n_free] (any may be NULL if
  * its flag is clear).  scratch: device doubles, at least d2dx_colloc_scratch_size(...) elements. */
+/* scratch must be ZERO before its first use (it starts with the tickets of the single-launch cost reduction; every call
+ * leaves them zero again) and must not be shared by evaluations in flight on different streams. */
 int64_t d2dx_colloc_scratch_size(const d2dx_colloc_problem* p_host, int32_t n_prob);
 int d2dx_colloc_eval(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t n_prob,
                      const double* free_, int32_t layout, uint32_t what, double* residual,
@@ -312,6 +314,37 @@ int d2dx_colloc_eval_shard(d2dx_handle* h, const d2dx_colloc_problem* p_local_ho
 /* packs the x,y slices of a (shard-local) free vector into pos[n_ac][2][N], the all-gather send buffer */
 int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const double* free_local,
                                double* pos, void* stream);
+
+/* -------- aircraft-sharded evaluation over NVLink peer memory: ONE kernel per rank, no collective call --------
+ * The exchange step the north star names ("all-gather aircraft positions for the cross-shard avoidance terms, reduce
+ * costs") done by the evaluation kernel itself: each rank stores its aircraft's x, y straight from free_local into every
+ * peer's position table (peer memory), computes everything local while the stores travel, waits on per-tile flags, adds
+ * the collision terms, and the last block of a problem exchanges the four cost sums the same way, so that every rank
+ * ends with the identical total cost[n_prob].  Replaces d2dx_colloc_pack_positions + all-gather + d2dx_colloc_eval_shard
+ * + all-reduce for the callbacks of 07_multioptyplan.py:69-78 when one problem is spread over the GPUs of a box.
+ *
+ * d2dx_peer_create allocates this rank's exchange buffer (the only allocation; capacity: max_prob problems of n_ac_total
+ * aircraft x N nodes).  Between processes the ranks swap d2dx_peer_ipc_handle blobs (64 bytes each, e.g. with
+ * torch.distributed.all_gather_object) and call d2dx_peer_connect_ipc; inside one process d2dx_peer_connect_local takes
+ * the other ranks' objects.  Every rank must then make the same sequence of d2dx_colloc_eval_peer calls (same n_prob,
+ * same `what`); a call is asynchronous on `stream`, may be captured in a CUDA graph, and never blocks forever: a peer
+ * that does not answer within ~1 s per wait is counted in status[0] of d2dx_peer_status ([1] = evaluations completed,
+ * [2] = resident blocks the kernel is sized for, [3] = exchange buffer KiB) and the outputs of that call are undefined. */
+typedef struct d2dx_peer d2dx_peer;
+#define D2DX_PEER_MAX_WORLD 16
+#define D2DX_IPC_HANDLE_BYTES 64
+int d2dx_peer_create(d2dx_handle* h, int32_t world, int32_t rank, int32_t max_prob, int32_t n_ac_total, int32_t N,
+                     d2dx_peer** out);
+int d2dx_peer_ipc_handle(d2dx_peer* p, void* handle_host64);
+int d2dx_peer_connect_ipc(d2dx_peer* p, const void* handles_host /* [world][64], rank order */);
+int d2dx_peer_connect_local(d2dx_peer* p, d2dx_peer* const* peers_host /* [world], rank order */);
+int d2dx_peer_status(d2dx_peer* p, int32_t* status_host4);
+int d2dx_peer_destroy(d2dx_peer* p);
+/* p_local_host / free_local / residual / jac (compact) / grad as in d2dx_colloc_eval_shard, for n_prob problems stacked on
+ * a leading axis; cost[n_prob] receives the TOTAL cost of each problem (all ranks' shares, summed in rank order). */
+int d2dx_colloc_eval_peer(d2dx_handle* h, d2dx_peer* peer, const d2dx_colloc_problem* p_local_host, int32_t n_prob,
+                          int32_t a_lo, const double* free_local, uint32_t what, double* residual, double* jac,
+                          double* cost, double* grad, void* stream);
 
 /* -------- single-shooting evaluation of the planner NLP --------
  * On the backward-Euler grid the defects of d2dx_colloc_eval determine the states from the inputs:

@@ -1,5 +1,5 @@
-"""Two-GPU tests (skipped on a single-GPU box): NCCL all-gather of positions + all-reduce of the cost in the
-aircraft-sharded collocation evaluation, and scenario-sharded rollouts with the final statistics reduction."""
+"""Two-GPU tests (skipped on a single-GPU box): the aircraft-sharded collocation evaluation (fused peer-memory kernel over
+NVLink, its CUDA-graph replay, and the NCCL all-gather + all-reduce formulation), and scenario-sharded rollouts with the final statistics reduction."""
 import os
 import socket
 
@@ -25,9 +25,22 @@ def _worker(rank, world, port, free, inst, ret):
     from d2d_b200.distributed import ShardedCollocation, reduce_population_stats, shard_range
     eng = get_engine()
     cs = CostSpec(vsp=12., kvel=70., kbank=1., kcol=10., rcol=10., all_pairs=True, kobs=0.5, obstacles=[(60., 5., 12.)], obs_kind=1)
-    sc = ShardedCollocation(16, 500, 0.02, (0., 0.), inst, cs, engine=eng)
+    import copy
+    sc = ShardedCollocation(16, 500, 0.02, (0., 0.), inst, copy.copy(cs), engine=eng)            # fused peer-memory kernel (NVLink)
     fl = eng.to_device(free[sc.shard.idx_free])
-    res, jac, cost, grad = sc.evaluate(fl)
+    res, jac, cost, grad = (t.clone() for t in sc.evaluate(fl))
+    replay, outs = sc.graph(fl)                                                                  # the same, replayed from a CUDA graph
+    for _ in range(5):
+        replay()
+    torch.cuda.synchronize()
+    st = sc.check()
+    assert st["evaluations"] == 8, st
+    for a_, b_ in zip(outs, (res, jac, cost, grad)):
+        assert torch.equal(a_, b_)
+    sc2 = ShardedCollocation(16, 500, 0.02, (0., 0.), inst, copy.copy(cs), engine=eng, backend="collective")   # NCCL all-gather + all-reduce
+    res2, jac2, cost2, grad2 = sc2.evaluate(fl)
+    assert torch.equal(res2, res) and torch.equal(jac2, jac) and torch.equal(grad2, grad)
+    assert abs(float(cost2[0]) - float(cost[0])) <= 1e-13 * abs(float(cost[0]))
     # scenario-sharded rollout: each rank its contiguous half of 64 circles, then the one final all-reduce
     rng = np.random.default_rng(0)
     B = 64
