@@ -31,6 +31,7 @@ FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "704"))
 # From the same capture (profiles/r1_final_rollout_dfff_circle.md, one launch of 1e6 scenarios x 1000 steps, log x100):
 # dram__bytes_read.sum + dram__bytes_write.sum, and the fp64 pipe's active fraction.
 NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 185.17e6 + 628.88e6
+NCU_TRAFFIC_CONFIG = (10 ** 6, 10 ** 4, 100, 10)       # (scenarios, steps, log_every, chunks) the capture was taken at
 NCU_FP64_PIPE_ACTIVE = 0.757
 LOG_BYTES_PER_LOGGED_SAMPLE = 56          # 5 state + 2 input doubles
 
@@ -130,42 +131,163 @@ def python_port_rate():
     return 2 * 150 / (_time.perf_counter() - t0)
 
 
+def _timed(fn, reps, warm=3):
+    """average seconds per call of fn on the current stream (CUDA events, after `warm` untimed calls)"""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); e1.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+C4 = dict(n_ac=16, N=500, h=0.02)
+
+
+def _c4_cost():
+    from d2d_b200.collocation import CostSpec
+    return CostSpec(vsp=12., kvel=70., kbank=1., kcol=10., rcol=10., all_pairs=True)
+
+
+def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
+    """The rest of BASELINE.json's metric at EVERY N: collocation evals/s with the problems sharded over the
+    ranks (no data-path collective), the formation rollout sharded by formation, and -- for N > 1 -- ONE C4 problem and a
+    batch of C4 problems sharded by AIRCRAFT through the fused peer-memory kernel, checked against rank 0's unsharded
+    evaluation.  Every rank runs its share; times are CUDA events, max over ranks; rank 0 returns the aggregate."""
+    import torch
+    import torch.distributed as dist
+    from d2d_b200 import _lib
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    from d2d_b200.simulation import chain_incidence
+    out, checks = {}, {}
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    rng = np.random.default_rng(seed + 1000 * rank)
+    # (1) batched collocation, problems sharded over ranks: each rank evaluates its own n_prob problems per launch
+    for tag, n_ac, N, h, n_prob, cost in (
+            ("c3_batch4096", 1, 1001, 0.02, 4096, CostSpec(vsp=12., kvel=1.)),
+            ("c4_batch256_allpairs", C4["n_ac"], C4["N"], C4["h"], 256, _c4_cost())):
+        prob = CollocationProblem(n_ac, N, h, inst=[(k, 0, 0.) for k in range(3 * n_ac)], cost=cost)
+        free = eng.to_device(rng.normal(0, 3., (n_prob, prob.num_free)) + 12. * (np.arange(prob.num_free) >= 4 * n_ac * N))
+        bufs = prob.buffers(n_prob)
+        sync_all()
+        dt = max_over_ranks(_timed(lambda: prob.evaluate_device(free, _lib.EVAL_ALL, bufs), 20))
+        bytes_alg = 200.0 * n_ac * N * n_prob                      # SURVEY 8d: 200 B per aircraft-node, compact layout
+        line = {"evals_per_s": world * n_prob / dt, "ms_per_launch": dt * 1e3, "problems_per_gpu": n_prob,
+                "aircraft_nodes_per_launch": n_ac * N * n_prob, "sharding": f"by problem x{world}, no collective",
+                "roofline": {"bound": "hbm", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / dt / 1e9 / hbm_peak,
+                             "algorithmic_bytes_per_launch": bytes_alg}}
+        if n_ac > 1:       # the pair terms make this launch fp64 / issue work as well: ~30 fp64 instructions (45 flop) per pair-node
+            pairs = n_ac * (n_ac - 1) // 2
+            flop = (45.0 * pairs + 230.0 * n_ac) * N * n_prob      # audited from the SASS of colloc_pairs_kernel (DESIGN 4.3)
+            line["roofline"]["fp64"] = {"achieved": flop / dt / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flop / dt / 1e12 / fp64_peak,
+                                        "flop_per_pair_node": 45.0, "flop_per_aircraft_node": 230.0}
+        out[tag] = line
+        del prob, free, bufs
+    # (2) formation rollout, config C2 replicated, formations sharded over ranks (whole waves per GPU)
+    n_ac, T = 6, 1200
+    F = eng.sm_count * 5 * (eng.formation_threads_per_sm // 32)        # whole waves: 5 formations per warp
+    M = F * n_ac
+    X0 = eng.to_device(np.ascontiguousarray(np.tile(np.array([20, 30, -np.pi / 2, 0, 10.]), (M, 1)).T))
+    c, r, ac = eng.zeros(2, M), eng.to_device(np.full(M, 60.)), eng.to_device(np.stack([np.full(M, 0.01), np.full(M, 1.)]))
+    z = np.ones(n_ac - 1) * 2 * np.pi / n_ac
+    Xf = eng.empty(5, M)
+    sync_all()
+    dt = max_over_ranks(_timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3))
+    # 5 RK4 sub-steps of ~150 fp64 flop + DCF/GVF ~ 250 per aircraft-step (ncu: profiles/r1_final_formation_c2.md, 1130 flop per aircraft-step)
+    flop = 1130.0 * M * (T - 1)
+    out["formation_c2_batch"] = {"aircraft_steps_per_s": world * M * (T - 1) / dt, "rk4_substeps_per_s": world * M * (T - 1) * 5 / dt,
+                                 "formations_per_gpu": F, "ms_per_launch": dt * 1e3, "sharding": f"by formation x{world}, no collective",
+                                 "roofline": {"bound": "fp64", "achieved": flop / dt / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                                              "frac": flop / dt / 1e12 / fp64_peak, "flop_per_aircraft_step": 1130.0}}
+    del X0, c, r, ac, Xf
+    # (3) ONE C4 problem (and a batch of 64) sharded by aircraft over the ranks: fused peer-memory kernel, CUDA graph
+    rng0 = np.random.default_rng(seed)                                # the same problems on every rank
+    n_ac, N, h = C4["n_ac"], C4["N"], C4["h"]
+    nf = 5 * n_ac * N
+    PB = 64
+    free_all = rng0.normal(0, 30., (PB, nf)); free_all[:, 4 * n_ac * N:] = 12. + rng0.normal(0, 1, (PB, n_ac * N))
+    inst = [(3 * a + k, 0, float(a + k)) for a in range(n_ac) for k in range(3)]
+    full = CollocationProblem(n_ac, N, h, inst=inst, cost=_c4_cost())
+    fd1, fdB = eng.to_device(free_all[:1].copy()), eng.to_device(free_all)
+    b1, bB = full.buffers(1), full.buffers(PB)
+    replay1, _ = full.graph(fd1)
+    t1 = _timed(replay1, 200, warm=20)
+    tB = _timed(lambda: full.evaluate_device(fdB, _lib.EVAL_ALL, bB), 50)
+    alg1 = 200.0 * n_ac * N
+    out["c4_single_allpairs"] = {"evals_per_s": 1.0 / t1, "us_per_eval": t1 * 1e6, "how": "one GPU, CUDA-graph replay of the fused evaluation",
+                                 "roofline": {"bound": "launch latency", "achieved": alg1 / t1 / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg1 / t1 / 1e9 / hbm_peak}}
+    out["c4_batch64_allpairs_one_gpu"] = {"evals_per_s": PB / tB, "us_per_launch": tB * 1e6}
+    if world > 1 and n_ac % world == 0:
+        from d2d_b200.distributed import ShardedCollocation
+        sc1 = ShardedCollocation(n_ac, N, h, (0., 0.), inst, _c4_cost(), engine=eng, max_prob=1)
+        scB = ShardedCollocation(n_ac, N, h, (0., 0.), inst, _c4_cost(), engine=eng, max_prob=PB)
+        fl1 = eng.to_device(free_all[0, sc1.shard.idx_free].copy())
+        flB = eng.to_device(np.ascontiguousarray(free_all[:, scB.shard.idx_free]))
+        rep1, o1 = sc1.graph(fl1)
+        repB, oB = scB.graph(flB)
+        sync_all()
+        ts1 = max_over_ranks(_timed(rep1, 200, warm=20))
+        sync_all()
+        tsB = max_over_ranks(_timed(repB, 50, warm=5))
+        sync_all()
+        st1, stB = sc1.check(), scB.check()
+        # parity: every rank's shard of the batch against rank 0's unsharded evaluation of the same problems
+        full.evaluate_device(fdB, _lib.EVAL_ALL, bB)
+        diffs = []
+        for name, mine, idx in (("res", oB[0], scB.shard.idx_con), ("jac", oB[1], scB.shard.idx_jac), ("grad", oB[3], scB.shard.idx_free)):
+            ref = bB[name][:, torch.from_numpy(idx).to(eng.device)]
+            diffs.append(float((mine - ref).abs().max().item()))
+        diffs.append(float((oB[2] - bB["cost"]).abs().max().item() / bB["cost"].abs().max().item()))
+        worst = max_over_ranks(max(diffs))
+        checks["sharded_c4_max_abs_diff"] = worst
+        checks["sharded_c4_peer_timeouts"] = int(max_over_ranks(float(st1["timeouts"] + stB["timeouts"])))
+        sharded_line = {"evals_per_s": 1.0 / ts1, "us_per_eval": ts1 * 1e6, "aircraft_per_gpu": n_ac // world, "one_gpu_us_per_eval": t1 * 1e6,
+                        "how": "one kernel per rank and evaluation: positions and cost sums as peer-memory stores over NVLink, CUDA-graph replay",
+                        "roofline": {"bound": "launch + NVLink flag latency", "achieved": alg1 / ts1 / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": alg1 / ts1 / 1e9 / hbm_peak}}
+        out["c4_single_sharded_by_aircraft"] = sharded_line
+        out["c4_batch64_sharded_by_aircraft"] = {"evals_per_s": PB / tsB, "us_per_launch": tsB * 1e6, "one_gpu_us_per_launch": tB * 1e6,
+                                                 "speedup_vs_one_gpu": tB / tsB,
+                                                 "roofline": {"bound": "hbm", "achieved": alg1 * PB / world / tsB / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                              "frac": alg1 * PB / world / tsB / 1e9 / hbm_peak,
+                                                              "note": "per-GPU algorithmic bytes (1/world of each problem) over the launch time"}}
+        del sc1, scB
+    return out, checks
+
+
 def secondary_metrics(eng, hbm_peak):
-    """The other rows of the metric (collocation evals/s, formation aircraft-steps/s), device-resident, CUDA events.
-    Collocation is HBM-bound: 200 algorithmic bytes per aircraft-node in the compact layout."""
+    """Single-GPU extras beyond BASELINE.json's metric (single-problem latencies, CPU figures)."""
     import torch
     from d2d_b200 import _lib
     from d2d_b200.collocation import CollocationProblem, CostSpec
     out = {}
-
-    def timed(fn, reps):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record(); e1.synchronize()
-        return e0.elapsed_time(e1) * 1e-3 / reps
-
+    timed = lambda fn, reps: _timed(fn, reps)
     rng = np.random.default_rng(12345)
-    for tag, n_ac, N, h, n_prob, cost in (
-            ("c3_batch4096", 1, 1001, 0.02, 4096, CostSpec(vsp=12., kvel=1.)),
-            ("c4_batch256_allpairs", 16, 500, 0.02, 256, CostSpec(vsp=12., kvel=70., kbank=1., kcol=10., rcol=10., all_pairs=True)),
-            ("c3_single", 1, 1001, 0.02, 1, CostSpec(vsp=12., kvel=1.)),
-            ("c4_single_allpairs", 16, 500, 0.02, 1, CostSpec(vsp=12., kvel=70., kbank=1., kcol=10., rcol=10., all_pairs=True))):
+    for tag, n_ac, N, h, n_prob, cost in (("c3_single", 1, 1001, 0.02, 1, CostSpec(vsp=12., kvel=1.)),):
         prob = CollocationProblem(n_ac, N, h, inst=[(k, 0, 0.) for k in range(3 * n_ac)], cost=cost)
         free = eng.to_device(rng.normal(0, 3., (n_prob, prob.num_free)) + 12. * (np.arange(prob.num_free) >= 4 * n_ac * N))
         bufs = prob.buffers(n_prob)
-        dt = timed(lambda: prob.evaluate_device(free, _lib.EVAL_ALL, bufs), 20 if n_prob > 1 else 200)
+        dt = timed(lambda: prob.evaluate_device(free, _lib.EVAL_ALL, bufs), 200)
         bytes_alg = 200.0 * n_ac * N * n_prob
-        extra = {}
-        if n_prob == 1:                                  # the same launch replayed from a CUDA graph
-            replay, _ = prob.graph(free)
-            extra = {"graph_replay_evals_per_s": 1.0 / timed(replay, 200)}
-        out[tag] = {**extra, "evals_per_s": n_prob / dt, "ms_per_launch": dt * 1e3, "aircraft_nodes_per_launch": n_ac * N * n_prob,
-                    "roofline": {"bound": "hbm" if n_prob > 1 else "launch latency", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        replay, _ = prob.graph(free)
+        out[tag] = {"graph_replay_evals_per_s": 1.0 / timed(replay, 200), "evals_per_s": n_prob / dt, "ms_per_launch": dt * 1e3,
+                    "roofline": {"bound": "launch latency", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_alg / dt / 1e9 / hbm_peak}}
     # CPU figure for the collocation path: the NumPy oracle (lambdified-EoM class of the survey) on one core, C3
     try:
@@ -181,18 +303,8 @@ def secondary_metrics(eng, hbm_peak):
         out["c3_cpu_numpy_1core"] = {"evals_per_s": reps / (_time.perf_counter() - t0), "kind": "port", "cores": 1}
     except Exception as e:
         out["c3_cpu_numpy_1core"] = {"error": str(e)}
-    # formation rollout, config C2 replicated: F formations of 6 aircraft, 1200 samples, dt 0.05, RK4 nsub 5
-    from d2d_b200.simulation import chain_incidence
-    n_ac, T = 6, 1200
-    F = eng.sm_count * 5 * (eng.formation_threads_per_sm // 32)        # whole waves: 5 formations per warp
-    M = F * n_ac
-    X0 = eng.to_device(np.ascontiguousarray(np.tile(np.array([20, 30, -np.pi / 2, 0, 10.]), (M, 1)).T))
-    c, r, ac = eng.zeros(2, M), eng.to_device(np.full(M, 60.)), eng.to_device(np.stack([np.full(M, 0.01), np.full(M, 1.)]))
-    z = np.ones(n_ac - 1) * 2 * np.pi / n_ac
-    Xf = eng.empty(5, M)
-    dt = timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3)
-    out["formation_c2_batch"] = {"aircraft_steps_per_s": M * (T - 1) / dt, "rk4_substeps_per_s": M * (T - 1) * 5 / dt, "formations": F, "ms_per_launch": dt * 1e3}
     # C5's second population: randomised min-snap polynomials, POLY-specialised rollout kernel, 2000 steps
+    from d2d_b200.simulation import chain_incidence  # noqa: F401
     from d2d_b200 import trajectory as ddt
     from d2d_b200.simulation import MonteCarloRollout
     Bp, Tp, dur = 500000, 2000, 33.65
@@ -329,10 +441,11 @@ def main():
     ap.add_argument("--scenarios", type=int, default=int(os.environ.get("D2DX_BENCH_B", 10 ** 6)), help="aircraft-scenarios per GPU")
     ap.add_argument("--horizon", type=int, default=int(os.environ.get("D2DX_BENCH_T", 10 ** 4)), help="RK4 steps per scenario")
     ap.add_argument("--log-every", type=int, default=100)
-    ap.add_argument("--chunks", type=int, default=10)
+    ap.add_argument("--chunks", type=int, default=25, help="launches per sweep (the log rows of a chunk are copied out while the next chunk computes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--core-only", action="store_true", help="skip the single-GPU extras (planner solves, tracker, pursuit, CPU figures)")
     ap.add_argument("--seed", type=int, default=12345)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -357,7 +470,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * Bc * Tc / val, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                "extrapolated": True,        # a bounded sample of the config's population and horizon is timed; steps/s is size-independent
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "extrapolated": True,
                                  "note": "C port of the oracle (generic 3x3 CARE per step, pthreads); the reference itself is "
                                          "single-threaded Python (366 steps/s/core measured in the survey)"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -436,7 +550,8 @@ def main():
     ms_per_step = ms_total / max(args.steps, 1)
     total_steps = float(B) * T_steps * world
     value = total_steps / (ms_per_step * 1e-3)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs])) / mc.launches_per_run     # avg duration of ONE launch
+    launches_per_run = mc.launches_per_run
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs])) / launches_per_run     # avg duration of ONE launch
 
     # ---- end-to-end through the host-buffer API (`e2e`) ----
     e2e = None
@@ -456,25 +571,37 @@ def main():
         e2e = {"value": total_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(mc.h2d_bytes), "d2h_bytes_per_step": int(mc.d2h_bytes),
                "ms_per_step": ms_e2e, "host_log": host_log, "api": "d2d_b200.simulation.MonteCarloRollout.run (pinned host buffers in/out)"}
 
+    # ---- the rest of the metric (collocation evals/s, formation, aircraft-sharded C4) on every rank, at every N ----
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    peak_tf, probe = eng.measure_fp64_peak(details=True)
+    core, core_checks = None, {}
+    if not args.no_secondary:
+        del mc                                             # the sweep's 6 GB of logs are no longer needed
+        torch.cuda.empty_cache()
+        try:
+            core, core_checks = core_metrics(eng, hbm_peak or 6650.0, peak_tf, world, rank, args.seed)
+        except Exception as e:                             # never lose the headline line over a side metric
+            core = {"error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                raise
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (rollout_dfff_kernel<CIRCLE>) ----
-    peak_tf = eng.measure_fp64_peak()
-    steps_per_launch = float(B) * (T_steps / mc.launches_per_run)
+    steps_per_launch = float(B) * (T_steps / launches_per_run)
     ach_tf = steps_per_launch * FP64_FLOP_PER_STEP / (kernel_ms * 1e-3) / 1e12
-    hbm_peak = None
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:
-        pass
     log_bytes = steps_per_launch / args.log_every * LOG_BYTES_PER_LOGGED_SAMPLE
     roofline = {"bound": "fp64", "kernel": "rollout_dfff_kernel<CIRCLE>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach_tf / peak_tf, "peak_source": "DFMA probe kernel timed in this run (MEASURED_PEAKS.json has no fp64 figure); nominal 37.2",
+                "frac": ach_tf / peak_tf, "peak_source": "DFMA probe kernel timed in this run (MEASURED_PEAKS.json has no fp64 figure); nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2",
+                "peak_probe": probe,
                 "flop_per_aircraft_step": FP64_FLOP_PER_STEP, "kernel_ms": kernel_ms, "steps_per_launch": steps_per_launch,
-                "traffic": NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH if (B, T_steps, args.log_every, args.chunks) == (10 ** 6, 10 ** 4, 100, 10) else None,
+                "traffic": NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH if (B, T_steps, args.log_every, args.chunks) == NCU_TRAFFIC_CONFIG else None,
                 "traffic_note": "ncu dram bytes of one launch at the default sizes (profiles/r1_final_rollout_dfff_circle.md); algorithmic bytes = log_bytes_per_launch",
                 "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE, "log_bytes_per_launch": log_bytes,
                 "hbm": {"achieved_gbs": log_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak or 6650.0,
@@ -484,19 +611,19 @@ def main():
         from oracle import c_oracle as co
         cores = co.max_threads()
         rate, cores, sample, _ = cpu_port_run(512 * cores, min(1000, T_steps), args.seed)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "extrapolated": True,
                "python_port_1core": python_port_rate()}
-    secondary = None
-    if not args.no_secondary and world == 1:
+    secondary = core
+    if not args.no_secondary and world == 1 and not args.core_only:
         try:
-            secondary = secondary_metrics(eng, hbm_peak or 6650.0)
+            secondary = {**(core or {}), **secondary_metrics(eng, hbm_peak or 6650.0)}
         except Exception as e:                          # never lose the headline line over a side metric
-            secondary = {"error": f"{type(e).__name__}: {e}"}
+            secondary = {**(core or {}), "extended_error": f"{type(e).__name__}: {e}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
-            "checks": {"nonfinite_or_unconverged_scenarios": flags_bad, "population_rms_pos_err": float(np.sqrt(pop[0].item() / (B * world * (T_steps + 1)))),
+            "checks": {**core_checks, "nonfinite_or_unconverged_scenarios": flags_bad, "population_rms_pos_err": float(np.sqrt(pop[0].item() / (B * world * (T_steps + 1)))),
                        "population_max_pos_err": float(pop[1].item())}}
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()

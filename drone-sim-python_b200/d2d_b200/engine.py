@@ -344,17 +344,24 @@ class Engine:
         self.launches += 1
         return out
 
-    def measure_fp64_peak(self, iters=20000, reps=5):
-        """TFLOP/s of a pure DFMA kernel (16 independent chains per thread, 8 x 256 threads per SM), best of reps."""
+    def measure_fp64_peak(self, iters=20000, reps=5, details=False):
+        """TFLOP/s of a pure DFMA kernel (16 independent chains per thread, 8 x 256 threads per SM), best of reps.
+        details=True also returns the probe's parameters so that the division can be redone from the bench line."""
         sink = self.zeros(1)
         blocks, threads = self.sm_count * 8, 256
-        best = 0.
+        best, best_ms = 0., None
         for _ in range(reps + 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             check(lib.d2dx_dfma_burn(self.h, blocks, threads, iters, _ptr(sink), self.stream_ptr()), "d2dx_dfma_burn")
             e1.record(); e1.synchronize()
-            best = max(best, blocks * threads * iters * 32.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            ms = e0.elapsed_time(e1)
+            tf = blocks * threads * iters * 32.0 / (ms * 1e-3) / 1e12
+            if tf > best:
+                best, best_ms = tf, ms
+        if details:
+            return best, {"blocks": blocks, "threads": threads, "iters": iters, "flop_per_thread_iter": 32, "ms": best_ms,
+                          "formula": "blocks*threads*iters*32 / ms"}
         return best
 
 

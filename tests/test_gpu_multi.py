@@ -34,7 +34,7 @@ def _worker(rank, world, port, free, inst, ret):
         replay()
     torch.cuda.synchronize()
     st = sc.check()
-    assert st["evaluations"] == 8, st
+    assert st["evaluations"] == 7, st      # 1 eager + 1 warm-up before the capture + 5 replays
     for a_, b_ in zip(outs, (res, jac, cost, grad)):
         assert torch.equal(a_, b_)
     sc2 = ShardedCollocation(16, 500, 0.02, (0., 0.), inst, copy.copy(cs), engine=eng, backend="collective")   # NCCL all-gather + all-reduce
