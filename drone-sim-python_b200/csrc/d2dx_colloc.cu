@@ -14,6 +14,7 @@ namespace d2dx {
 
 constexpr int kCollocThreads = 128;
 constexpr int kMaxTickets = 64;
+constexpr long kNodeKernelMinNodes = 16384;   // n_prob * N from which the thread-per-node all-pairs kernel fills the GPU
 constexpr int kPairWarps = 8;       // warps per block of colloc_pairs_kernel (aircraft w, w + 8, ... per warp)
 
 // finishes the cost of problem `prob`: per-block partials -> scratch; in ticket mode the last block of the problem sums
@@ -192,14 +193,21 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const 
     double gx = sg[(a_l * 2) * 32], gy = sg[(a_l * 2 + 1) * 32];
     const int kmax = (even && a_l < half) ? half - 1 : half;
     const double* pb = pa - 64;                    // partner a_l - 1 (upper copy: no wrap)
-    int al = a_l - 1;
+    // the slot of round k was written by aircraft a_l - k (mod n): sE[(k-1) n + a_l - k] while a_l - k >= 0, n entries
+    // further once it wraps -- two runs with the same constant stride instead of a modulo per pair
+    const int k1 = kmax < a_l ? kmax : a_l;
+    const int stride = (n - 1) * 32;
+    const double* pe = sE + (a_l - 1) * 32;
 #pragma unroll 4
-    for (int k = 1; k <= kmax; ++k) {
-      if (al < 0) al += n;
-      const double es = sE[((k - 1) * n + al) * 32];
-      const double wgt = cw * es;
+    for (int k = 1; k <= k1; ++k, pe += stride, pb -= 64) {
+      const double wgt = cw * pe[0];
       gx = fma(wgt, xa - pb[0], gx); gy = fma(wgt, ya - pb[32], gy);
-      pb -= 64; --al;
+    }
+    pe += n * 32;
+#pragma unroll 4
+    for (int k = k1 + 1; k <= kmax; ++k, pe += stride, pb -= 64) {
+      const double wgt = cw * pe[0];
+      gx = fma(wgt, xa - pb[0], gx); gy = fma(wgt, ya - pb[32], gy);
     }
     if (valid) colloc_node(a, fr, prob, a_l, i, xa, ya, gx, gy, want_cg, s_v, s_phi);
   }
@@ -221,6 +229,78 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const 
       for (int q = 0; q < W; ++q) { b4[0] += sred[q * 4]; b4[1] += sred[q * 4 + 1]; b4[2] += sred[q * 4 + 2]; b4[3] += sred[q * 4 + 3]; }
       cost_finish(a, prob, tile, b4, use_obs, true, lane);
     }
+  }
+}
+
+// All-pairs collision mode for BATCHES of problems: one thread = one node of one problem, ALL aircraft.  The positions and
+// the position gradient of the NAC aircraft stay in registers (4 NAC doubles), every unordered pair is evaluated once and
+// credited to both members, then the thread does the node's residual / Jacobian / input-cost work aircraft by aircraft.
+// No shared memory, no barrier, no exchange between threads; the independent pair evaluations give the instruction-level
+// parallelism that hides latency at ~10 warps per SM.  Every load / store is still coalesced along the node index
+// (consecutive threads = consecutive nodes of one aircraft's row).  Used when the launch has enough nodes to fill the GPU;
+// single problems keep colloc_pairs_kernel (32 x more threads per problem: lower latency).
+constexpr int kNodeThreads = 64;
+template <int NAC>
+__global__ void __launch_bounds__(kNodeThreads, 5) colloc_pairs_node_kernel(const __grid_constant__ CollocArgs a) {
+  __shared__ double sred[kNodeThreads / 32][4];
+  const d2dx_colloc_problem& P = a.p;
+  const int N = P.N;
+  const int tile = blockIdx.x % a.ntiles, prob = blockIdx.x / a.ntiles;
+  const int i = tile * kNodeThreads + threadIdx.x;
+  const bool valid = i < N;
+  const double* fr = a.free_ + (size_t)prob * a.n_free;
+  const bool use_obs = enabled(P.kobs) && P.n_obs > 0;
+  double s_v = 0.0, s_phi = 0.0, s_obs = 0.0, s_col = 0.0;
+  if (valid) {
+    double x[NAC], y[NAC], gx[NAC], gy[NAC];
+#pragma unroll
+    for (int g = 0; g < NAC; ++g) { x[g] = fr[(3 * g) * N + i]; y[g] = fr[(3 * g + 1) * N + i]; gx[g] = 0.0; gy[g] = 0.0; }
+    if (use_obs) obstacle_terms(P, a.sN, x[0], y[0], s_obs, gx[0], gy[0]);
+    const double nkr2 = a.nkr2, cw = a.cw;
+#pragma unroll
+    for (int p = 0; p < NAC; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < NAC; ++q) {
+        const double dx = x[p] - x[q], dy = y[p] - y[q];
+        const double es = fm::exp_neg(nkr2 * fma(dx, dx, dy * dy));
+        s_col += es;
+        const double wgt = cw * es;
+        gx[p] = fma(wgt, dx, gx[p]); gy[p] = fma(wgt, dy, gy[p]);
+        gx[q] = fma(-wgt, dx, gx[q]); gy[q] = fma(-wgt, dy, gy[q]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < NAC; ++g) colloc_node(a, fr, prob, g, i, x[g], y[g], gx[g], gy[g], true, s_v, s_phi);
+  }
+  if (tile == 0) {                                 // instance constraints: first tile of each problem
+    for (int k = threadIdx.x; k < P.n_inst; k += kNodeThreads) {
+      if (a.what & D2DX_EVAL_RESIDUAL)
+        a.res[(size_t)prob * a.n_con + 3 * NAC * (N - 1) + k] = fr[P.inst_var[k] * N + P.inst_node[k]] - P.inst_val[k];
+      if (a.what & D2DX_EVAL_JAC) a.jac[(size_t)prob * a.nnz + (a.nnz - P.n_inst) + k] = 1.0;
+    }
+  }
+  if (a.what & D2DX_EVAL_COST) {
+    const double v4[4] = {warp_sum(s_v), warp_sum(s_phi), warp_sum(s_obs), warp_sum(s_col)};
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sred[w][0] = v4[0]; sred[w][1] = v4[1]; sred[w][2] = v4[2]; sred[w][3] = v4[3]; }
+    __syncthreads();
+    if (w == 0) {
+      double b4[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int q = 0; q < kNodeThreads / 32; ++q) { b4[0] += sred[q][0]; b4[1] += sred[q][1]; b4[2] += sred[q][2]; b4[3] += sred[q][3]; }
+      cost_finish(a, prob, tile, b4, use_obs, true, lane);
+    }
+  }
+}
+
+typedef void (*NodeKernel)(const CollocArgs);
+static NodeKernel node_kernel_for(int n_ac) {
+  switch (n_ac) {
+    case 2: return colloc_pairs_node_kernel<2>;   case 3: return colloc_pairs_node_kernel<3>;
+    case 4: return colloc_pairs_node_kernel<4>;   case 5: return colloc_pairs_node_kernel<5>;
+    case 6: return colloc_pairs_node_kernel<6>;   case 7: return colloc_pairs_node_kernel<7>;
+    case 8: return colloc_pairs_node_kernel<8>;   case 10: return colloc_pairs_node_kernel<10>;
+    case 12: return colloc_pairs_node_kernel<12>; case 16: return colloc_pairs_node_kernel<16>;
+    default: return nullptr;
   }
 }
 
@@ -298,6 +378,48 @@ __global__ void pack_positions_kernel(int n_ac, int N, const double* __restrict_
   }
 }
 
+// CostBank with use_mean = False (d2d/opty_utils.py:68-82): cost = obj_scale max_i phi_i^2; gradient = one entry
+// obj_scale 2 phi_i at i = np.argmax(phi^2) (first maximum), zeros elsewhere.  One block per problem.
+__global__ void __launch_bounds__(256) bank_max_kernel(int n_free, int off_phi, int N, double obj_scale, const double* __restrict__ free_,
+                                                       double* __restrict__ cost, double* __restrict__ grad) {
+  __shared__ double sv[8];
+  __shared__ int si[8];
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const double* fr = free_ + (size_t)prob * n_free;
+  double best = -1.0;
+  int idx = 0x7fffffff;
+  for (int i = tid; i < N; i += 256) {
+    const double q = fr[off_phi + i] * fr[off_phi + i];
+    if (q > best) { best = q; idx = i; }         // strided scan keeps the first maximum of this thread's subsequence
+  }
+  auto better = [](double v, int i, double bv, int bi) { return v > bv || (v == bv && i < bi); };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (better(ov, oi, best, idx)) { best = ov; idx = oi; }
+  }
+  if ((tid & 31) == 0) { sv[tid >> 5] = best; si[tid >> 5] = idx; }
+  __syncthreads();
+  if (tid < 32) {
+    best = tid < 8 ? sv[tid] : -1.0; idx = tid < 8 ? si[tid] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (better(ov, oi, best, idx)) { best = ov; idx = oi; }
+    }
+    if (tid == 0) { sv[0] = best; si[0] = idx; }
+  }
+  __syncthreads();
+  best = sv[0]; idx = si[0];
+  if (cost && tid == 0) cost[prob] = obj_scale * best;
+  if (grad) {
+    double* go = grad + (size_t)prob * n_free;
+    for (int k = tid; k < n_free; k += 256) go[k] = (k == off_phi + idx) ? obj_scale * 2.0 * fr[k] : 0.0;
+  }
+}
+
 int colloc_resident_threads_per_sm() {
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, colloc_kernel<false>, kCollocThreads, 0);
@@ -354,7 +476,12 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
   const bool col = want_cg && enabled_h(p->kcol) && n_total > 1;
   const bool obs = want_cg && enabled_h(p->kobs) && p->n_obs > 0;
   cudaStream_t st = as_stream(stream);
-  if (col && p->col_all_pairs && pos_all == nullptr && pairs_smem_bytes(p->n_ac) <= 200 * 1024) {
+  NodeKernel nk = (col && p->col_all_pairs && pos_all == nullptr && (long)n_prob * p->N >= kNodeKernelMinNodes) ? node_kernel_for(p->n_ac) : nullptr;
+  if (nk) {                                      // batches: one thread per node, all aircraft in registers
+    a.TN = kNodeThreads; a.APP = p->n_ac; a.ntiles = (p->N + kNodeThreads - 1) / kNodeThreads; a.nparts = a.ntiles;
+    nk<<<(unsigned)((long)n_prob * a.ntiles), kNodeThreads, 0, st>>>(a);
+    D2DX_LAUNCH_CHECK("colloc_pairs_node_kernel");
+  } else if (col && p->col_all_pairs && pos_all == nullptr && pairs_smem_bytes(p->n_ac) <= 200 * 1024) {
     a.TN = 32; a.APP = kPairWarps; a.ntiles = (p->N + 31) / 32; a.nparts = a.ntiles;
     const size_t smem = pairs_smem_bytes(p->n_ac);
     if (smem > 48 * 1024)
@@ -440,6 +567,17 @@ int d2dx_colloc_eval_shard(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t
                  "d2dx_colloc_eval_shard: shard [%d,+%d) of %d", a_lo, p ? p->n_ac : -1, n_ac_total);
   return launch_eval(h, p, 1, n_ac_total, a_lo, free_local, pos_all, D2DX_JAC_COMPACT, what, residual, jac, cost, grad, scratch,
                      stream, "d2dx_colloc_eval_shard");
+}
+
+int d2dx_cost_bank_max(d2dx_handle* h, int32_t n_prob, int32_t n_free, int32_t off_phi, int32_t N, double obj_scale, const double* free_,
+                       double* cost, double* grad, void* stream) {
+  D2DX_CHECK_ARG(h && free_ && (cost || grad), "d2dx_cost_bank_max: null argument");
+  D2DX_CHECK_ARG(n_prob >= 1 && N >= 1 && off_phi >= 0 && off_phi + N <= n_free, "d2dx_cost_bank_max: n_prob=%d off_phi=%d N=%d n_free=%d", n_prob,
+                 off_phi, N, n_free);
+  D2DX_CUDA(cudaSetDevice(h->device));
+  bank_max_kernel<<<n_prob, 256, 0, as_stream(stream)>>>(n_free, off_phi, N, obj_scale, free_, cost, grad);
+  D2DX_LAUNCH_CHECK("bank_max_kernel");
+  return D2DX_OK;
 }
 
 int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const double* free_local, double* pos, void* stream) {

@@ -23,8 +23,13 @@ __device__ __forceinline__ double rcp_f(double v) { return 1.0 / v; }
 __device__ __forceinline__ double div_f(double a, double b) { return a / b; }
 #else
 __device__ __forceinline__ void sincos_b(double x, double& s, double& c) { fm::sincos(x, s, c); }
+// libdevice's Payne-Hanek path for huge phases, out of line and by value: its scratch array stays in ITS frame, the caller
+// keeps no address-taken locals (a by-reference call put a stack frame and STL / LDL pairs into every rollout kernel)
+struct SinCos { double s, c; };
+static __device__ __noinline__ SinCos sincos_slow(double x) { SinCos r; ::sincos(x, &r.s, &r.c); return r; }
 __device__ __forceinline__ void sincos_any(double x, double& s, double& c) {
-  if (fabs(x) < 1.0e5) fm::sincos(x, s, c); else ::sincos(x, &s, &c);      // libdevice's Payne-Hanek path for huge phases
+  if (fabs(x) < 1.0e5) fm::sincos(x, s, c);
+  else { const SinCos r = sincos_slow(x); s = r.s; c = r.c; }
 }
 __device__ __forceinline__ double atan2_f(double y, double x) { return fm::atan2(y, x); }
 __device__ __forceinline__ double atan_f(double v) { return fm::atan(v); }
@@ -210,9 +215,11 @@ __device__ __forceinline__ void cont_dyn(const AcPar& a, double psi, double phi,
 
 // Reference formulation of one control step (every stage with full-range sin / cos): used for the single-call
 // entry points' odd inputs and as the fallback of rk4_step when a stage leaves the fast path's validity range.
-static __device__ __noinline__ void rk4_step_generic(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
+// Arguments and result travel by value (registers): nothing of the caller's state has its address taken.
+struct State5 { double x, y, psi, phi, v; };
+static __device__ __noinline__ State5 rk4_step_generic(const AcPar a, const State5 X, double phi_c, double v_c, double dt, int nsub) {
   const double h = dt / nsub, hh = 0.5 * h, h6 = h / 6.0;
-  double x = X[0], y = X[1], psi = X[2], phi = X[3], v = X[4];
+  double x = X.x, y = X.y, psi = X.psi, phi = X.phi, v = X.v;
   for (int s = 0; s < nsub; ++s) {
     double k1[5], k2[5], k3[5], k4[5];
     cont_dyn(a, psi, phi, v, phi_c, v_c, k1[0], k1[1], k1[2], k1[3], k1[4]);
@@ -225,13 +232,21 @@ static __device__ __noinline__ void rk4_step_generic(const AcPar& a, double* X, 
     phi += h6 * (k1[3] + 2.0 * k2[3] + 2.0 * k3[3] + k4[3]);
     v += h6 * (k1[4] + 2.0 * k2[4] + 2.0 * k3[4] + k4[4]);
   }
-  X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
+  State5 r;
+  r.x = x; r.y = y; r.psi = wrap_pi(psi); r.phi = phi; r.v = v;
+  return r;
+}
+__device__ __forceinline__ void rk4_generic_inplace(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
+  State5 in;
+  in.x = X[0]; in.y = X[1]; in.psi = X[2]; in.phi = X[3]; in.v = X[4];
+  const State5 r = rk4_step_generic(a, in, phi_c, v_c, dt, nsub);
+  X[0] = r.x; X[1] = r.y; X[2] = r.psi; X[3] = r.phi; X[4] = r.v;
 }
 
 #ifdef D2DX_USE_LIBM
 template <bool ONE = false>
 __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c, double v_c, double dt, int nsub) {
-  rk4_step_generic(a, X, phi_c, v_c, dt, nsub);
+  rk4_generic_inplace(a, X, phi_c, v_c, dt, nsub);
 }
 #else
 // g tan(phi) / v with one reciprocal through the Pade ratio of d2dx_math.cuh (|phi| <= 1.15, checked by the caller)
@@ -295,10 +310,8 @@ __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c
     phi += h6 * (k1f + 2.0 * k2f + 2.0 * k3f + k4f);
     v += h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
   }
-  if (!fast_ok) {                            // NaN compares false: also caught.  The generic path works on a copy, so that
-    double T[5] = {X[0], X[1], X[2], X[3], X[4]};   // the caller's state stays in registers (only T has its address taken)
-    rk4_step_generic(a, T, phi_c, v_c, dt, nsub);
-    X[0] = T[0]; X[1] = T[1]; X[2] = T[2]; X[3] = T[3]; X[4] = T[4];
+  if (!fast_ok) {                            // NaN compares false: also caught
+    rk4_generic_inplace(a, X, phi_c, v_c, dt, nsub);
     return;
   }
   X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
@@ -367,7 +380,8 @@ __device__ __forceinline__ void care_update(double& C, double& S, double& al, do
 }
 
 // Full Newton iteration loop (cold starts, trajectory corners, anything the two-step fast path did not finish).
-static __device__ __noinline__ bool care_newton_loop(const CareStep& k, double& C, double& S, double& al, int max_it) {
+struct CareRoot { double C, S, al; bool conv; };
+static __device__ __noinline__ CareRoot care_newton_loop_v(const CareStep k, double C, double S, double al, int max_it) {
   bool conv = false;
   for (int it = 0; it < max_it && !conv; ++it) {
     double be, F1, F2;
@@ -382,7 +396,14 @@ static __device__ __noinline__ bool care_newton_loop(const CareStep& k, double& 
     C = Cn * nrm; S = Sn * nrm; al += dal;
     conv = fabs(dth) < 3e-8 && fabs(dal) < 3e-8 * fabs(al);        // quadratic convergence: remaining error ~1e-15
   }
-  return conv;
+  CareRoot r;
+  r.C = C; r.S = S; r.al = al; r.conv = conv;
+  return r;
+}
+__device__ __forceinline__ bool care_newton_loop(const CareStep& k, double& C, double& S, double& al, int max_it) {
+  const CareRoot r = care_newton_loop_v(k, C, S, al, max_it);
+  C = r.C; S = r.S; al = r.al;
+  return r.conv;
 }
 
 // Gain in the path frame.  Warm start = previous solution extrapolated by its last change (the reference moves

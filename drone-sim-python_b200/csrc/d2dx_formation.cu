@@ -21,23 +21,30 @@ struct FormArgs {
 };
 
 // DCFController.get, d2d/guidance.py:103-126, for the formation whose first lane is `base`.
-// Every lane of the warp must call it.  Returns U_r of this lane's aircraft; e_out = this lane's edge error [rad].
+// Every lane of the warp must call it.  Returns U_r of this lane's aircraft.  Lane j of the formation owns the edges
+// j, j + n_ac, j + 2 n_ac, ... (the reference accepts any incidence matrix: a complete graph has more edges than aircraft);
+// `emit(edge, e)` receives each owned edge's wrapped error [rad].
+template <typename Emit>
 __device__ __forceinline__ double dcf_warp(const double* sB, const double* sz, int n_ac, int n_e, int base, int j,
-                                           double theta, double kr, double& e_out) {
-  double z = 0.0;
-  for (int i = 0; i < n_ac; ++i) {                       // z = B^T theta
-    const double th_i = __shfl_sync(0xffffffffu, theta, base + i);
-    if (j < n_e) z = fma(sB[i * n_e + j], th_i, z);
-  }
-  double e = (j < n_e) ? z - sz[j] : 0.0;
-  if (e > kPi) e -= kTwoPi;                              // :115-120, both tests in sequence
-  if (e <= -kPi) e += kTwoPi;
+                                           double theta, double kr, Emit emit) {
   double ur = 0.0;
-  for (int k = 0; k < n_e; ++k) {                        // U_r = -kr B e
-    const double e_k = __shfl_sync(0xffffffffu, e, base + k);
-    if (j < n_ac) ur = fma(sB[j * n_e + k], e_k, ur);
+  for (int e0 = 0; e0 < n_e; e0 += n_ac) {                 // one pass when n_e <= n_ac (chain and ring graphs)
+    const int edge = e0 + j;
+    double z = 0.0;
+    for (int i = 0; i < n_ac; ++i) {                       // z = B^T theta
+      const double th_i = __shfl_sync(0xffffffffu, theta, base + i);
+      if (edge < n_e) z = fma(sB[i * n_e + edge], th_i, z);
+    }
+    double e = (edge < n_e) ? z - sz[edge] : 0.0;
+    if (e > kPi) e -= kTwoPi;                              // :115-120, both tests in sequence
+    if (e <= -kPi) e += kTwoPi;
+    if (edge < n_e) emit(edge, e);
+    const int kk_end = n_e - e0 < n_ac ? n_e - e0 : n_ac;
+    for (int kk = 0; kk < kk_end; ++kk) {                  // U_r = -kr B e
+      const double e_k = __shfl_sync(0xffffffffu, e, base + kk);
+      ur = fma(sB[j * n_e + e0 + kk], e_k, ur);
+    }
   }
-  e_out = e;
   return -kr * ur;
 }
 
@@ -76,8 +83,10 @@ __global__ void __launch_bounds__(kFormThreads) rollout_formation_kernel(const _
       for (int k = 0; k < 5; ++k) a.o.X_log[(row * 5 + k) * M + g] = X[k];
     }
     const double theta = atan2_f(X[1] - cy, X[0] - cx);
-    double e_edge;
-    const double Ur = dcf_warp(sB, sz, a.n_ac, a.n_e, base, j, theta, a.kr, e_edge);
+    const bool log_eth = log_now && a.o.eth_log != nullptr;
+    const double Ur = dcf_warp(sB, sz, a.n_ac, a.n_e, base, j, theta, a.kr, [&](int edge, double e) {
+      if (log_eth) a.o.eth_log[row * ((size_t)a.F * a.n_e) + (size_t)f * a.n_e + edge] = e * (180.0 / kPi);
+    });
     const double Rr = Ur + R;                            // 08_CircularFormation_Full.py:76
     double U, U1, U2;
     gvf_control(X[0], X[1], X[2], X[4], cx, cy, Rr, a.ke, a.kd, U, U1, U2);
@@ -85,7 +94,6 @@ __global__ void __launch_bounds__(kFormThreads) rollout_formation_kernel(const _
     if (log_now) {
       if (a.o.U_log) a.o.U_log[row * M + g] = phi_c;
       if (a.o.Rr_log) a.o.Rr_log[row * M + g] = Rr;
-      if (a.o.eth_log && j < a.n_e) a.o.eth_log[row * ((size_t)a.F * a.n_e) + (size_t)f * a.n_e + j] = e_edge * (180.0 / kPi);
     }
     rk4_step(ap, X, phi_c, a.v_c, a.dt, a.nsub);         // :90
     if (log_in == 0) { log_in = log_every; ++row; }
@@ -128,12 +136,10 @@ __global__ void __launch_bounds__(kFormThreads) dcf_kernel(const __grid_constant
   const int base = lf * a.n_ac < 32 ? lf * a.n_ac : 0;
   const size_t M = (size_t)a.F * a.n_ac, g = (size_t)f * a.n_ac + j;
   const double theta = atan2_f(a.p[M + g] - a.c[M + g], a.p[g] - a.c[g]);
-  double e_edge;
-  const double Ur = dcf_warp(sB, sz, a.n_ac, a.n_e, base, j, theta, a.kr, e_edge);
-  if (active) {
-    a.Ur[g] = Ur;
-    if (j < a.n_e) a.e_deg[(size_t)f * a.n_e + j] = e_edge * (180.0 / kPi);
-  }
+  const double Ur = dcf_warp(sB, sz, a.n_ac, a.n_e, base, j, theta, a.kr, [&](int edge, double e) {
+    if (active) a.e_deg[(size_t)f * a.n_e + edge] = e * (180.0 / kPi);
+  });
+  if (active) a.Ur[g] = Ur;
 }
 
 __global__ void __launch_bounds__(kFormThreads) gvf_kernel(int n, const double* __restrict__ X, const double* __restrict__ c,

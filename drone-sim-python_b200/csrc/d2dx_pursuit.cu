@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kPpThreads) rollout_pursuit_kernel(const __gri
       if (a.U_log) { a.U_log[((size_t)i * 2 + 0) * B + g] = phi_sp; a.U_log[((size_t)i * 2 + 1) * B + g] = v_sp; }
       if (a.idx_log) a.idx_log[(size_t)i * B + g] = idx;
     }
-    rk4_step_generic(ap, X, phi_sp, v_sp, a.dt, a.nsub);     // every lane integrates the same state
+    rk4_generic_inplace(ap, X, phi_sp, v_sp, a.dt, a.nsub);  // every lane integrates the same state
   }
   if (lane == 0) {
 #pragma unroll

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
     // plain single-segment trajectories with first_seg[b] == b: every parameter row of the tile is one
     // contiguous run of the SoA table -> one TMA bulk copy per row (when the tile is full and 16B aligned)
     const int b0 = blockIdx.x * kRolloutThreads;
-    const bool bulk = (b0 + kRolloutThreads <= S) && ((S & 1) == 0);
+    const bool bulk = (b0 + kRolloutThreads <= S) && ((S & 1) == 0) && ((reinterpret_cast<uintptr_t>(tt.seg_par) & 15) == 0);
     constexpr int kRows = (UNIFORM == D2DX_SEG_CIRCLE) ? 6 : (UNIFORM == D2DX_SEG_LINE) ? 5 : D2DX_SEG_NPAR;
     if (bulk) {
       if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -235,7 +235,10 @@ extern "C" int d2dx_rollout_dfff(d2dx_handle* h, const d2dx_scenarios* s, const 
   D2DX_CUDA(cudaSetDevice(h->device));
   const bool logging = out->X_log || out->U_log || out->Xr_log || out->K_log;
   cudaStream_t st = as_stream(stream);
-  switch (s->traj.uniform_type) {
+  D2DX_CHECK_ARG(s->traj.uniform_type == 0 || s->traj.n_seg == s->traj.n_traj,
+                 "d2dx_rollout_dfff: uniform_type=%d promises one plain segment per trajectory but n_seg=%d != n_traj=%d",
+                 s->traj.uniform_type, s->traj.n_seg, s->traj.n_traj);
+  switch (s->traj.uniform_type - 1) {
     case D2DX_SEG_CIRCLE: return launch_rollout<D2DX_SEG_CIRCLE>(a, logging, st);
     case D2DX_SEG_POLY: return launch_rollout<D2DX_SEG_POLY>(a, logging, st);
     case D2DX_SEG_LINE: return launch_rollout<D2DX_SEG_LINE>(a, logging, st);

@@ -52,7 +52,7 @@ class DeviceTable:
                   ("first_seg", "n_segs", "traj_t0", "traj_dur", "seg_type", "seg_end", "seg_par")}
         self.c = _lib.TrajTable(packed.n_traj, packed.n_seg, *[_ptr(self.t[k]) for k in
                                 ("first_seg", "n_segs", "traj_t0", "traj_dur", "seg_type", "seg_end", "seg_par")],
-                                packed.uniform_type)
+                                packed.uniform_type + 1)      # ABI: 0 = mixed, 1 + type = uniform
         if packed.tables is not None:
             self.tab = eng.to_device(packed.tables, non_blocking)
             n = packed.tables.shape[1]
@@ -271,6 +271,16 @@ class Engine:
         check(lib.d2dx_colloc_eval(self.h, C.byref(prob), n_prob, _ptr(free), layout, what, _ptr(residual), _ptr(jac),
                                    _ptr(cost), _ptr(grad), _ptr(scratch), self.stream_ptr()), "d2dx_colloc_eval")
         self.launches += 1
+
+    def cost_bank_max(self, free, off_phi, N, obj_scale, want_cost=True, want_grad=True):
+        """free: device (n_prob, n_free) -> (cost (n_prob,), grad (n_prob, n_free)) of CostBank's max mode"""
+        n_prob, n_free = free.shape
+        cost = self.empty(n_prob) if want_cost else None
+        grad = self.empty(n_prob, n_free) if want_grad else None
+        check(lib.d2dx_cost_bank_max(self.h, n_prob, n_free, int(off_phi), int(N), float(obj_scale), _ptr(free), _ptr(cost), _ptr(grad),
+                                     self.stream_ptr()), "d2dx_cost_bank_max")
+        self.launches += 1
+        return cost, grad
 
     def colloc_eval_shard(self, prob_local, n_ac_total, a_lo, free_local, pos_all, what, residual, jac, cost, grad, scratch):
         check(lib.d2dx_colloc_eval_shard(self.h, C.byref(prob_local), n_ac_total, a_lo, _ptr(free_local), _ptr(pos_all), what,

@@ -73,13 +73,28 @@ class CostAirVel(_EngineCost):                               # d2d/opty_utils.py
     def spec(self): return CostSpec(vsp=self.vsp, kvel=1.)
 
 
-class CostBank(_EngineCost):                                 # :68-82 (mean-squared mode)
+class CostBank(_EngineCost):                                 # :68-82: mean squared bank (default) or max squared bank
     use_mean = True
 
-    def spec(self):
-        if not self.use_mean:
-            raise NotImplementedError("CostBank max mode (use_mean=False) is not on the engine")
-        return CostSpec(kbank=1.)
+    def spec(self): return CostSpec(kbank=1.)
+
+    def _max_mode(self, free, _p, want_cost, want_grad):
+        from .engine import get_engine
+        eng = get_engine()
+        free = np.asarray(free, dtype=np.float64)
+        sl = _p._slice_phi
+        fd = eng.to_device(np.ascontiguousarray(free.reshape(1, -1)))
+        return eng.cost_bank_max(fd, sl.start, sl.stop - sl.start, float(_p.obj_scale), want_cost, want_grad)
+
+    def cost(self, free, _p):
+        if self.use_mean:
+            return super().cost(free, _p)
+        return float(self._max_mode(free, _p, True, False)[0].cpu()[0])          # obj_scale * max(phi^2), :73
+
+    def cost_grad(self, free, _p):
+        if self.use_mean:
+            return super().cost_grad(free, _p)
+        return self._max_mode(free, _p, False, True)[1].cpu().numpy()[0]         # one entry at np.argmax(phi^2), :78-81
 
 
 class CostInput(_EngineCost):                                # :85-97

@@ -120,6 +120,13 @@ def rollout(time, trajs, wind, X0, perts=None, tau_phi=0.01, tau_v=1., nsub=1, l
         if last:
             break
         i, Xc = j, X_final
+    if return_log and not final_control and (T - 1) % log_every == 0:
+        # without the trailing controller evaluation (05_test_simulation.py:33) the kernel never visits sample T-1: its state
+        # row comes from X_final, its input / reference / gain rows do not exist and read zero
+        X_log[n_rows - 1] = X_final
+        for t_ in (U_log, Xr_log, K_log):
+            if t_ is not None:
+                t_[n_rows - 1].zero_()
     res = RolloutResult()
     res.time_log = time[::log_every]
     res.X_final = X_final.cpu().numpy().T

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define D2DX_VERSION 100
+#define D2DX_VERSION 101
 
 enum { D2DX_OK = 0, D2DX_EINVAL = 1, D2DX_ECUDA = 2, D2DX_EUNSUPPORTED = 3 };
 
@@ -75,8 +75,11 @@ typedef struct {
   const int32_t* seg_type;   /* [S]                                                              */
   const double* seg_end;     /* [S]  CompositeTraj.steps_end (np.cumsum)                         */
   const double* seg_par;     /* [D2DX_SEG_NPAR][S]                                               */
-  int32_t uniform_type;      /* >= 0: every trajectory is ONE plain segment of this type and
-                                first_seg[b] == b (selects a specialised kernel); -1: mixed    */
+  int32_t uniform_type;      /* 0 (what a zero-initialised table gets): mixed -- the generic kernel reads the whole table;
+                                1 + D2DX_SEG_*: EVERY trajectory is ONE plain segment of that type, n_seg == n_traj and
+                                first_seg[b] == b -- selects a specialised kernel that reads seg_par only (n_segs,
+                                traj_t0, traj_dur, seg_type, seg_end are not consulted).  seg_par should be 16-byte
+                                aligned (rows then move as TMA bulk copies; plain loads otherwise)               */
   /* sample tables of D2DX_SEG_TABLE segments (all NULL when there is none): time, x, y and the
    * ground velocity v cos(psi) + wx, v sin(psi) + wy of each stored sample                        */
   int32_t n_tab;
@@ -300,6 +303,11 @@ int64_t d2dx_colloc_scratch_size(const d2dx_colloc_problem* p_host, int32_t n_pr
 int d2dx_colloc_eval(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t n_prob,
                      const double* free_, int32_t layout, uint32_t what, double* residual,
                      double* jac, double* cost, double* grad, double* scratch, void* stream);
+/* CostBank with use_mean = False (d2d/opty_utils.py:68-82): cost[p] = obj_scale * max_i phi_i^2 over the N values
+ * free[p][off_phi .. off_phi+N); grad[p][n_free] = zeros except obj_scale * 2 phi at the first maximum (np.argmax).
+ * cost or grad may be NULL. */
+int d2dx_cost_bank_max(d2dx_handle* h, int32_t n_prob, int32_t n_free, int32_t off_phi, int32_t N, double obj_scale,
+                       const double* free_, double* cost, double* grad, void* stream);
 /* Aircraft-sharded evaluation of ONE problem.  `p_local_host` describes THIS rank's shard as a
  * problem of n_ac = number of owned aircraft (free_local, residual, jac (compact layout), grad all use the
  * shard-local layout; in_div must be the TOTAL aircraft count).  The owned aircraft are global aircraft

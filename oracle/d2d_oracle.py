@@ -464,9 +464,9 @@ def run_formation(c, r, n_ac, t_end, ke, kd, kr, z_des, dt=0.05, nsub=5, X1=None
     time = np.arange(0, t_end, dt)
     T = len(time)
     X1 = np.array([20, 30, -np.pi / 2, 0, 10.]) if X1 is None else np.asarray(X1, float)
-    X = np.zeros((T, n_ac, 5)); U = np.zeros((T, n_ac)); Rr_log = np.zeros((T, n_ac)); eth = np.zeros((T, n_ac - 1))
+    B = chain_incidence(n_ac) if B is None else np.asarray(B, float)
+    X = np.zeros((T, n_ac, 5)); U = np.zeros((T, n_ac)); Rr_log = np.zeros((T, n_ac)); eth = np.zeros((T, B.shape[1]))
     X[0] = X1
-    B = chain_incidence(n_ac) if B is None else B
     c = np.asarray(c, float)
     for i in range(1, T):
         Ur, e_deg = dcf(B, c, X[i - 1, :, :2].T, z_des, kr)

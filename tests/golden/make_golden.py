@@ -405,6 +405,10 @@ def golden_colloc():
             out[f"cost1/{name}/{tag}/cost"] = np.array(c.cost(fr, P))
             out[f"cost1/{name}/{tag}/grad"] = np.asarray(c.cost_grad(fr, P))
         print(f"cost {name}: {float(out[f'cost1/{name}/sol/cost']):.15e} |grad| {np.linalg.norm(out[f'cost1/{name}/sol/grad']):.15e}")
+    bank_max = d2ou.CostBank(); bank_max.use_mean = False        # max-squared-bank mode, opty_utils.py:72,78-81
+    for tag, fr in (("sol", sol), ("noisy", free)):
+        out[f"cost1/bankmax/{tag}/cost"] = np.array(bank_max.cost(fr, SinglePlannerShim(N, 2.5)))
+        out[f"cost1/bankmax/{tag}/grad"] = np.asarray(bank_max.cost_grad(fr, SinglePlannerShim(N, 2.5)))
     P2 = SinglePlannerShim(N, 3.5)
     out["cost1/input_scaled/noisy/cost"] = np.array(costs["input"].cost(free, P2))
     out["cost1/input_scaled/noisy/grad"] = costs["input"].cost_grad(free, P2)

@@ -283,11 +283,14 @@ def test_reference_csv_solutions_are_feasible_and_round_trip(golden, tmp_path):
     assert np.abs(q.prob.con(q.solution)).max() < 1e-6
 
 
-@pytest.mark.parametrize("n_ac,N,n_prob", [(2, 33, 1), (3, 64, 2), (8, 100, 3), (16, 97, 2), (17, 40, 1), (5, 31, 70), (33, 20, 1)])
+@pytest.mark.parametrize("n_ac,N,n_prob", [(2, 33, 1), (3, 64, 2), (8, 100, 3), (16, 97, 2), (17, 40, 1), (5, 31, 70), (33, 20, 1),
+                                           (16, 97, 200), (3, 65, 300), (7, 150, 120), (2, 500, 40), (9, 100, 200)])
 def test_all_pairs_kernel_shapes_against_oracle(n_ac, N, n_prob):
     """colloc_pairs_kernel (every unordered pair once, exponentials handed over through shared-memory slots): even / odd
     aircraft counts, fewer aircraft than warps, more than two aircraft per warp, ragged last tile, the two-kernel cost
-    reduction of large batches (n_prob >= 64), and the ordered fallback beyond the shared-memory budget (33 aircraft)."""
+    reduction of large batches (n_prob >= 64), and the ordered fallback beyond the shared-memory budget (33 aircraft).
+    Launches of >= 16384 nodes take colloc_pairs_node_kernel<NAC> (one thread per node, all aircraft in registers) when
+    NAC is instantiated (16, 3, 7, 2 here; 9 is not and stays on the shared-memory kernel)."""
     from oracle import d2d_oracle as orc
     from d2d_b200.collocation import CollocationProblem, CostSpec
     rng = np.random.default_rng(100 + n_ac)
@@ -299,7 +302,7 @@ def test_all_pairs_kernel_shapes_against_oracle(n_ac, N, n_prob):
         inst = [(k, 0, 0.5 * k) for k in range(3 * n_ac)]
         prob = CollocationProblem(n_ac, N, h, wind=(1., 2.), inst=inst, cost=cs)
         res, jac, cost, grad = prob.evaluate(free)
-        for p in range(min(n_prob, 3)):
+        for p in sorted({0, 1, 2, n_prob - 1} & set(range(n_prob))):
             np.testing.assert_allclose(res[p], orc.colloc_residual(free[p], N, n_ac, h, (1., 2.), inst), rtol=RTOL, atol=1e-10)
             np.testing.assert_allclose(jac[p][:-len(inst)], orc.colloc_jac_compact(free[p], N, n_ac, h).reshape(-1), rtol=RTOL)
             co, go = orc.cost_and_grad(free[p], N, n_ac, spec, multi=True)
@@ -333,3 +336,22 @@ def test_fused_peer_evaluation_emulated_on_one_gpu(golden, world, n_prob):
     for r in range(world):
         np.testing.assert_array_equal(out["cost"][r], out["cost"][0])
         np.testing.assert_allclose(out["cost"][r], cost, rtol=1e-13)
+
+
+def test_cost_bank_max_mode_against_reference_golden(golden):
+    """CostBank with use_mean = False (d2d/opty_utils.py:72,78-81): obj_scale * max(phi^2), one gradient entry at the first
+    maximum; fixtures from the unmodified reference class."""
+    from d2d_b200 import opty_utils
+    g = golden["colloc"]
+    N = 1001
+
+    class P:
+        num_nodes, obj_scale = N, 2.5
+        _slice_x, _slice_y, _slice_psi, _slice_phi, _slice_v = (slice(k * N, (k + 1) * N) for k in range(5))
+    c = opty_utils.CostBank(); c.use_mean = False
+    for tag, fr in (("sol", g["c3/sol"]), ("noisy", g["c3/free"])):
+        np.testing.assert_allclose(c.cost(fr, P), g[f"cost1/bankmax/{tag}/cost"], rtol=1e-15)
+        np.testing.assert_array_equal(c.cost_grad(fr, P), g[f"cost1/bankmax/{tag}/grad"])
+    tie = np.zeros(5 * N); tie[3 * N + 7] = -0.3; tie[3 * N + 400] = 0.3          # equal squares: np.argmax takes the first
+    gr = c.cost_grad(tie, P)
+    assert gr[3 * N + 7] == 2.5 * 2 * -0.3 and np.count_nonzero(gr) == 1

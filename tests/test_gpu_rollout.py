@@ -441,3 +441,59 @@ def test_small_helpers_run_on_the_engine(d2d, golden):
     l0 = d2d.get_engine().launches
     guidance.norm_mpi_pi(np.zeros(3)); guidance.CircleTraj().get(np.zeros(5), 1.)
     assert d2d.get_engine().launches == l0 + 2
+
+
+def _ring_incidence(n):
+    B = np.zeros((n, n))
+    for j in range(n):
+        B[j, j], B[(j + 1) % n, j] = -1, 1
+    return B
+
+
+def _complete_incidence(n):
+    edges = [(a, b) for a in range(n) for b in range(a + 1, n)]
+    B = np.zeros((n, len(edges)))
+    for k, (a, b) in enumerate(edges):
+        B[a, k], B[b, k] = -1, 1
+    return B
+
+
+@pytest.mark.parametrize("graph,n_ac", [("ring", 5), ("complete", 4), ("complete", 6)])
+def test_dcf_general_incidence_matrices(d2d, graph, n_ac):
+    """The reference's DCFController.get takes ANY incidence matrix (d2d/guidance.py:103-126): ring graphs (n_e = n_ac) and
+    complete graphs (n_e > n_ac: lanes own several edges) in the single call and in the formation rollout, several
+    formations per warp."""
+    from d2d_b200 import guidance, simulation
+    from oracle import d2d_oracle as orc
+    rng = np.random.default_rng(30 + n_ac)
+    B = _ring_incidence(n_ac) if graph == "ring" else _complete_incidence(n_ac)
+    n_e = B.shape[1]
+    z = rng.uniform(-1, 1, n_e)
+    p, c = rng.normal(0, 40, (2, n_ac)), rng.normal(0, 5, (n_ac, 2))
+    Ur, e_deg = guidance.DCFController().get(n_ac, B, c, p, z, 20)
+    Uo, eo = orc.dcf(B, c, p, z.copy(), 20)
+    np.testing.assert_allclose(Ur[:, 0], Uo, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.ravel(e_deg), eo, rtol=1e-12, atol=1e-12)
+    F, T = 7, 120
+    cs = rng.normal(0, 3, (F, n_ac, 2))
+    X1 = np.array([20, 30, -np.pi / 2, 0, 10.])
+    out = simulation.formation_rollout(cs, 60., n_ac, T, 0.05, 4e-4, 15, 5., z, X1, B=B)
+    for f in (0, F - 1):
+        Xo, Uo_, _, Rro, etho = orc.run_formation(cs[f], 60., n_ac, T * 0.05 - 1e-9, 4e-4, 15, 5., z.copy(), B=B)
+        np.testing.assert_allclose(out["X"][f], Xo, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(out["e_theta"][f], etho, rtol=0, atol=1e-8)
+
+
+def test_rollout_without_final_control_has_defined_last_row(d2d, golden):
+    """final_control=False skips the trailing ctl.get of 05_test_simulation.py:33: the last state row is still the state at
+    the last sample, the last input row reads zero (never uninitialised memory)."""
+    from d2d_b200 import simulation, trajectory
+    g = golden["dfff_c1"]
+    time = g["time"][:300]
+    tr = trajectory.TrajectoryCircle(alpha0=3 * np.pi / 2)
+    a = simulation.rollout(time, [tr], [5., 0.], g["X"][:1], log_ref=True)
+    b = simulation.rollout(time, [tr], [5., 0.], g["X"][:1], log_ref=True, final_control=False)
+    np.testing.assert_array_equal(b.X, a.X)
+    np.testing.assert_array_equal(b.U[:, :-1], a.U[:, :-1])
+    assert not b.U[:, -1].any() and not b.K[:, -1].any() and not b.Xref[:, -1].any()
+    np.testing.assert_array_equal(b.X[:, -1], b.X_final)
