@@ -14,7 +14,6 @@ namespace d2dx {
 
 constexpr int kCollocThreads = 128;
 constexpr int kMaxTickets = 64;
-constexpr long kNodeKernelMinNodes = 16384;   // n_prob * N from which the thread-per-node all-pairs kernel fills the GPU
 constexpr int kPairWarps = 8;       // warps per block of colloc_pairs_kernel (aircraft w, w + 8, ... per warp)
 
 // finishes the cost of problem `prob`: per-block partials -> scratch; in ticket mode the last block of the problem sums
@@ -136,7 +135,10 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 5 : 8) colloc_kernel(c
 //   phase B  aircraft a collects the rounds in which it was the partner (slot sE[k-1][a - k]), then does the node's
 //            residual / Jacobian / input-cost work and writes the whole gradient row.
 // Two block barriers, no read-modify-write in shared memory, every sum in a fixed order.
-__global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const __grid_constant__ CollocArgs a) {
+// REGS: every warp owns at most two aircraft (n_ac <= 16): their phase-A gradients wait in registers, not in shared memory
+// (49 KB per block and 64 registers: four resident blocks = 32 warps per SM instead of 24).
+template <bool REGS>
+__global__ void __launch_bounds__(kPairWarps * 32, REGS ? 4 : 3) colloc_pairs_kernel(const __grid_constant__ CollocArgs a) {
   extern __shared__ double sm[];
   const d2dx_colloc_problem& P = a.p;
   const int N = P.N, n = P.n_ac, half = n / 2;
@@ -148,8 +150,8 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const 
   const double* fr = a.free_ + (size_t)prob * a.n_free;
   double* spos = sm + lane;                        // [2n][2][32]
   double* sE = spos + 2 * n * 64;                  // [half][n][32]
-  double* sg = sE + half * n * 32;                 // [n][2][32]  own-side position gradient of phase A
-  double* sred = sm + (2 * n * 64 + half * n * 32 + n * 64);   // [W][4]
+  double* sg = sE + half * n * 32;                 // [n][2][32]  own-side position gradient of phase A (!REGS)
+  double* sred = sm + (2 * n * 64 + half * n * 32 + (REGS ? 0 : n * 64));   // [W][4]
   const bool use_obs = enabled(P.kobs) && P.n_obs > 0;
 
   for (int g = w; g < n; g += W) {
@@ -163,10 +165,10 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const 
   const double sN = a.sN, nkr2 = a.nkr2, cw = a.cw;
   double s_v = 0.0, s_phi = 0.0, s_obs = 0.0, s_col = 0.0;
 
-  for (int a_l = w; a_l < n; a_l += W) {           // phase A
+  auto phase_a = [&](int a_l, double& gx, double& gy) {
     const double* pa = spos + (a_l * 2) * 32;
     const double xa = pa[0], ya = pa[32];
-    double gx = 0.0, gy = 0.0;
+    gx = 0.0; gy = 0.0;
     if (use_obs && a_l == 0 && valid) obstacle_terms(P, sN, xa, ya, s_obs, gx, gy);
     const int kmax = (even && a_l >= half) ? half - 1 : half;
     const double* pb = pa + 64;                    // partner a_l + 1
@@ -181,16 +183,10 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const 
       gx = fma(wgt, dx, gx); gy = fma(wgt, dy, gy);
       pb += 64; e += n * 32;
     }
-    sg[(a_l * 2) * 32] = gx; sg[(a_l * 2 + 1) * 32] = gy;
-  }
-  if (!valid) s_col = 0.0;                         // overhanging lanes of the last tile evaluated zeros
-  __syncthreads();
-
-  const bool want_cg = true;
-  for (int a_l = w; a_l < n; a_l += W) {           // phase B
+  };
+  auto phase_b = [&](int a_l, double gx, double gy) {
     const double* pa = spos + ((a_l + n) * 2) * 32;
     const double xa = pa[0], ya = pa[32];
-    double gx = sg[(a_l * 2) * 32], gy = sg[(a_l * 2 + 1) * 32];
     const int kmax = (even && a_l < half) ? half - 1 : half;
     const double* pb = pa - 64;                    // partner a_l - 1 (upper copy: no wrap)
     // the slot of round k was written by aircraft a_l - k (mod n): sE[(k-1) n + a_l - k] while a_l - k >= 0, n entries
@@ -209,7 +205,27 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const 
       const double wgt = cw * pe[0];
       gx = fma(wgt, xa - pb[0], gx); gy = fma(wgt, ya - pb[32], gy);
     }
-    if (valid) colloc_node(a, fr, prob, a_l, i, xa, ya, gx, gy, want_cg, s_v, s_phi);
+    if (valid) colloc_node(a, fr, prob, a_l, i, xa, ya, gx, gy, true, s_v, s_phi);
+  };
+
+  if (REGS) {
+    const bool h0 = w < n, h1 = w + W < n;
+    double gx0 = 0.0, gy0 = 0.0, gx1 = 0.0, gy1 = 0.0;
+    if (h0) phase_a(w, gx0, gy0);
+    if (h1) phase_a(w + W, gx1, gy1);
+    if (!valid) s_col = 0.0;                       // overhanging lanes of the last tile evaluated zeros
+    __syncthreads();
+    if (h0) phase_b(w, gx0, gy0);
+    if (h1) phase_b(w + W, gx1, gy1);
+  } else {
+    for (int a_l = w; a_l < n; a_l += W) {
+      double gx, gy;
+      phase_a(a_l, gx, gy);
+      sg[(a_l * 2) * 32] = gx; sg[(a_l * 2 + 1) * 32] = gy;
+    }
+    if (!valid) s_col = 0.0;
+    __syncthreads();
+    for (int a_l = w; a_l < n; a_l += W) phase_b(a_l, sg[(a_l * 2) * 32], sg[(a_l * 2 + 1) * 32]);
   }
 
   if (tile == 0) {                                 // instance constraints: first tile of each problem
@@ -232,79 +248,11 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) colloc_pairs_kernel(const 
   }
 }
 
-// All-pairs collision mode for BATCHES of problems: one thread = one node of one problem, ALL aircraft.  The positions and
-// the position gradient of the NAC aircraft stay in registers (4 NAC doubles), every unordered pair is evaluated once and
-// credited to both members, then the thread does the node's residual / Jacobian / input-cost work aircraft by aircraft.
-// No shared memory, no barrier, no exchange between threads; the independent pair evaluations give the instruction-level
-// parallelism that hides latency at ~10 warps per SM.  Every load / store is still coalesced along the node index
-// (consecutive threads = consecutive nodes of one aircraft's row).  Used when the launch has enough nodes to fill the GPU;
-// single problems keep colloc_pairs_kernel (32 x more threads per problem: lower latency).
-constexpr int kNodeThreads = 64;
-template <int NAC>
-__global__ void __launch_bounds__(kNodeThreads, 5) colloc_pairs_node_kernel(const __grid_constant__ CollocArgs a) {
-  __shared__ double sred[kNodeThreads / 32][4];
-  const d2dx_colloc_problem& P = a.p;
-  const int N = P.N;
-  const int tile = blockIdx.x % a.ntiles, prob = blockIdx.x / a.ntiles;
-  const int i = tile * kNodeThreads + threadIdx.x;
-  const bool valid = i < N;
-  const double* fr = a.free_ + (size_t)prob * a.n_free;
-  const bool use_obs = enabled(P.kobs) && P.n_obs > 0;
-  double s_v = 0.0, s_phi = 0.0, s_obs = 0.0, s_col = 0.0;
-  if (valid) {
-    double x[NAC], y[NAC], gx[NAC], gy[NAC];
-#pragma unroll
-    for (int g = 0; g < NAC; ++g) { x[g] = fr[(3 * g) * N + i]; y[g] = fr[(3 * g + 1) * N + i]; gx[g] = 0.0; gy[g] = 0.0; }
-    if (use_obs) obstacle_terms(P, a.sN, x[0], y[0], s_obs, gx[0], gy[0]);
-    const double nkr2 = a.nkr2, cw = a.cw;
-#pragma unroll
-    for (int p = 0; p < NAC; ++p) {
-#pragma unroll
-      for (int q = p + 1; q < NAC; ++q) {
-        const double dx = x[p] - x[q], dy = y[p] - y[q];
-        const double es = fm::exp_neg(nkr2 * fma(dx, dx, dy * dy));
-        s_col += es;
-        const double wgt = cw * es;
-        gx[p] = fma(wgt, dx, gx[p]); gy[p] = fma(wgt, dy, gy[p]);
-        gx[q] = fma(-wgt, dx, gx[q]); gy[q] = fma(-wgt, dy, gy[q]);
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < NAC; ++g) colloc_node(a, fr, prob, g, i, x[g], y[g], gx[g], gy[g], true, s_v, s_phi);
-  }
-  if (tile == 0) {                                 // instance constraints: first tile of each problem
-    for (int k = threadIdx.x; k < P.n_inst; k += kNodeThreads) {
-      if (a.what & D2DX_EVAL_RESIDUAL)
-        a.res[(size_t)prob * a.n_con + 3 * NAC * (N - 1) + k] = fr[P.inst_var[k] * N + P.inst_node[k]] - P.inst_val[k];
-      if (a.what & D2DX_EVAL_JAC) a.jac[(size_t)prob * a.nnz + (a.nnz - P.n_inst) + k] = 1.0;
-    }
-  }
-  if (a.what & D2DX_EVAL_COST) {
-    const double v4[4] = {warp_sum(s_v), warp_sum(s_phi), warp_sum(s_obs), warp_sum(s_col)};
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { sred[w][0] = v4[0]; sred[w][1] = v4[1]; sred[w][2] = v4[2]; sred[w][3] = v4[3]; }
-    __syncthreads();
-    if (w == 0) {
-      double b4[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int q = 0; q < kNodeThreads / 32; ++q) { b4[0] += sred[q][0]; b4[1] += sred[q][1]; b4[2] += sred[q][2]; b4[3] += sred[q][3]; }
-      cost_finish(a, prob, tile, b4, use_obs, true, lane);
-    }
-  }
+static size_t pairs_smem_bytes(int n) {
+  const bool regs = n <= 2 * kPairWarps;
+  return ((size_t)(2 * n * 64 + (n / 2) * n * 32 + (regs ? 0 : n * 64)) + kPairWarps * 4) * sizeof(double);
 }
 
-typedef void (*NodeKernel)(const CollocArgs);
-static NodeKernel node_kernel_for(int n_ac) {
-  switch (n_ac) {
-    case 2: return colloc_pairs_node_kernel<2>;   case 3: return colloc_pairs_node_kernel<3>;
-    case 4: return colloc_pairs_node_kernel<4>;   case 5: return colloc_pairs_node_kernel<5>;
-    case 6: return colloc_pairs_node_kernel<6>;   case 7: return colloc_pairs_node_kernel<7>;
-    case 8: return colloc_pairs_node_kernel<8>;   case 10: return colloc_pairs_node_kernel<10>;
-    case 12: return colloc_pairs_node_kernel<12>; case 16: return colloc_pairs_node_kernel<16>;
-    default: return nullptr;
-  }
-}
-
-static size_t pairs_smem_bytes(int n) { return ((size_t)(2 * n * 64 + (n / 2) * n * 32 + n * 64) + kPairWarps * 4) * sizeof(double); }
 
 // second pass of the cost for large batches: one warp per problem sums the per-block partials in a fixed order
 __global__ void __launch_bounds__(128) colloc_cost_kernel(const __grid_constant__ CollocArgs a, int use_obs, int use_col) {
@@ -476,18 +424,15 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
   const bool col = want_cg && enabled_h(p->kcol) && n_total > 1;
   const bool obs = want_cg && enabled_h(p->kobs) && p->n_obs > 0;
   cudaStream_t st = as_stream(stream);
-  NodeKernel nk = (col && p->col_all_pairs && pos_all == nullptr && (long)n_prob * p->N >= kNodeKernelMinNodes) ? node_kernel_for(p->n_ac) : nullptr;
-  if (nk) {                                      // batches: one thread per node, all aircraft in registers
-    a.TN = kNodeThreads; a.APP = p->n_ac; a.ntiles = (p->N + kNodeThreads - 1) / kNodeThreads; a.nparts = a.ntiles;
-    nk<<<(unsigned)((long)n_prob * a.ntiles), kNodeThreads, 0, st>>>(a);
-    D2DX_LAUNCH_CHECK("colloc_pairs_node_kernel");
-  } else if (col && p->col_all_pairs && pos_all == nullptr && pairs_smem_bytes(p->n_ac) <= 200 * 1024) {
+  const bool all_pairs_local = col && p->col_all_pairs && pos_all == nullptr;
+  if (all_pairs_local && pairs_smem_bytes(p->n_ac) <= 200 * 1024) {
     a.TN = 32; a.APP = kPairWarps; a.ntiles = (p->N + 31) / 32; a.nparts = a.ntiles;
     const size_t smem = pairs_smem_bytes(p->n_ac);
-    if (smem > 48 * 1024)
-      D2DX_CUDA(cudaFuncSetAttribute(colloc_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool regs = p->n_ac <= 2 * kPairWarps;
+    auto kern = regs ? colloc_pairs_kernel<true> : colloc_pairs_kernel<false>;
+    if (smem > 48 * 1024) D2DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int warps = p->n_ac < kPairWarps ? p->n_ac : kPairWarps;
-    colloc_pairs_kernel<<<(unsigned)((long)n_prob * a.ntiles), warps * 32, smem, st>>>(a);
+    kern<<<(unsigned)((long)n_prob * a.ntiles), warps * 32, smem, st>>>(a);
     D2DX_LAUNCH_CHECK("colloc_pairs_kernel");
   } else {
     tile_shape(p->n_ac, a.TN, a.APP);

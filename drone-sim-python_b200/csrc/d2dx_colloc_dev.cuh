@@ -57,20 +57,40 @@ __device__ __forceinline__ void obstacle_terms(const d2dx_colloc_problem& P, dou
   }
 }
 
+// inputs of one (aircraft, node) beyond its position: heading, bank, speed and the previous node's x, y, psi
+struct NodeIn { double psi, phi, v, xp, yp, pp; };
+
+__device__ __forceinline__ void colloc_offsets(const d2dx_colloc_problem& P, int a_l, int i, int& ox, int& ophi, int& ov) {
+  const int N = P.N, n_ac = P.n_ac, n = 3 * n_ac;
+  const int bphi = P.perm_phi ? P.perm_phi[a_l] : a_l;
+  const int bv = P.perm_v ? P.perm_v[a_l] : n_ac + a_l;
+  ox = 3 * a_l * N + i; ophi = (n + bphi) * N + i; ov = (n + bv) * N + i;
+}
+
+__device__ __forceinline__ NodeIn colloc_load(const CollocArgs& a, const double* __restrict__ fr, int a_l, int i) {
+  int ox, ophi, ov;
+  colloc_offsets(a.p, a_l, i, ox, ophi, ov);
+  const int N = a.p.N;
+  NodeIn in;
+  in.psi = fr[ox + 2 * N]; in.phi = fr[ophi]; in.v = fr[ov];
+  in.xp = in.yp = in.pp = 0.0;
+  if ((a.what & D2DX_EVAL_RESIDUAL) && i >= 1) { in.xp = fr[ox - 1]; in.yp = fr[ox + N - 1]; in.pp = fr[ox + 2 * N - 1]; }
+  return in;
+}
+
 // One (aircraft a_l, node i < N) of problem `prob`: backward-Euler defects (equation-major, opty layout), the 12 structural
 // Jacobian entries (compact or opty-dense), the input cost sums and every gradient entry of the node; (gx, gy) = the
 // position gradient the caller accumulated (obstacles, collisions; STORE_XY = false leaves those two entries to the caller).
 // Offsets inside one problem fit 32 bits.
 template <bool STORE_XY = true>
-__device__ __forceinline__ void colloc_node(const CollocArgs& a, const double* __restrict__ fr, int prob, int a_l, int i,
-                                            double x, double y, double gx, double gy, bool want_cg, double& s_v, double& s_phi) {
+__device__ __forceinline__ void colloc_node_in(const CollocArgs& a, int prob, int a_l, int i, double x, double y, const NodeIn& in,
+                                               double gx, double gy, bool want_cg, double& s_v, double& s_phi) {
   const d2dx_colloc_problem& P = a.p;
   const int N = P.N, n_ac = P.n_ac, n = 3 * n_ac;
-  const int bphi = P.perm_phi ? P.perm_phi[a_l] : a_l;
-  const int bv = P.perm_v ? P.perm_v[a_l] : n_ac + a_l;
-  const int ox = 3 * a_l * N + i, oy = ox + N, ops = oy + N;
-  const int ophi = (n + bphi) * N + i, ov = (n + bv) * N + i;
-  const double psi = fr[ops], phi = fr[ophi], v = fr[ov];
+  int ox, ophi, ov;
+  colloc_offsets(P, a_l, i, ox, ophi, ov);
+  const int oy = ox + N, ops = oy + N;
+  const double psi = in.psi, phi = in.phi, v = in.v;
 
   if ((a.what & (D2DX_EVAL_RESIDUAL | D2DX_EVAL_JAC)) && i >= 1) {
     const double ih = a.ih;
@@ -81,11 +101,10 @@ __device__ __forceinline__ void colloc_node(const CollocArgs& a, const double* _
     const double tn = sp * rcp_f(cp);            // tan(phi)
     const double gtv = kG * tn * iv;             // g tan(phi) / v
     if (a.what & D2DX_EVAL_RESIDUAL) {           // equation-major, node-minor (opty layout)
-      const double xp = fr[ox - 1], yp = fr[oy - 1], pp = fr[ops - 1];
       double* r = a.res + (size_t)prob * a.n_con + (3 * a_l * (N - 1) + (i - 1));
-      r[0] = (x - xp) * ih - v * c + P.wind[0];
-      r[N - 1] = (y - yp) * ih - v * s + P.wind[1];
-      r[2 * (N - 1)] = (psi - pp) * ih - gtv;
+      r[0] = (x - in.xp) * ih - v * c + P.wind[0];
+      r[N - 1] = (y - in.yp) * ih - v * s + P.wind[1];
+      r[2 * (N - 1)] = (psi - in.pp) * ih - gtv;
     }
     if (a.what & D2DX_EVAL_JAC) {
       const double j[12] = {ih, v * s, -ih, -c, ih, -v * c, -ih, -s, ih, -ih, -kG * fma(tn, tn, 1.0) * iv, gtv * iv};
@@ -94,6 +113,7 @@ __device__ __forceinline__ void colloc_node(const CollocArgs& a, const double* _
 #pragma unroll
         for (int k = 0; k < 12; ++k) jo[k * (N - 1)] = j[k];
       } else {                                   // opty-dense: [(N-1)][3 n_ac][8 n_ac]
+        const int bphi = P.perm_phi ? P.perm_phi[a_l] : a_l, bv = P.perm_v ? P.perm_v[a_l] : n_ac + a_l;
         const int q = 2 * n_ac, W = 2 * n + q;
         double* jo = a.jac + (size_t)prob * a.nnz + ((size_t)(i - 1) * n + 3 * a_l) * W;
         const int cx = 3 * a_l, cp_ = n + 3 * a_l, cphi = 2 * n + bphi, cv = 2 * n + bv;
@@ -121,6 +141,13 @@ __device__ __forceinline__ void colloc_node(const CollocArgs& a, const double* _
       go[ov] = (P.kvel * 2.0 * dv) * norm_in;
     }
   }
+}
+
+template <bool STORE_XY = true>
+__device__ __forceinline__ void colloc_node(const CollocArgs& a, const double* __restrict__ fr, int prob, int a_l, int i,
+                                            double x, double y, double gx, double gy, bool want_cg, double& s_v, double& s_phi) {
+  const NodeIn in = colloc_load(a, fr, a_l, i);
+  colloc_node_in<STORE_XY>(a, prob, a_l, i, x, y, in, gx, gy, want_cg, s_v, s_phi);
 }
 
 // cost of one problem from the four summed partials (CostComposit, multiopty_utils.py:156-174 / opty_utils.py:147-165)

@@ -17,10 +17,10 @@ __device__ __forceinline__ void sincos_b(double x, double& s, double& c) { ::sin
 __device__ __forceinline__ void sincos_any(double x, double& s, double& c) { ::sincos(x, &s, &c); }
 __device__ __forceinline__ double atan2_f(double y, double x) { return ::atan2(y, x); }
 __device__ __forceinline__ double atan_f(double v) { return ::atan(v); }
-__device__ __forceinline__ double sqrt_f(double v) { return ::sqrt(v); }
-__device__ __forceinline__ double rsqrt_f(double v) { return ::rsqrt(v); }
-__device__ __forceinline__ double rcp_f(double v) { return 1.0 / v; }
-__device__ __forceinline__ double div_f(double a, double b) { return a / b; }
+__host__ __device__ __forceinline__ double sqrt_f(double v) { return ::sqrt(v); }
+__host__ __device__ __forceinline__ double rsqrt_f(double v) { return 1.0 / ::sqrt(v); }
+__host__ __device__ __forceinline__ double rcp_f(double v) { return 1.0 / v; }
+__host__ __device__ __forceinline__ double div_f(double a, double b) { return a / b; }
 #else
 __device__ __forceinline__ void sincos_b(double x, double& s, double& c) { fm::sincos(x, s, c); }
 // libdevice's Payne-Hanek path for huge phases, out of line and by value: its scratch array stays in ITS frame, the caller
@@ -33,10 +33,19 @@ __device__ __forceinline__ void sincos_any(double x, double& s, double& c) {
 }
 __device__ __forceinline__ double atan2_f(double y, double x) { return fm::atan2(y, x); }
 __device__ __forceinline__ double atan_f(double v) { return fm::atan(v); }
-__device__ __forceinline__ double sqrt_f(double v) { return fm::sqrt(v); }
-__device__ __forceinline__ double rsqrt_f(double v) { return fm::rsqrt(v); }
-__device__ __forceinline__ double rcp_f(double v) { return fm::rcp(v); }
-__device__ __forceinline__ double div_f(double a, double b) { return fm::div(a, b); }
+// host instances (plain IEEE operations) exist so that the Riccati reductions below can be compiled for the CPU and checked
+// against scipy.linalg.solve_continuous_are without a GPU (csrc/host_check.cu, tests/test_care_math.py)
+#ifdef __CUDA_ARCH__
+__host__ __device__ __forceinline__ double sqrt_f(double v) { return fm::sqrt(v); }
+__host__ __device__ __forceinline__ double rsqrt_f(double v) { return fm::rsqrt(v); }
+__host__ __device__ __forceinline__ double rcp_f(double v) { return fm::rcp(v); }
+__host__ __device__ __forceinline__ double div_f(double a, double b) { return fm::div(a, b); }
+#else
+__host__ __device__ __forceinline__ double sqrt_f(double v) { return ::sqrt(v); }
+__host__ __device__ __forceinline__ double rsqrt_f(double v) { return 1.0 / ::sqrt(v); }
+__host__ __device__ __forceinline__ double rcp_f(double v) { return 1.0 / v; }
+__host__ __device__ __forceinline__ double div_f(double a, double b) { return a / b; }
+#endif
 #endif
 
 constexpr double kPi = 3.141592653589793;        // np.pi
@@ -351,7 +360,8 @@ __device__ __forceinline__ void flatness(const FlatOut& Y, double wx, double wy,
 // a 2x2 Newton iteration (quadratic, warm-started from the previous control step; cold start = the decoupled
 // b2 = 0 solution C = 0, S = 1, al = sqrt(q3 + 2 v c1 sqrt(q))).  K' = [[C, S, al]/sqrt(r1) ; [S, -C, be]/sqrt(r2)]
 // (times sqrt(q) on the first two columns) and K1 = K' T.  Checked against scipy.linalg.solve_continuous_are
-// over v in [0.3, 60], |phi| < 1.4 to 3e-13 (tests/test_care_math.py).
+// over v in [0.3, 60], |phi| < 1.4 to 3e-13 (tests/test_care_math.py runs THIS code, compiled for the host by
+// csrc/host_check.cu, against SciPy; tests/test_gpu_rollout.py checks the device instance).
 struct CareState { double C, S, al, dth, dal; };   // solution of the previous control step and its last change
 
 struct CareConst { double sq, q3, sr1, sr2, isr1, isr2; };
@@ -366,14 +376,14 @@ __host__ __device__ __forceinline__ CareConst care_const(const d2dx_dfff_gains& 
 struct CareStep { double k1, ba, vc2, ve, k2, q3; };   // per-control-step constants of the two residuals
 
 // residuals F1, F2 at (C, S, al); also returns be
-__device__ __forceinline__ void care_residual(const CareStep& k, double C, double S, double al, double& be, double& F1, double& F2) {
+__host__ __device__ __forceinline__ void care_residual(const CareStep& k, double C, double S, double al, double& be, double& F1, double& F2) {
   be = fma(k.k1, C, k.ba * al);
   F1 = fma(C, al, fma(S, be, fma(k.vc2, C, k.ve * S)));
   F2 = fma(al, al, fma(be, be, -fma(k.k2, S, k.q3)));
 }
 
 // apply the update (dth, dal): rotate (C, S) by dth (first order + one Newton normalisation step), al += dal
-__device__ __forceinline__ void care_update(double& C, double& S, double& al, double dth, double dal) {
+__host__ __device__ __forceinline__ void care_update(double& C, double& S, double& al, double dth, double dal) {
   const double Cn = fma(-S, dth, C), Sn = fma(C, dth, S);
   const double nrm = fma(-0.5, fma(Cn, Cn, Sn * Sn), 1.5);        // 1/sqrt(1 + dth^2) up to O(dth^4)
   C = Cn * nrm; S = Sn * nrm; al += dal;
@@ -381,7 +391,7 @@ __device__ __forceinline__ void care_update(double& C, double& S, double& al, do
 
 // Full Newton iteration loop (cold starts, trajectory corners, anything the two-step fast path did not finish).
 struct CareRoot { double C, S, al; bool conv; };
-static __device__ __noinline__ CareRoot care_newton_loop_v(const CareStep k, double C, double S, double al, int max_it) {
+static __host__ __device__ __noinline__ CareRoot care_newton_loop_v(const CareStep k, double C, double S, double al, int max_it) {
   bool conv = false;
   for (int it = 0; it < max_it && !conv; ++it) {
     double be, F1, F2;
@@ -400,7 +410,7 @@ static __device__ __noinline__ CareRoot care_newton_loop_v(const CareStep k, dou
   r.C = C; r.S = S; r.al = al; r.conv = conv;
   return r;
 }
-__device__ __forceinline__ bool care_newton_loop(const CareStep& k, double& C, double& S, double& al, int max_it) {
+__host__ __device__ __forceinline__ bool care_newton_loop(const CareStep& k, double& C, double& S, double& al, int max_it) {
   const CareRoot r = care_newton_loop_v(k, C, S, al, max_it);
   C = r.C; S = r.S; al = r.al;
   return r.conv;
@@ -410,7 +420,7 @@ __device__ __forceinline__ bool care_newton_loop(const CareStep& k, double& C, d
 // smoothly, so the start is already O(drift^2) close); then ONE Newton step and ONE chord step (same Jacobian) in
 // straight-line code, accepted when the chord step is below 3e-8 (=> error ~1e-15); otherwise the general loop.
 // Returns false when not even the loop converged.
-__device__ __forceinline__ bool care_gain(const CareConst& cc, double v, double c1, double e, CareState& st, bool cold, double* K0) {
+__host__ __device__ __forceinline__ bool care_gain(const CareConst& cc, double v, double c1, double e, CareState& st, bool cold, double* K0) {
   const double c1q = c1 * cc.sq;                                   // c1 = sqrt(r1)/b1, e = b2 c1
   CareStep k;
   k.k1 = c1q * cc.isr2; k.ba = e * cc.isr2; k.vc2 = v * cc.sr2; k.ve = v * e; k.k2 = 2.0 * v * c1q; k.q3 = cc.q3;

@@ -145,26 +145,27 @@ __device__ __forceinline__ void sincos_small(double d, double& s, double& c) {
 
 // exp(y) for y <= 0 (Gaussian-type penalties): k = rint(y log2 e), r = y - k ln2 (two-term), degree-13 Taylor polynomial
 // on |r| <= ln2/2 (truncation 4e-18 relative), scaling through the exponent field; flushes to 0 below 2^-1000.
+// The polynomial is evaluated by Estrin's scheme: 16 fp64 instructions instead of Horner's 13, but a dependency depth of 5
+// instead of 13 -- the collision kernels are bound by the latency of this chain, not by its instruction count.
 __device__ __forceinline__ double exp_neg(double y) {
   const double t = fma(y, kTab[60], kTab[1]);
   const int k = __double2loint(t);
   const double j = t - kTab[1];
   double r = fma(j, kTab[61], y);
   r = fma(j, kTab[62], r);
-  double p = kTab[63];                               // 1/13!
-  p = fma(p, r, kTab[64]);                           // 1/12!
-  p = fma(p, r, kTab[65]);                           // 1/11!
-  p = fma(p, r, kTab[66]);                           // 1/10!
-  p = fma(p, r, kTab[67]);                           // 1/9!
-  p = fma(p, r, kTab[68]);                           // 1/8!
-  p = fma(p, r, kTab[69]);                           // 1/7!
-  p = fma(p, r, kTab[70]);                           // 1/6!
-  p = fma(p, r, kTab[71]);                           // 1/5!
-  p = fma(p, r, kTab[72]);                           // 1/4!
-  p = fma(p, r, kTab[73]);                           // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  const double r2 = r * r;
+  const double p01 = 1.0 + r;                                   // c0 + c1 r
+  const double p23 = fma(kTab[73], r, 0.5);                     // c2 + c3 r       (1/2!, 1/3!)
+  const double p45 = fma(kTab[71], r, kTab[72]);                // 1/4! + r/5!
+  const double p67 = fma(kTab[69], r, kTab[70]);                // 1/6! + r/7!
+  const double p89 = fma(kTab[67], r, kTab[68]);                // 1/8! + r/9!
+  const double pab = fma(kTab[65], r, kTab[66]);                // 1/10! + r/11!
+  const double pcd = fma(kTab[63], r, kTab[64]);                // 1/12! + r/13!
+  const double r4 = r2 * r2;
+  const double q0 = fma(p23, r2, p01), q1 = fma(p67, r2, p45), q2 = fma(pab, r2, p89);
+  const double r8 = r4 * r4;
+  const double s0 = fma(q1, r4, q0), s1 = fma(pcd, r4, q2);
+  const double p = fma(s1, r8, s0);
   const int hi = __double2hiint(p) + (k << 20);
   const double v = __hiloint2double(hi, __double2loint(p));
   return (k < -1000) ? 0.0 : v;

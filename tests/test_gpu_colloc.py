@@ -289,8 +289,7 @@ def test_all_pairs_kernel_shapes_against_oracle(n_ac, N, n_prob):
     """colloc_pairs_kernel (every unordered pair once, exponentials handed over through shared-memory slots): even / odd
     aircraft counts, fewer aircraft than warps, more than two aircraft per warp, ragged last tile, the two-kernel cost
     reduction of large batches (n_prob >= 64), and the ordered fallback beyond the shared-memory budget (33 aircraft).
-    Launches of >= 16384 nodes take colloc_pairs_node_kernel<NAC> (one thread per node, all aircraft in registers) when
-    NAC is instantiated (16, 3, 7, 2 here; 9 is not and stays on the shared-memory kernel)."""
+    n_ac <= 16 takes the instantiation whose phase-A gradients wait in registers, larger counts the shared-memory one."""
     from oracle import d2d_oracle as orc
     from d2d_b200.collocation import CollocationProblem, CostSpec
     rng = np.random.default_rng(100 + n_ac)
