@@ -157,8 +157,9 @@ __device__ __forceinline__ void segment_eval(int type, LD P, double t, FlatOut& 
       double l0, l1, l2, l3 = 0.0;   // lambda(t) and its derivatives: polynomial (PolynomialOne / AffineOne / CstOne) or SinOne (:26-38)
       if (P(16) == 0.0) {
         auto cl = [&](int k) { return P(5 + k); };
-        l0 = poly_row<0>(cl, t); l1 = poly_row<1>(cl, t); l2 = poly_row<2>(cl, t);
-        if (WANT3) l3 = poly_row<3>(cl, t);
+        const double td = t - P(14);  // time origin of the polynomial piece (0 for PolynomialOne / AffineOne; the knot of a FooOne piece)
+        l0 = poly_row<0>(cl, td); l1 = poly_row<1>(cl, td); l2 = poly_row<2>(cl, td);
+        if (WANT3) l3 = poly_row<3>(cl, td);
       } else {
         const double a = P(6), om = P(7);
         double sa, ca;

@@ -3,8 +3,8 @@
 //
 // Every rank owns an exchange buffer (cudaMalloc) that all other ranks map (CUDA IPC between processes, plain pointers
 // inside one process).  One evaluation =
-//   phase 0  each block stores its tile of the OWNED aircraft's x, y straight from free_local into every peer's position
-//            table, then (fence + flag per peer) publishes the tile;
+//   phase 0  each block stores its tiles of the OWNED aircraft's x, y straight from free_local into every peer's position
+//            table, then (one fence, one flag per tile and peer) publishes them -- for ALL its tiles before anything else;
 //   phase 1  residual / Jacobian / input cost / gradient of psi, phi, v of the owned aircraft (needs no remote data: this is
 //            what hides the NVLink latency);
 //   phase 2  wait for the same tile of every peer, stage all positions in shared memory;
@@ -82,22 +82,18 @@ __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const _
   const double* cpart_in = reinterpret_cast<const double*>(mine + g.off_cpart);
   double* lpart = reinterpret_cast<double*>(mine + g.off_lpart);
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {   // same order on every rank: see the deadlock note in DESIGN
-    const int prob = item / g.ntiles, tile = item - prob * g.ntiles;
-    const int i = tile * 32 + lane;
-    const bool valid = i < N;
-    const double* fr = a.free_ + (size_t)prob * a.n_free;
-    __syncthreads();                               // shared memory of the previous item is free
-
-    // ---- phase 0: publish the owned positions of this tile ----
-    if (use_col) {
-      for (int a_l = w; a_l < n_own; a_l += W) {
-        const int gl = a.a_lo + a_l;
-        double x = 0.0, y = 0.0;
-        if (valid) { x = fr[(3 * a_l) * N + i]; y = fr[(3 * a_l + 1) * N + i]; }
-        spos[(gl * 2) * 32] = x; spos[(gl * 2 + 1) * 32] = y;
-        if (valid) {
-          const size_t o = (((size_t)prob * n_total + gl) * 2) * N + i;
+  // ---- sweep A: publish the owned positions of EVERY tile this block will process, one fence, then the flags; by the time
+  // the block comes to a tile's collision terms the peers' stores for it have long landed (the NVLink latency of a batch
+  // is paid once, not per tile) ----
+  if (use_col && g.world > 1) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int prob = item / g.ntiles, tile = item - prob * g.ntiles;
+      const int i = tile * 32 + lane;
+      if (i < N) {
+        const double* fr = a.free_ + (size_t)prob * a.n_free;
+        for (int a_l = w; a_l < n_own; a_l += W) {
+          const double x = fr[(3 * a_l) * N + i], y = fr[(3 * a_l + 1) * N + i];
+          const size_t o = (((size_t)prob * n_total + a.a_lo + a_l) * 2) * N + i;
           for (int r = 0; r < g.world; ++r) {
             if (r == g.rank) continue;
             double* dst = reinterpret_cast<double*>(g.base[r] + g.off_pos);
@@ -105,10 +101,33 @@ __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const _
           }
         }
       }
-      __syncthreads();
-      if (threadIdx.x < g.world && threadIdx.x != g.rank) {
-        uint32_t* f = reinterpret_cast<uint32_t*>(g.base[threadIdx.x] + g.off_posflag);
-        flag_store(f + ((size_t)g.rank * g.max_prob + prob) * g.ntiles + tile, epoch);
+    }
+    __syncthreads();
+    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    bool fenced = false;
+    for (int idx = threadIdx.x; idx < my_items * g.world; idx += blockDim.x) {
+      const int r = idx % g.world, item = blockIdx.x + (idx / g.world) * gridDim.x;
+      if (r == g.rank) continue;
+      if (!fenced) { __threadfence_system(); fenced = true; }
+      const int prob = item / g.ntiles, tile = item - prob * g.ntiles;
+      uint32_t* f = reinterpret_cast<uint32_t*>(g.base[r] + g.off_posflag);
+      *reinterpret_cast<volatile uint32_t*>(f + ((size_t)g.rank * g.max_prob + prob) * g.ntiles + tile) = epoch;
+    }
+  }
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {   // same order on every rank: see the deadlock note in DESIGN
+    const int prob = item / g.ntiles, tile = item - prob * g.ntiles;
+    const int i = tile * 32 + lane;
+    const bool valid = i < N;
+    const double* fr = a.free_ + (size_t)prob * a.n_free;
+    __syncthreads();                               // shared memory of the previous item is free
+
+    if (use_col) {                                 // the owned positions of this tile into shared memory
+      for (int a_l = w; a_l < n_own; a_l += W) {
+        const int gl = a.a_lo + a_l;
+        double x = 0.0, y = 0.0;
+        if (valid) { x = fr[(3 * a_l) * N + i]; y = fr[(3 * a_l + 1) * N + i]; }
+        spos[(gl * 2) * 32] = x; spos[(gl * 2 + 1) * 32] = y;
       }
     }
 

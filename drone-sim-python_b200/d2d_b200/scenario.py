@@ -1,7 +1,7 @@
 """Named scenarios -- the `d2d.scenario` registry (d2d/scenario.py): trajectories + time grid + wind + initial
 states + perturbations.  Data only; `d2d_b200.simulation.test_simulation` runs one on the engine.
-Scenarios built on spline / tabulated trajectories ("dual opty", "opty2", the default "circle") need files or
-FITPACK and are outside the hot path; "circle" is offered in its constant-ground-speed form."""
+"circle" defaults, like upstream, to the constant-air-speed space-indexed circle (TrajSiSpline: its constructor runs the
+upstream optimiser with the flat output evaluated on the engine); `cst_gvel=True` gives the plain TrajectoryCircle."""
 import numpy as np
 
 from . import trajectory as ddt
@@ -80,13 +80,14 @@ class ScenLine2(Scenario):                                   # :88-98
 
 
 @register
-class ScenCircle(Scenario):                                  # :101-139, constant ground speed variant (:106-107)
+class ScenCircle(Scenario):                                  # :101-139
     name = desc = "circle"
 
-    def __init__(self, duration=None, cst_gvel=True):
-        if not cst_gvel:
-            raise NotImplementedError("ScenCircle(cst_gvel=False) needs TrajSiSpline (FITPACK + optimiser), outside the hot path")
-        self.trajs = [ddt.TrajectoryCircle(alpha0=3 * np.pi / 2)]
+    def __init__(self, duration=None, cst_gvel=False, knots=None):
+        if cst_gvel:                                         # constant ground speed (:106-107)
+            self.trajs = [ddt.TrajectoryCircle(alpha0=3 * np.pi / 2)]
+        else:                                                # constant air speed (:108-109): upstream's default
+            self.trajs = [ddtf.TrajSiSpline(duration=20., knots=knots)]
         self.extends = (-10, 75, -10, 75)
         self.windfield = WindField([5, 0])
         self.time = np.arange(0, self.trajs[0].duration, 0.01)

@@ -221,8 +221,34 @@ class SpaceIndexedTraj(Trajectory):
         self._dyn = dyn
         self.duration = dyn.duration
 
+    def _piecewise(self):
+        """knots / values of a piecewise-linear dynamic (FooOne, d2d/trajectory_factory.py:225-234), else None"""
+        dyn = self._dyn
+        return (dyn.xs, dyn.ys, dyn.ds) if all(hasattr(dyn, k) for k in ("xs", "ys", "ds")) else None
+
+    def is_composite(self):
+        return self._piecewise() is not None
+
+    @property
+    def steps_end(self):
+        return self._piecewise()[0][1:]
+
     def segments(self):
-        g, dyn = self._geom, self._dyn
+        pw = self._piecewise()
+        if pw is not None:
+            # one space-indexed segment per linear piece: lambda = ys[i] + (t - xs[i]) ds[i] (bit-identical: the Horner
+            # recurrence in (t - knot) does the same multiply and add), selected like CompositeTraj selects its steps
+            xs, ys, ds = pw
+            out = []
+            for i in range(len(ds)):
+                ty, p = self._segment_for(_AffinePiece(ys[i], ds[i]))
+                p[14] = xs[i]
+                out.append((ty, p))
+            return out
+        return [self._segment_for(self._dyn)]
+
+    def _segment_for(self, dyn):
+        g = self._geom
         p = np.zeros(_lib.SEG_NPAR)
         if isinstance(dyn, SinOne):
             p[5], p[6], p[7], p[8], p[16] = dyn.c, dyn.a, dyn.om, dyn.t0, 1.
@@ -235,11 +261,19 @@ class SpaceIndexedTraj(Trajectory):
             uv = g.un * g.v
             p1 = np.asarray(g.p1, dtype=float) - uv * g.t0          # geometry evaluated at lambda: p1 + un v (lambda - t0)
             p[1], p[2], p[3], p[4] = p1[0], p1[1], uv[0], uv[1]
-            return [(_lib.SEG_SI_LINE, p)]
+            return (_lib.SEG_SI_LINE, p)
         if isinstance(g, TrajectoryCircle):
             p[0], p[1], p[2], p[3], p[4], p[13] = g.t0, g.c[0], g.c[1], g.r, g.omega, g.alpha0
-            return [(_lib.SEG_SI_CIRCLE, p)]
+            return (_lib.SEG_SI_CIRCLE, p)
         raise NotImplementedError("SpaceIndexedTraj: only line and circle geometries run on the engine")
+
+
+class _AffinePiece:
+    """coefficient rows of value + slope * t in the PolynomialOne layout (4, 8)"""
+
+    def __init__(self, value, slope):
+        self.coefs = np.zeros((4, 8))
+        self.coefs[0, 0], self.coefs[0, 1], self.coefs[1, 0] = value, slope, slope
 
 
 class CircleBatch:

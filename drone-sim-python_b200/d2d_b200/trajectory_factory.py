@@ -1,6 +1,5 @@
 """Named trajectories -- the `d2d.trajectory_factory` registry (d2d/trajectory_factory.py) for the
-trajectory families the engine evaluates.  Spline / tabulated trajectories (TrajSpline, TrajSiSpline,
-TrajTabulated) are outside the hot path and are not provided."""
+trajectory families the engine evaluates, spline, tabulated and space-indexed ones included."""
 import numpy as np
 
 from . import _lib
@@ -194,6 +193,60 @@ class SplineOne:                                             # d2d/trajectory_fa
         tab = eng.table(PackedTrajectories([0], [n], [0.], [np.inf], [_lib.SEG_POLY] * n, ends, par))
         Y = eng.traj_eval(tab, eng.to_device(np.array([float(t)])))
         return Y.cpu().numpy().reshape(4, 2)[:, 0].copy()
+
+
+class FooOne:                                                # d2d/trajectory_factory.py:225-234
+    """Piecewise-linear scalar dynamic through (xs, ys): value, slope, 0, 0."""
+
+    def __init__(self, xs, ys):
+        self.xs, self.ys = np.asarray(xs), np.asarray(ys)
+        self.dxs, self.dys = self.xs[1:] - self.xs[:-1], self.ys[1:] - self.ys[:-1]
+        self.ds = self.dys / self.dxs
+        self.duration = xs[-1]
+
+    def get(self, t):
+        _i = np.where(t >= self.xs)[0][-1]
+        return np.array([self.ys[_i] + (t - self.xs[_i]) * self.ds[_i], self.ds[_i], 0, 0])
+
+
+@register
+class TrajSiSpline(ddt.SpaceIndexedTraj):                    # d2d/trajectory_factory.py:241-285
+    """Three quarters of a circle flown at (nearly) constant AIR speed in a 5 m/s wind: the space-indexed circle whose
+    piecewise-linear dynamic lambda(t) the upstream constructor finds with scipy.optimize.minimize (:264-279).  Like upstream,
+    the object is left with the LAST dynamic the optimiser probed (err_fun calls set_dyn; the fitted spline goes to `_dyn4`
+    and is not installed).  Every evaluation of the flat output inside the optimisation runs on the engine (one traj_eval
+    launch per probe); the linear pieces become space-indexed segments of one composite trajectory.
+
+    `knots=(xs, ys)` installs a given dynamic instead of running the optimiser (a BFGS path is not reproducible to the last
+    bit across BLAS / libm builds: parity tests feed the knots the unmodified reference ended with)."""
+    name, desc = "sispline", "spline dev"
+    extends = (-10, 100, -10, 50)
+
+    def __init__(self, duration=30., knots=None, vtarget=10., wind=(5., 0.)):
+        geometry = ddt.TrajectoryCircle(c=[30., 30.], r=30., v=2 * np.pi * 30., t0=0., alpha0=0, dalpha=3 * np.pi / 2)
+        dynamic = ddt.AffineOne(1. / duration, 0., duration=duration)
+        ddt.SpaceIndexedTraj.__init__(self, geometry, dynamic)
+        self._dyn1 = self._dyn
+        self.ts = np.arange(0, self._dyn.duration, 0.5)
+        if knots is not None:
+            self.set_dyn(FooOne(np.asarray(knots[0], dtype=float), np.asarray(knots[1], dtype=float)))
+            self._dyn4 = SplineOne(self._dyn.xs, self._dyn.ys)
+            return
+        npts = 10
+        xs = np.linspace(0, 30, npts)
+        w = np.asarray(wind, dtype=float)
+
+        def err_fun(p):
+            ys = np.concatenate(([0.], np.cumsum(p)))
+            self.set_dyn(FooOne(xs, ys))
+            flat_out = self.get_many(self.ts)
+            vair = np.linalg.norm(flat_out[:, 1] - w, axis=1)
+            return np.mean(np.square(vair - vtarget))
+        import scipy.optimize
+        res = scipy.optimize.minimize(err_fun, [1. / npts] * (npts - 1))
+        self.fit_error = float(res.fun)
+        ys = np.concatenate(([0.], np.cumsum(res.x)))
+        self._dyn4 = SplineOne(xs, ys)
 
 
 def print_available():

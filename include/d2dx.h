@@ -54,8 +54,9 @@ enum {
   D2DX_SEG_SLALOM = 2,  /* par: 0 t0 | 1 p1x 2 p1y | 3 (un*v)x 4 (un*v)y | 5 phase                */
   D2DX_SEG_POLY = 3,    /* par: 0 t0 | 1..8 x coefs[0][0..7] | 9..16 y coefs[0][0..7]             */
   D2DX_SEG_SI_LINE = 4, /* SpaceIndexedTraj, line geometry: 0 unused | 1 p1x 2 p1y 3 (un*v)x 4 (un*v)y (geometry, t0=0)
-                           dynamics lambda(t): slot 16 = 0 -> polynomial 5..12 coefs[0][0..7] (PolynomialOne, AffineOne,
-                           CstOne); slot 16 = 1 -> SinOne (d2d/trajectory.py:26-38): 5 c | 6 a | 7 om | 8 t0       */
+                           dynamics lambda(t): slot 16 = 0 -> polynomial 5..12 coefs[0][0..7] in (t - slot 14) (PolynomialOne,
+                           AffineOne, CstOne with slot 14 = 0; one linear piece of FooOne, d2d/trajectory_factory.py:225-234,
+                           with slot 14 = its knot); slot 16 = 1 -> SinOne (d2d/trajectory.py:26-38): 5 c | 6 a | 7 om | 8 t0 */
   D2DX_SEG_TABLE = 5,   /* par: 0 t0(unused) | 1 first row in the tab_* arrays | 2 number of rows:
                            TrajTabulated, d2d/trajectory_factory.py:149-171 (zero-order lookup of a
                            planner solution: row = first sample time >= t, row 0 past the end)       */

@@ -630,6 +630,19 @@ def golden_spline(sim):
     X0b = ddg.DiffFlatness.state_and_input_from_output(tr.get(0.5), wind2.sample(0, None), ac)[0] + np.array([1., 1., 0., 0., 1.])
     Xb, Ub, _, _, _ = run_dfff(sim, time2[50:], tr, wind2, X0b, np.zeros((len(time2) - 50, 5)))
     si["si/run/time"], si["si/run/wind"], si["si/run/X0"], si["si/run/X"], si["si/run/U"] = time2[50:], np.array([0.5, -0.5]), X0b, Xb, Ub
+    # TrajSiSpline (trajectory_factory.py:241-285) as ScenCircle builds it by default (scenario.py:109): the constructor's
+    # optimiser leaves the object with the last FooOne it probed; its knots are stored so that the engine-side class can be
+    # given the same dynamic (a BFGS path is not bit-reproducible across builds), then the whole default "circle" scenario
+    import d2d.scenario as dds
+    scen = dds.ScenCircle()
+    tr_s = scen.trajs[0]
+    t_s = np.linspace(0., tr_s.duration - 0.01, 300)
+    si["sisp/xs"], si["sisp/ys"], si["sisp/duration"] = np.asarray(tr_s._dyn.xs, float), np.asarray(tr_s._dyn.ys, float), np.array(tr_s.duration)
+    si["sisp/t"], si["sisp/Y"] = t_s, np.array([tr_s.get(t) for t in t_s])
+    Xs, Us, _, Xrs, Ks = run_dfff(sim, scen.time, tr_s, scen.windfield, scen.X0s[0], scen.perts[0])
+    si["sisp/time"], si["sisp/X0"], si["sisp/X"], si["sisp/U"] = scen.time, np.asarray(scen.X0s[0], float), Xs[::10], Us[::10]
+    vair = np.linalg.norm(si["sisp/Y"][:, 1] - np.array([5., 0.]), axis=1)
+    print("sispline: duration", tr_s.duration, "knots ys", si["sisp/ys"], "air speed range", vair.min(), vair.max(), "X[-1]", Xs[-1])
     np.savez_compressed(os.path.join(HERE, "spline.npz"), duration=traj.duration, ts=ts, Y=Y, one_xs=xs, one_ys=ys, one_t=t1, one_Y=Y1,
                         time=time, wind=np.array([1., 0.5]), X0=X0, X=X, U=U, **si)
 

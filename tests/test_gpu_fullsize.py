@@ -103,3 +103,132 @@ def test_long_horizon_against_c_oracle():
     err = np.abs(res.X[ok] - ref["X"][ok]).max()
     print("long horizon: max |dX| =", err, "over", int(ok.sum()), "scenarios x 101 logged samples")
     assert err < 1e-9
+
+
+def _teacher_forced_max_err(eng, table, time, wind, X_ref, log_every, seg_rows):
+    """Re-seeds the engine from the oracle's logged state at every logged sample and advances one log interval: returns the
+    largest |dX| over all (scenario, window) pairs against the oracle's next logged state, and the per-window maxima."""
+    import torch
+    n, rows = X_ref.shape[0], X_ref.shape[1]
+    Wd = eng.to_device(np.ascontiguousarray(wind.T))
+    acd = eng.to_device(np.stack([np.full(n, 0.01), np.full(n, 1.)]))
+    td = eng.to_device(time)
+    worst = np.zeros(rows - 1)
+    for k in range(rows - 1):
+        X0d = eng.to_device(np.ascontiguousarray(X_ref[:, k].T))
+        Xf = eng.empty(5, n)
+        flags = eng.zeros(n, dtype=torch.int32)
+        eng.rollout_dfff(table, X0d, Wd, acd, td, k * log_every, (k + 1) * log_every, nsub=1, final_control=False, X_final=Xf, flags=flags)
+        got = Xf.cpu().numpy().T
+        d = np.abs(got - X_ref[:, k + 1])
+        d[:, 2] = np.abs((d[:, 2] + np.pi) % (2 * np.pi) - np.pi)        # a heading at the +-pi seam may sit on either side
+        worst[k] = d.max()
+    return worst.max(), worst
+
+
+def test_c5_every_sampled_scenario_teacher_forced_against_c_oracle():
+    """Closes the hole of the free-running comparison: about a fifth of the C5 population asks for more than the 45 deg bank
+    limit (tight circle, high speed), leaves its reference and then evolves chaotically, so free-running trajectories of the
+    engine and of the oracle separate for those although every step agrees.  Here EVERY one of the 384 sampled scenarios --
+    diverging ones included -- is compared window by window: the engine restarts from the oracle's logged state every 100
+    steps and must land on the oracle's next logged state within north_star's 1e-9."""
+    import bench
+    from d2d_b200 import _lib, get_engine
+    from d2d_b200.engine import PackedTrajectories
+    from d2d_b200.simulation import MonteCarloRollout
+    from oracle import c_oracle as co
+    eng = get_engine()
+    B, T, every = 10 ** 6, 10 ** 4, 100
+    w = bench.workload(B, 12345)
+    X0 = bench.flat_state0(w) + w["noise"]
+    time = np.arange(T + 1) * 0.01
+    rng = np.random.default_rng(7)
+    idx = np.sort(rng.choice(B, 384, replace=False))
+    n = len(idx)
+    ty, opar = co.circle_par(w["cx"][idx], w["cy"][idx], w["r"][idx], w["v"][idx], w["a0"][idx])
+    ref = co.rollout(time, ty, opar, w["wind"][idx], X0[idx], log_every=every)
+    assert ref["failed"] == 0
+    par = np.zeros((_lib.SEG_NPAR, n)); par[:6] = opar[:, :6].T
+    ar = np.arange(n, dtype=np.int32)
+    table = eng.table(PackedTrajectories(ar, np.ones(n, np.int32), np.zeros(n), np.zeros(n), np.full(n, _lib.SEG_CIRCLE, np.int32), np.zeros(n), par,
+                                         _lib.SEG_CIRCLE))
+    worst, per_window = _teacher_forced_max_err(eng, table, time, w["wind"][idx], ref["X"], every, None)
+    # free-running comparison of the same sample: which scenarios separate from the oracle, and why
+    mc = MonteCarloRollout(n, time, _lib.SEG_CIRCLE, log_every=every, n_chunks=4, host_log=False)
+    mc.set_inputs(par[:6], w["wind"][idx], X0[idx])
+    mc.run()
+    free = np.abs(mc.d_Xlog.cpu().numpy().transpose(2, 0, 1) - ref["X"]).max(axis=(1, 2))
+    apart = free > 1e-9
+    # what the reference asks of the aircraft along its circle (flat output -> bank and air-speed command, d2d/guidance.py:25-44)
+    al = np.linspace(0, 2 * np.pi, 64, endpoint=False)[:, None]
+    om = (w["v"] / w["r"])[None]
+    vax, vay = -w["v"][None] * np.sin(al) - w["wind"][None, :, 0], w["v"][None] * np.cos(al) - w["wind"][None, :, 1]
+    y2x, y2y = -om * w["v"][None] * np.cos(al), -om * w["v"][None] * np.sin(al)
+    va = np.hypot(vax, vay)
+    phi_ref = np.arctan((y2y * vax - y2x * vay) / va / 9.81)
+    u_v = (vax * y2x + vay * y2y) / va + va                    # tau_v = 1
+    over_bank = np.abs(phi_ref).max(0) > np.deg2rad(45.)
+    over_v = (u_v.max(0) > 20.) | (u_v.min(0) < 4.)
+    infeasible = over_bank | over_v
+    print(f"C5 teacher-forced: max |dX| over {n} scenarios x {len(per_window)} windows of {every} steps = {worst:.3e}; "
+          f"free-running, {int(apart.sum())} of {n} separate from the oracle by more than 1e-9 (max {free.max():.3e}), "
+          f"{int((apart & infeasible[idx]).sum())} of them with a reference outside the input limits; population: "
+          f"{over_bank.mean() * 100:.2f} % ask for more than 45 deg of bank, {over_v.mean() * 100:.2f} % for an air speed outside [4, 20] m/s")
+    assert worst < 1e-9
+    assert free[~apart].size > 0.7 * n
+
+
+def test_c5_mixed_population_full_size_teacher_forced():
+    """SURVEY 8d's second C5 population at full size: 5 x 10^5 circles and 5 x 10^5 randomised min-snap polynomials, sorted by
+    type (one specialised launch sequence per family), 3000 steps; a sample of each family is compared with the C oracle
+    free-running where it tracks and teacher-forced (every 100 steps) everywhere."""
+    import bench
+    from d2d_b200 import _lib, get_engine, trajectory as ddt
+    from d2d_b200.engine import PackedTrajectories
+    from d2d_b200.simulation import MonteCarloRollout
+    from oracle import c_oracle as co
+    eng = get_engine()
+    Bh, T, every, dur = 500000, 3000, 100, 33.65
+    time = np.arange(T + 1) * 0.01
+    rng = np.random.default_rng(2024)
+    # circles
+    w = bench.workload(Bh, 4321)
+    X0c = bench.flat_state0(w) + w["noise"]
+    mc = MonteCarloRollout(Bh, time, _lib.SEG_CIRCLE, log_every=every, n_chunks=3, host_log=False)
+    parc = np.zeros((6, Bh)); parc[1], parc[2], parc[3], parc[4], parc[5] = w["cx"], w["cy"], w["r"], w["v"] / w["r"], w["a0"]
+    mc.set_inputs(parc, w["wind"], X0c)
+    outc = mc.run()
+    Xc = mc.d_Xlog.cpu().numpy()
+    # min-snap polynomials (TrajMinSnapDemo-like boundary conditions, randomised)
+    Y0 = np.zeros((Bh, 2, 4)); Y1 = np.zeros((Bh, 2, 4))
+    a0, a1 = rng.uniform(-0.5, 0.5, Bh), rng.uniform(1.0, 2.0, Bh)
+    Y0[:, 0, 0], Y0[:, 1, 0] = rng.uniform(-20, 20, Bh), rng.uniform(-20, 20, Bh)
+    Y0[:, 0, 1], Y0[:, 1, 1] = 10 * np.cos(a0), 10 * np.sin(a0)
+    Y1[:, 0, 0], Y1[:, 1, 0] = Y0[:, 0, 0] + rng.uniform(150, 250, Bh), Y0[:, 1, 0] + rng.uniform(150, 250, Bh)
+    Y1[:, 0, 1], Y1[:, 1, 1] = 10 * np.cos(a1), 10 * np.sin(a1)
+    msb = ddt.MinSnapBatch.from_boundaries(Y0, Y1, dur)
+    windp = rng.normal(0, 1.0, (Bh, 2))
+    X0p = np.stack([Y0[:, 0, 0] + rng.normal(0, 2, Bh), Y0[:, 1, 0] + rng.normal(0, 2, Bh), a0, 0 * a0, 10. + rng.normal(0, 0.3, Bh)], 1)
+    mp_ = MonteCarloRollout(Bh, time, _lib.SEG_POLY, log_every=every, n_chunks=3, host_log=False)
+    parp = np.zeros((_lib.SEG_NPAR, Bh)); parp[1:9] = msb.coefs0[:, 0].T; parp[9:17] = msb.coefs0[:, 1].T
+    mp_.set_inputs(parp, windp, X0p)
+    outp = mp_.run()
+    Xp = mp_.d_Xlog.cpu().numpy()
+    assert not outc["flags"].any() and not (outp["flags"] & 1).any()
+    for fam, Xlog, types, par_rows, wind, X0, seg in (("circle", Xc, co.T_CIRCLE, parc, w["wind"], X0c, _lib.SEG_CIRCLE),
+                                                      ("minsnap", Xp, co.T_POLY, parp, windp, X0p, _lib.SEG_POLY)):
+        idx = np.sort(rng.choice(Bh, 192, replace=False))
+        n = len(idx)
+        opar = np.zeros((n, 17)); opar[:, :par_rows.shape[0]] = par_rows[:, idx].T
+        ref = co.rollout(time, np.full(n, types, np.int32), opar, wind[idx], X0[idx], log_every=every)
+        assert ref["failed"] == 0
+        tracked = ref["max_err"] < 10.0
+        got = Xlog[:, :, idx].transpose(2, 0, 1)
+        free_err = np.abs(got[tracked] - ref["X"][tracked]).max()
+        par = np.zeros((_lib.SEG_NPAR, n)); par[:par_rows.shape[0]] = par_rows[:, idx]
+        ar = np.arange(n, dtype=np.int32)
+        table = eng.table(PackedTrajectories(ar, np.ones(n, np.int32), np.zeros(n), np.zeros(n), np.full(n, seg, np.int32), np.zeros(n), par, seg))
+        worst, _ = _teacher_forced_max_err(eng, table, time, wind[idx], ref["X"], every, None)
+        print(f"mixed population, {fam}: free-running max |dX| = {free_err:.3e} over {int(tracked.sum())} tracked of {n}; "
+              f"teacher-forced max |dX| = {worst:.3e} over all {n}")
+        assert free_err < 1e-9 and worst < 1e-9

@@ -39,7 +39,8 @@ def _worker(rank, world, port, free, inst, ret):
         assert torch.equal(a_, b_)
     sc2 = ShardedCollocation(16, 500, 0.02, (0., 0.), inst, copy.copy(cs), engine=eng, backend="collective")   # NCCL all-gather + all-reduce
     res2, jac2, cost2, grad2 = sc2.evaluate(fl)
-    assert torch.equal(res2, res) and torch.equal(jac2, jac) and torch.equal(grad2, grad)
+    for a_, b_, tol in ((res2, res, 1e-14), (jac2, jac, 1e-14), (grad2, grad, 1e-13)):      # two different kernels: same values, not same bits
+        assert torch.allclose(a_, b_, rtol=tol, atol=1e-16), float((a_ - b_).abs().max())
     assert abs(float(cost2[0]) - float(cost[0])) <= 1e-13 * abs(float(cost[0]))
     # scenario-sharded rollout: each rank its contiguous half of 64 circles, then the one final all-reduce
     rng = np.random.default_rng(0)

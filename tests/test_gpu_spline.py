@@ -78,3 +78,32 @@ def test_space_indexed_geometries_and_dynamics():
     X, U, _ = run_simulation(time, ddyn.Aircraft(), ddg.WindField(list(g["si/run/wind"])), ctl, g["si/run/X0"], np.zeros((len(time), 5)))
     np.testing.assert_allclose(X, g["si/run/X"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(U, g["si/run/U"], rtol=0, atol=1e-8)
+
+
+def test_trajsispline_and_default_circle_scenario_against_reference_golden(golden):
+    """TrajSiSpline (d2d/trajectory_factory.py:241-285) and the default ScenCircle built on it (d2d/scenario.py:109), given the
+    knots the unmodified reference's constructor ended with: flat output to 1e-11, DFFF closed loop to 1e-9; and the
+    constructor's own optimisation (flat output evaluated on the engine at every probe) reaches the reference's fit."""
+    from d2d_b200 import scenario as dds, simulation, trajectory_factory as ddtf
+    g = golden["spline"]
+    knots = (g["sisp/xs"], g["sisp/ys"])
+    tr = ddtf.TrajSiSpline(duration=20., knots=knots)
+    assert tr.duration == float(g["sisp/duration"]) and tr.is_composite()
+    np.testing.assert_allclose(tr.get_many(g["sisp/t"]), g["sisp/Y"], rtol=0, atol=1e-11)
+    for t in (0., 3.3333333333333335, 12.34, 29.5):                      # knot, interior, last sample of the optimiser grid
+        np.testing.assert_allclose(tr.get(t), tr.get_many([t])[0], rtol=0, atol=0)
+    scen = dds.ScenCircle(knots=knots)
+    assert len(scen.time) == len(g["sisp/time"])
+    np.testing.assert_allclose(np.asarray(scen.X0s[0], float), g["sisp/X0"], rtol=0, atol=1e-11)
+    Xs, Us, _ = simulation.test_simulation(scen)
+    np.testing.assert_allclose(Xs[0][::10], g["sisp/X"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(Us[0][::10], g["sisp/U"], rtol=0, atol=1e-8)
+    # the constructor as upstream runs it (scipy.optimize.minimize over the 9 increments of lambda): same objective value
+    # class as the reference's fit (its knots give this air-speed error on the optimiser's own grid)
+    def fit_err(t_):
+        Y = t_.get_many(t_.ts)
+        return np.mean(np.square(np.linalg.norm(Y[:, 1] - np.array([5., 0.]), axis=1) - 10.))
+    own = ddtf.TrajSiSpline(duration=20.)
+    ref_fit = fit_err(ddtf.TrajSiSpline(duration=20., knots=knots))
+    assert own.fit_error <= ref_fit * 1.05 + 1e-6, (own.fit_error, ref_fit)
+    assert dds.get("circle") is not None
