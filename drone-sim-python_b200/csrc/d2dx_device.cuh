@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/d2dx.h"
 #include "d2dx_math.cuh"
@@ -57,7 +58,10 @@ constexpr double kG = 9.81;                      // d2d/dynamic.py:9, d2d/guidan
 // fmod for |a| < 4 pi (a - 2pi is exact there by Sterbenz) and skip CUDA's iterative fmod.
 __device__ __forceinline__ double wrap_pi(double v) {
   double a = v + kPi, m;
-  if (a >= 0.0 && a < kTwoPi) m = a;
+  // common case first, decided by ONE unsigned compare of the high word: hi(a) < hi(2 pi) = 0x401921FB implies 0 <= a < 2 pi
+  // (sign bit clear, magnitude below); the exact comparisons below take everything else, including hi(a) == hi(2 pi)
+  if (static_cast<unsigned>(__double2hiint(a)) < 0x401921FBu) m = a;
+  else if (a >= 0.0 && a < kTwoPi) m = a;
   else if (a >= kTwoPi && a < 2.0 * kTwoPi) m = a - kTwoPi;
   else if (a < 0.0 && a > -kTwoPi) m = a + kTwoPi;
   else {
@@ -274,6 +278,11 @@ __device__ __forceinline__ void stage_heading(double s0, double c0, double d, do
   c = fma(-s0, sd, c0 * cd);
 }
 
+// |x| below a validity threshold given by its HIGH WORD (integer pipe; NaN compares false).  The thresholds of the fast RK4 path
+// are safety margins, not sharp limits: 0x3FB99999 = just under 0.1, 0x3FF26666 = just under 1.15.
+__device__ __forceinline__ bool abs_below(double x, int thr_hi) { return (__double2hiint(x) & 0x7fffffff) < thr_hi; }
+constexpr int kHiIncr = 0x3FB99999, kHiBank = 0x3FF26666;
+
 // Fixed-step stand-in for Aircraft.disc_dyn (d2d/dynamic.py:25-28): nsub classical RK4 sub-steps of cont_dyn
 // (:14-23) with the input held, then psi wrapped once (:27).  Straight-line fast path: the four stage headings share
 // one full sincos (stages 2-4 by angle addition of the increment h psi_dot), tan(phi) is a Pade ratio folded into
@@ -295,22 +304,22 @@ __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c
     // stage 1
     const double k1x = v * c1 + a.wx, k1y = v * s1 + a.wy, k1p = turn_rate(phi, v);
     const double k1f = a.n_inv_tau_phi * (phi - phi_c), k1v = a.n_inv_tau_v * (v - v_c);
-    fast_ok = fast_ok && (fabs(phi) <= 1.15);
+    fast_ok = fast_ok && abs_below(phi, kHiBank);
     // stage 2
     double ph = phi + hh * k1f, vv = v + hh * k1v;
-    d = hh * k1p; fast_ok = fast_ok && (fabs(d) < 0.1) && (fabs(ph) <= 1.15);
+    d = hh * k1p; fast_ok = fast_ok && abs_below(d, kHiIncr) && abs_below(ph, kHiBank);
     stage_heading(s1, c1, d, s, c);
     const double k2x = vv * c + a.wx, k2y = vv * s + a.wy, k2p = turn_rate(ph, vv);
     const double k2f = a.n_inv_tau_phi * (ph - phi_c), k2v = a.n_inv_tau_v * (vv - v_c);
     // stage 3
     ph = phi + hh * k2f; vv = v + hh * k2v;
-    d = hh * k2p; fast_ok = fast_ok && (fabs(d) < 0.1) && (fabs(ph) <= 1.15);
+    d = hh * k2p; fast_ok = fast_ok && abs_below(d, kHiIncr) && abs_below(ph, kHiBank);
     stage_heading(s1, c1, d, s, c);
     const double k3x = vv * c + a.wx, k3y = vv * s + a.wy, k3p = turn_rate(ph, vv);
     const double k3f = a.n_inv_tau_phi * (ph - phi_c), k3v = a.n_inv_tau_v * (vv - v_c);
     // stage 4
     ph = phi + h * k3f; vv = v + h * k3v;
-    d = h * k3p; fast_ok = fast_ok && (fabs(d) < 0.1) && (fabs(ph) <= 1.15);
+    d = h * k3p; fast_ok = fast_ok && abs_below(d, kHiIncr) && abs_below(ph, kHiBank);
     stage_heading(s1, c1, d, s, c);
     const double k4x = vv * c + a.wx, k4y = vv * s + a.wy, k4p = turn_rate(ph, vv);
     const double k4f = a.n_inv_tau_phi * (ph - phi_c), k4v = a.n_inv_tau_v * (vv - v_c);
@@ -363,6 +372,17 @@ __device__ __forceinline__ void flatness(const FlatOut& Y, double wx, double wy,
 // (times sqrt(q) on the first two columns) and K1 = K' T.  Checked against scipy.linalg.solve_continuous_are
 // over v in [0.3, 60], |phi| < 1.4 to 3e-13 (tests/test_care_math.py runs THIS code, compiled for the host by
 // csrc/host_check.cu, against SciPy; tests/test_gpu_rollout.py checks the device instance).
+// high word of a double (sign, exponent, top 20 mantissa bits): magnitude and sign tests on the integer pipe
+__host__ __device__ __forceinline__ int hi_word(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2hiint(x);
+#else
+  long long b;
+  memcpy(&b, &x, sizeof(b));
+  return (int)(b >> 32);
+#endif
+}
+
 struct CareState { double C, S, al, dth, dal; };   // solution of the previous control step and its last change
 
 struct CareConst { double sq, q3, sr1, sr2, isr1, isr2; };
@@ -448,7 +468,8 @@ __host__ __device__ __forceinline__ bool care_gain(const CareConst& cc, double v
     care_update(C, S, al, dth, dal);                               // chord step
     // accept when the chord step is tiny AND the root is on the stabilising branch (S > 0, al > 0 there: kappa_2's
     // first component and K_13 are positive for every v, b1 > 0)
-    ok = fabs(dth) < 3e-8 && fabs(dal) < 3e-8 * fabs(al) && S > 0.0 && al > 0.0;
+    // (sign tests and the fixed threshold on the integer pipe: hi word of 3e-8 = 0x3E601B2B; S, al > 0 <=> sign bit clear, not zero)
+    ok = (hi_word(dth) & 0x7fffffff) < 0x3E601B2B && fabs(dal) < 3e-8 * fabs(al) && hi_word(S) > 0 && hi_word(al) > 0;
     if (!ok) {                                                     // corner of the reference, big jump: iterate from the
       C = C0; S = S0; al = al0;                                    // previous solution, not from the failed extrapolation
       ok = care_newton_loop(k, C, S, al, 40) && S > 0.0 && al > 0.0;
@@ -457,7 +478,7 @@ __host__ __device__ __forceinline__ bool care_gain(const CareConst& cc, double v
     // change over this control step (angle from the cross product of the unit vectors); only a small, smooth change
     // is worth extrapolating
     st.dth = fma(C0, S, -S0 * C); st.dal = al - al0;
-    if (!(fabs(st.dth) < 0.02 && fabs(st.dal) < 0.02 * al)) { st.dth = 0.0; st.dal = 0.0; }
+    if (!((hi_word(st.dth) & 0x7fffffff) < 0x3F947AE1 && fabs(st.dal) < 0.02 * al)) { st.dth = 0.0; st.dal = 0.0; }   // hi(0.02)
   }
   st.C = C; st.S = S; st.al = al;
   const double be = fma(k.k1, C, k.ba * al);

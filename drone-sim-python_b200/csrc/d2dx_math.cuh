@@ -176,8 +176,14 @@ __device__ __forceinline__ double exp_neg(double y) {
 // t = |y|/|x| never formed: (t-c)/(1+ct) = (|y| - c|x|)/(|x| + c|y|)).  x = y = 0 returns 0 like np.arctan2.
 __device__ __forceinline__ double atan2(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
-  // interval id from t = ay/ax without dividing: thresholds 7/16, 11/16, 19/16, 39/16
-  const bool g0 = 16.0 * ay >= 7.0 * ax, g1 = 16.0 * ay >= 11.0 * ax, g2 = 16.0 * ay >= 19.0 * ax, g3 = 16.0 * ay >= 39.0 * ax;
+  // interval id from a 20-bit estimate of t = ay/ax (MUFU seed x one multiply), compared on the HIGH WORD with integer
+  // instructions: thresholds 7/16, 11/16, 19/16, 39/16 have zero low words, and the reduction is valid on either side of a
+  // threshold, so an estimate that is off in the 20th bit only moves the switch point.  (Four DSETP + five DMUL on the fp64
+  // pipe before: the rollout kernel is bound by that pipe.)  ax = 0 or ay/ax overflowing gives inf / NaN -> last interval.
+  double rax;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rax) : "d"(ax));
+  const int qh = __double2hiint(ay * rax) & 0x7fffffff;
+  const bool g0 = qh >= 0x3FDC0000, g1 = qh >= 0x3FE60000, g2 = qh >= 0x3FF30000, g3 = qh >= 0x40038000;
   const double cc = g2 ? 1.5 : (g1 ? 1.0 : (g0 ? 0.5 : 0.0));
   double num = fma(-cc, ax, ay), den = fma(cc, ay, ax);
   if (g3) { num = -ax; den = ay; }
@@ -198,7 +204,9 @@ __device__ __forceinline__ double atan2(double y, double x) {
 // atan(v): the same reduction with x = 1 (thresholds are compile-time constants)
 __device__ __forceinline__ double atan(double v) {
   const double ay = fabs(v);
-  const bool g0 = ay >= 0.4375, g1 = ay >= 0.6875, g2 = ay >= 1.1875, g3 = ay >= 2.4375;
+  // the four thresholds have zero low words: comparing the high word is the exact comparison, on the integer pipe (NaN -> g3)
+  const int qh = __double2hiint(ay);
+  const bool g0 = qh >= 0x3FDC0000, g1 = qh >= 0x3FE60000, g2 = qh >= 0x3FF30000, g3 = qh >= 0x40038000;
   const double cc = g2 ? 1.5 : (g1 ? 1.0 : (g0 ? 0.5 : 0.0));
   double num = ay - cc, den = fma(cc, ay, 1.0);
   if (g3) { num = -1.0; den = ay; }

@@ -41,7 +41,8 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
 ia, ie, iss = h.index("Source"), h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
-ops, st, tot = collections.Counter(), collections.Counter(), 0
+ip = h.index("Predicated-On Thread Instructions Executed") if "Predicated-On Thread Instructions Executed" in h else None
+ops, st, thr, tot = collections.Counter(), collections.Counter(), collections.Counter(), 0
 for r in rows[2:]:
     if len(r) <= ie:
         continue
@@ -49,6 +50,12 @@ for r in rows[2:]:
     op = (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
     n = int(r[ie] or 0)
     ops[op] += n; st[op] += int(r[iss] or 0); tot += n
+    if ip is not None:
+        thr[op] += int(r[ip] or 0)
+if flop != flop and ip is not None:        # the per-opcode counters were not in this capture: same count from the SASS page
+    flop = thr["DADD"] + thr["DMUL"] + 2 * thr["DFMA"]
+    print(f"* executed fp64 flop from the source page (predicated-on thread instructions: DADD {thr['DADD']:.4g} + DMUL {thr['DMUL']:.4g} "
+          f"+ 2 x DFMA {thr['DFMA']:.4g}) = {flop:.4g} -> **{flop / units:.1f} flop per {unit_name}**, {flop / dur_s / 1e12:.2f} TFLOP/s under ncu")
 print(f"\n## SASS opcode mix (warp-level instructions executed; {tot / (units / 32):.0f} per warp per {unit_name})\n")
 print("| opcode | executed | share | stall samples |\n|---|---|---|---|")
 for op, n in ops.most_common(16):
