@@ -192,11 +192,12 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
                 "aircraft_nodes_per_launch": n_ac * N * n_prob, "sharding": f"by problem x{world}, no collective",
                 "roofline": {"bound": "hbm", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / dt / 1e9 / hbm_peak,
                              "algorithmic_bytes_per_launch": bytes_alg}}
-        if n_ac > 1:       # the pair terms make this launch fp64 / issue work as well: ~30 fp64 instructions (45 flop) per pair-node
-            pairs = n_ac * (n_ac - 1) // 2
-            flop = (45.0 * pairs + 230.0 * n_ac) * N * n_prob      # audited from the SASS of colloc_pairs_kernel
+        if n_ac > 1:       # the pair terms make this launch fp64 / issue work as well: executed fp64 flop from the ncu capture
+            flop = 557.0 * n_ac * N * n_prob                       # profiles/r2_colloc_c4_batch256_allpairs.md (16 aircraft, all pairs)
             line["roofline"]["fp64"] = {"achieved": flop / dt / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flop / dt / 1e12 / fp64_peak,
-                                        "flop_per_pair_node": 45.0, "flop_per_aircraft_node": 230.0}
+                                        "flop_per_aircraft_node": 557.0}
+            line["roofline"]["note"] = ("neither roof binds: 1064 warp instructions per warp and aircraft-node at 60 % of the issue slots, 32 resident "
+                                        "warps per SM (64 registers, 49 KB of shared memory per block) -- latency of the dependent fp64 chains")
         out[tag] = line
         del prob, free, bufs
     # (2) formation rollout, config C2 replicated, formations sharded over ranks (whole waves per GPU)
