@@ -248,6 +248,8 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
         tsB = max_over_ranks(_timed(repB, 50, warm=5))
         sync_all()
         st1, stB = sc1.check(), scB.check()
+        rep1(); torch.cuda.synchronize()
+        tl = sc1.peer.timeline()                            # rank 0's phase stamps of one more evaluation (ns since its kernel start)
         # parity: every rank's shard of the batch against rank 0's unsharded evaluation of the same problems
         full.evaluate_device(fdB, _lib.EVAL_ALL, bB)
         diffs = []
@@ -260,6 +262,7 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
         checks["sharded_c4_peer_timeouts"] = int(max_over_ranks(float(st1["timeouts"] + stB["timeouts"])))
         sharded_line = {"evals_per_s": 1.0 / ts1, "us_per_eval": ts1 * 1e6, "aircraft_per_gpu": n_ac // world, "one_gpu_us_per_eval": t1 * 1e6,
                         "how": "one kernel per rank and evaluation: positions and cost sums as peer-memory stores over NVLink, CUDA-graph replay",
+                        "timeline_ns_rank0": tl,
                         "roofline": {"bound": "launch + NVLink flag latency", "achieved": alg1 / ts1 / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": alg1 / ts1 / 1e9 / hbm_peak}}
         out["c4_single_sharded_by_aircraft"] = sharded_line
@@ -589,6 +592,28 @@ def main():
             core = {"error": f"{type(e).__name__}: {e}"}
             if world > 1:
                 raise
+    # ---- the host side of `e2e` at this N: every rank copies 1 GiB device -> pinned host at once (what the log copies of
+    # MonteCarloRollout.run do); whole-box GB/s = the ceiling of the end-to-end path ----
+    d2h_ceiling = None
+    if e2e is not None:
+        try:
+            nb = 1 << 30
+            dsrc = torch.empty(nb // 8, dtype=torch.float64, device=eng.device).normal_()
+            hdst = torch.empty(nb // 8, dtype=torch.float64).pin_memory()
+            best = 1e30
+            for _ in range(3):
+                barrier()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(); hdst.copy_(dsrc, non_blocking=True); c1.record(); c1.synchronize()
+                best = min(best, reduce_max(c0.elapsed_time(c1)))
+            d2h_ceiling = world * nb / (best * 1e-3) / 1e9
+            del dsrc, hdst
+            e2e["host_d2h_ceiling_gbs"] = d2h_ceiling
+            e2e["d2h_floor_ms"] = world * e2e["d2h_bytes_per_step"] / d2h_ceiling / 1e6
+            e2e["note"] = ("ms_per_step cannot fall below d2h_floor_ms = all ranks' log bytes / the box's measured concurrent D2H rate "
+                           "(host memory / PCIe root, one NUMA node): at 8 GPUs that floor exceeds the compute time")
+        except Exception as e:
+            e2e["host_d2h_ceiling_error"] = f"{type(e).__name__}: {e}"
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

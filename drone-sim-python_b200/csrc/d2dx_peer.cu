@@ -4,16 +4,21 @@
 // Every rank owns an exchange buffer (cudaMalloc) that all other ranks map (CUDA IPC between processes, plain pointers
 // inside one process).  One evaluation =
 //   phase 0  each block stores its tiles of the OWNED aircraft's x, y straight from free_local into every peer's position
-//            table, then (one fence, one flag per tile and peer) publishes them -- for ALL its tiles before anything else;
+//            table -- for ALL its tiles before anything else;
 //   phase 1  residual / Jacobian / input cost / gradient of psi, phi, v of the owned aircraft (needs no remote data: this is
 //            what hides the NVLink latency);
-//   phase 2  wait for the same tile of every peer, stage all positions in shared memory;
+//   phase 2  read the same tile of every peer from the own table (spinning until it has arrived), stage all positions in
+//            shared memory;
 //   phase 3  collision terms of the owned aircraft against every other aircraft, gradient of x, y;
-//   phase 4  the last block of a problem sums this rank's partials, writes them to every peer (fence + flag) and adds up
-//            the partials of all ranks in rank order: every rank ends with the same, deterministic total cost.
-// There is no collective call, no pack kernel and no host synchronisation; flags carry a monotonically increasing
-// evaluation number kept on the device, so the launch can be captured in a CUDA graph and replayed.  Phase 4 doubles as the
-// barrier that keeps evaluation e + 1 from overwriting tables a slower rank still reads in evaluation e.
+//   phase 4  the block of a problem's last tile sums this rank's per-tile partials, writes the four sums to every rank and
+//            adds up the sums of all ranks: every rank ends with the same, deterministic total cost.
+// The exchange carries its own arrival flags ("LL" protocol, as in NCCL's low-latency path): every double travels as two
+// 8-byte words {half of the bits, evaluation number}; an 8-byte store arrives whole, so a receiver that reads both
+// evaluation numbers it expects holds valid data -- no memory fence (MEMBAR.SYS cost ~4 us per use in the fence + flag
+// version, profiles/r2_sharded_c4.md), no separate flag, one NVLink traversal of latency.  Twice the bytes, of a 128 kB
+// exchange.  There is no collective call, no pack kernel and no host synchronisation; the evaluation number lives on the
+// device, so the launch can be captured in a CUDA graph and replayed.  Phase 4 doubles as the barrier that keeps
+// evaluation e + 1 from overwriting tables a slower rank still reads in evaluation e.
 // A peer that never answers costs `spin_cycles` per wait and is reported by d2dx_peer_status (never a hang).
 #include <string.h>
 
@@ -26,7 +31,7 @@ struct d2dx_peer {
   unsigned char* base[D2DX_PEER_MAX_WORLD];   // every rank's buffer as mapped here (base[rank] == local)
   bool ipc_opened[D2DX_PEER_MAX_WORLD];
   bool connected;
-  size_t bytes, off_tickets, off_posflag, off_costflag, off_cpart, off_lpart, off_pos;
+  size_t bytes, off_cpart, off_lpart, off_pos;
   int resident_blocks;
 };
 
@@ -34,30 +39,49 @@ namespace d2dx {
 
 constexpr int kPeerWarps = 8;
 
-struct PeerCtrl { uint32_t epoch, done_blocks, timeouts, pad; };
+struct PeerCtrl {
+  uint32_t epoch, done_blocks, timeouts, pad;
+  unsigned long long stamp[8];   // %globaltimer [ns] of the last evaluation, block 0 / the last block of problem 0:
+                                 // 0 start, 1 tiles published, 2 local work done, 3 peers' positions arrived, 4 pair terms done,
+                                 // 5 own cost sums sent, 6 all ranks' sums arrived (cost written), 7 block 0 leaves
+};
 
 struct PeerArgs {
   CollocArgs c;                  // c.p = the local shard as a problem of n_own aircraft; c.n_total, c.a_lo; outputs shard-local
   int world, rank, max_prob, ntiles;
   unsigned char* base[D2DX_PEER_MAX_WORLD];
-  size_t off_tickets, off_posflag, off_costflag, off_cpart, off_lpart, off_pos;
+  size_t off_cpart, off_lpart, off_pos;
   long long spin_cycles;
 };
 
-__device__ __forceinline__ void flag_store(uint32_t* p, uint32_t v) {      // publishes everything this thread has observed
-  __threadfence_system();
-  *reinterpret_cast<volatile uint32_t*>(p) = v;
+// LL words: {low 32 bits | evaluation number << 32}, {high 32 bits | evaluation number << 32}, stored and loaded as one
+// 16-byte access (each 8-byte half is delivered whole)
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, uint32_t epoch) {
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned long long e = static_cast<unsigned long long>(epoch) << 32;
+  const unsigned long long w0 = (bits & 0xffffffffull) | e, w1 = (bits >> 32) | e;
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" :: "l"(slot), "l"(w0), "l"(w1) : "memory");
 }
-
-// waits until *p has reached `epoch`; false on timeout
-__device__ __forceinline__ bool flag_wait(const uint32_t* p, uint32_t epoch, long long spin_cycles) {
-  const volatile uint32_t* vp = reinterpret_cast<const volatile uint32_t*>(p);
+// true when both halves carry `epoch`
+__device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, uint32_t epoch, double& v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  v = __longlong_as_double(static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32)));
+  return static_cast<uint32_t>(w0 >> 32) == epoch && static_cast<uint32_t>(w1 >> 32) == epoch;
+}
+// spins until the value of this evaluation has arrived; false on timeout (v then undefined)
+__device__ __forceinline__ bool ll_load(const unsigned long long* slot, uint32_t epoch, long long spin_cycles, double& v) {
+  if (ll_try_load(slot, epoch, v)) return true;
   const long long t0 = clock64();
-  while ((int32_t)(*vp - epoch) < 0) {
+  while (!ll_try_load(slot, epoch, v)) {
     if (clock64() - t0 > spin_cycles) return false;
   }
-  __threadfence_system();
   return true;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const __grid_constant__ PeerArgs g) {
@@ -71,20 +95,18 @@ __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const _
   unsigned char* mine = g.base[g.rank];
   PeerCtrl* ctrl = reinterpret_cast<PeerCtrl*>(mine);
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(&ctrl->epoch) + 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->stamp[0] = now_ns();
   const bool want_cg = (a.what & (D2DX_EVAL_COST | D2DX_EVAL_GRAD)) != 0;
   const bool use_col = want_cg && enabled(P.kcol) && n_total > 1;
   const bool use_obs = want_cg && enabled(P.kobs) && P.n_obs > 0;
   const int n_items = a.n_prob * g.ntiles;
-  int32_t* tickets = reinterpret_cast<int32_t*>(mine + g.off_tickets);
-  const uint32_t* posflag_in = reinterpret_cast<const uint32_t*>(mine + g.off_posflag);
-  const uint32_t* costflag_in = reinterpret_cast<const uint32_t*>(mine + g.off_costflag);
-  const double* pos_in = reinterpret_cast<const double*>(mine + g.off_pos);
-  const double* cpart_in = reinterpret_cast<const double*>(mine + g.off_cpart);
-  double* lpart = reinterpret_cast<double*>(mine + g.off_lpart);
+  const unsigned long long* pos_in = reinterpret_cast<const unsigned long long*>(mine + g.off_pos);
+  const unsigned long long* cpart_in = reinterpret_cast<const unsigned long long*>(mine + g.off_cpart);
+  unsigned long long* lpart = reinterpret_cast<unsigned long long*>(mine + g.off_lpart);
 
-  // ---- sweep A: publish the owned positions of EVERY tile this block will process, one fence, then the flags; by the time
-  // the block comes to a tile's collision terms the peers' stores for it have long landed (the NVLink latency of a batch
-  // is paid once, not per tile) ----
+  // ---- sweep A: publish the owned positions of EVERY tile this block will process before anything else: by the time the
+  // block comes to a tile's collision terms the peers' stores for it have long landed (the NVLink latency of a batch is
+  // paid once, not per tile) ----
   if (use_col && g.world > 1) {
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int prob = item / g.ntiles, tile = item - prob * g.ntiles;
@@ -93,27 +115,18 @@ __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const _
         const double* fr = a.free_ + (size_t)prob * a.n_free;
         for (int a_l = w; a_l < n_own; a_l += W) {
           const double x = fr[(3 * a_l) * N + i], y = fr[(3 * a_l + 1) * N + i];
-          const size_t o = (((size_t)prob * n_total + a.a_lo + a_l) * 2) * N + i;
+          const size_t o = ((((size_t)prob * n_total + a.a_lo + a_l) * 2) * N + i) * 2;      // two words per value
           for (int r = 0; r < g.world; ++r) {
             if (r == g.rank) continue;
-            double* dst = reinterpret_cast<double*>(g.base[r] + g.off_pos);
-            dst[o] = x; dst[o + N] = y;
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(g.base[r] + g.off_pos);
+            ll_store(dst + o, x, epoch); ll_store(dst + o + 2 * (size_t)N, y, epoch);
           }
         }
       }
     }
-    __syncthreads();
-    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    bool fenced = false;
-    for (int idx = threadIdx.x; idx < my_items * g.world; idx += blockDim.x) {
-      const int r = idx % g.world, item = blockIdx.x + (idx / g.world) * gridDim.x;
-      if (r == g.rank) continue;
-      if (!fenced) { __threadfence_system(); fenced = true; }
-      const int prob = item / g.ntiles, tile = item - prob * g.ntiles;
-      uint32_t* f = reinterpret_cast<uint32_t*>(g.base[r] + g.off_posflag);
-      *reinterpret_cast<volatile uint32_t*>(f + ((size_t)g.rank * g.max_prob + prob) * g.ntiles + tile) = epoch;
-    }
   }
+  const bool stamper = blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamper) ctrl->stamp[1] = now_ns();
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {   // same order on every rank: see the deadlock note in DESIGN
     const int prob = item / g.ntiles, tile = item - prob * g.ntiles;
@@ -140,24 +153,24 @@ __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const _
       }
     }
 
+    if (stamper && item == 0) ctrl->stamp[2] = now_ns();
     // ---- phase 2: the peers' positions of this tile ----
     if (use_col) {
-      if (threadIdx.x < g.world && threadIdx.x != g.rank) {
-        if (!flag_wait(posflag_in + ((size_t)threadIdx.x * g.max_prob + prob) * g.ntiles + tile, epoch, g.spin_cycles))
-          atomicAdd(&ctrl->timeouts, 1u);
-      }
-      __syncthreads();
+      bool arrived = true;
       for (int gl = w; gl < n_total; gl += W) {
         if (gl >= a.a_lo && gl < a.a_lo + n_own) continue;
         double x = 0.0, y = 0.0;
         if (valid) {
-          const size_t o = (((size_t)prob * n_total + gl) * 2) * N + i;
-          x = __ldcg(pos_in + o); y = __ldcg(pos_in + o + N);
+          const size_t o = ((((size_t)prob * n_total + gl) * 2) * N + i) * 2;
+          arrived = ll_load(pos_in + o, epoch, g.spin_cycles, x) && arrived;
+          arrived = ll_load(pos_in + o + 2 * (size_t)N, epoch, g.spin_cycles, y) && arrived;
         }
         spos[(gl * 2) * 32] = x; spos[(gl * 2 + 1) * 32] = y;
       }
+      if (!arrived) atomicAdd(&ctrl->timeouts, 1u);
       __syncthreads();
     }
+    if (stamper && item == 0) ctrl->stamp[3] = now_ns();
 
     // ---- phase 3: obstacle and collision terms of the owned aircraft, gradient of x, y ----
     if (want_cg && valid) {
@@ -188,6 +201,7 @@ __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const _
       }
     }
 
+    if (stamper && item == 0) ctrl->stamp[4] = now_ns();
     // instance constraints of the owned aircraft: first tile of each problem
     if (tile == 0) {
       for (int k = threadIdx.x; k < P.n_inst; k += blockDim.x) {
@@ -204,42 +218,49 @@ __global__ void __launch_bounds__(kPeerWarps * 32, 3) colloc_peer_kernel(const _
     if (w == 0) {
       double b4[4] = {0.0, 0.0, 0.0, 0.0};
       for (int q = 0; q < W; ++q) { b4[0] += sred[q * 4]; b4[1] += sred[q * 4 + 1]; b4[2] += sred[q * 4 + 2]; b4[3] += sred[q * 4 + 3]; }
-      double* parts = lpart + (size_t)prob * g.ntiles * 4;
-      if (lane == 0) { parts[tile * 4] = b4[0]; parts[tile * 4 + 1] = b4[1]; parts[tile * 4 + 2] = b4[2]; parts[tile * 4 + 3] = b4[3]; }
-      int last = 0;
-      if (lane == 0) {
-        __threadfence();
-        last = atomicAdd(&tickets[prob], 1) == g.ntiles - 1;
-      }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        __threadfence();
+      // the block's four sums go to its LOCAL slot, again as self-validating words: the block of the problem's LAST tile
+      // (every other tile of the problem has a lower item index: in progress or done, on any rank) collects them without
+      // atomics or fences, in a fixed order
+      unsigned long long* parts = lpart + ((size_t)prob * g.ntiles * 4) * 2;
+      if (lane < 4) ll_store(parts + (tile * 4 + lane) * 2, lane == 0 ? b4[0] : (lane == 1 ? b4[1] : (lane == 2 ? b4[2] : b4[3])), epoch);
+      if (tile == g.ntiles - 1) {
         double t4[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int t = lane; t < g.ntiles; t += 32)
-          for (int k = 0; k < 4; ++k) t4[k] += __ldcg(parts + t * 4 + k);
+        bool arrived = true;
+        for (int t = lane; t < g.ntiles; t += 32) {
+          double v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) arrived = ll_load(parts + (t * 4 + k) * 2, epoch, g.spin_cycles, v[k]) && arrived;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t4[k] += v[k];
+        }
+#pragma unroll
         for (int k = 0; k < 4; ++k) t4[k] = warp_sum(t4[k]);
-        if (lane == 0) tickets[prob] = 0;
-        if (lane < g.world) {                      // lane r: this rank's four sums -> rank r, then the flag
-          double* cp = reinterpret_cast<double*>(g.base[lane] + g.off_cpart) + ((size_t)g.rank * g.max_prob + prob) * 4;
-          cp[0] = t4[0]; cp[1] = t4[1]; cp[2] = t4[2]; cp[3] = t4[3];
-          flag_store(reinterpret_cast<uint32_t*>(g.base[lane] + g.off_costflag) + (size_t)g.rank * g.max_prob + prob, epoch);
-          if (!flag_wait(costflag_in + (size_t)lane * g.max_prob + prob, epoch, g.spin_cycles)) atomicAdd(&ctrl->timeouts, 1u);
+        // this rank's four sums -> every rank (lane k sends sum k; own buffer included), then lane r collects rank r's
+        if (lane < 4) {
+          const double mine_k = lane == 0 ? t4[0] : (lane == 1 ? t4[1] : (lane == 2 ? t4[2] : t4[3]));
+          for (int r = 0; r < g.world; ++r)
+            ll_store(reinterpret_cast<unsigned long long*>(g.base[r] + g.off_cpart) + (((size_t)g.rank * g.max_prob + prob) * 4 + lane) * 2, mine_k, epoch);
         }
-        __syncwarp();
-        if (lane == 0 && (a.what & D2DX_EVAL_COST)) {
-          double s4[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int r = 0; r < g.world; ++r) {
-            const double* cp = cpart_in + ((size_t)r * g.max_prob + prob) * 4;
-            for (int k = 0; k < 4; ++k) s4[k] += __ldcg(cp + k);
-          }
-          a.cost[prob] = colloc_cost_from_sums(a, s4, use_obs, use_col);
+        if (lane == 0 && prob == 0) ctrl->stamp[5] = now_ns();
+        double r4[4] = {0.0, 0.0, 0.0, 0.0};
+        if (lane < g.world) {
+          const unsigned long long* cp = cpart_in + (((size_t)lane * g.max_prob + prob) * 4) * 2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) arrived = ll_load(cp + 2 * k, epoch, g.spin_cycles, r4[k]) && arrived;
         }
+        if (!arrived) atomicAdd(&ctrl->timeouts, 1u);
+        double s4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s4[k] = warp_sum(r4[k]);     // the same lanes hold the same values on every rank: identical totals
+        if (lane == 0 && (a.what & D2DX_EVAL_COST)) a.cost[prob] = colloc_cost_from_sums(a, s4, use_obs, use_col);
+        if (lane == 0 && prob == 0) ctrl->stamp[6] = now_ns();
       }
     }
   }
 
   // the last block to leave advances the evaluation number (all blocks read it long ago)
   __syncthreads();
+  if (stamper) ctrl->stamp[7] = now_ns();
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(&ctrl->done_blocks, 1u) == gridDim.x - 1) {
@@ -271,12 +292,9 @@ int d2dx_peer_create(d2dx_handle* h, int32_t world, int32_t rank, int32_t max_pr
   p->device = h->device; p->world = world; p->rank = rank; p->max_prob = max_prob; p->n_total = n_ac_total; p->N = N;
   p->ntiles = (N + 31) / 32;
   size_t o = align_up(sizeof(PeerCtrl), 256);
-  p->off_tickets = o; o = align_up(o + sizeof(int32_t) * max_prob, 256);
-  p->off_posflag = o; o = align_up(o + sizeof(uint32_t) * (size_t)world * max_prob * p->ntiles, 256);
-  p->off_costflag = o; o = align_up(o + sizeof(uint32_t) * (size_t)world * max_prob, 256);
-  p->off_cpart = o; o = align_up(o + sizeof(double) * (size_t)world * max_prob * 4, 256);
-  p->off_lpart = o; o = align_up(o + sizeof(double) * (size_t)max_prob * p->ntiles * 4, 256);
-  p->off_pos = o; o = align_up(o + sizeof(double) * (size_t)max_prob * n_ac_total * 2 * N, 256);
+  p->off_cpart = o; o = align_up(o + 2 * sizeof(double) * (size_t)world * max_prob * 4, 256);        // LL: two words per value
+  p->off_lpart = o; o = align_up(o + 2 * sizeof(double) * (size_t)max_prob * p->ntiles * 4, 256);
+  p->off_pos = o; o = align_up(o + 2 * sizeof(double) * (size_t)max_prob * n_ac_total * 2 * N, 256);  // LL: two words per value
   p->bytes = o;
   void* buf = nullptr;
   cudaError_t e = cudaMalloc(&buf, p->bytes);
@@ -349,6 +367,15 @@ int d2dx_peer_status(d2dx_peer* p, int32_t* status_host4) {
   return D2DX_OK;
 }
 
+int d2dx_peer_timeline(d2dx_peer* p, uint64_t* stamps_host8) {
+  D2DX_CHECK_ARG(p && stamps_host8, "d2dx_peer_timeline: null argument");
+  D2DX_CUDA(cudaSetDevice(p->device));
+  PeerCtrl c;
+  D2DX_CUDA(cudaMemcpy(&c, p->local, sizeof(c), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; ++k) stamps_host8[k] = c.stamp[k];
+  return D2DX_OK;
+}
+
 int d2dx_peer_destroy(d2dx_peer* p) {
   if (!p) return D2DX_OK;
   cudaSetDevice(p->device);
@@ -384,15 +411,17 @@ int d2dx_colloc_eval_peer(d2dx_handle* h, d2dx_peer* peer, const d2dx_colloc_pro
   colloc_constants(a);
   g.world = peer->world; g.rank = peer->rank; g.max_prob = peer->max_prob; g.ntiles = peer->ntiles;
   for (int r = 0; r < peer->world; ++r) g.base[r] = peer->base[r];
-  g.off_tickets = peer->off_tickets; g.off_posflag = peer->off_posflag; g.off_costflag = peer->off_costflag;
   g.off_cpart = peer->off_cpart; g.off_lpart = peer->off_lpart; g.off_pos = peer->off_pos;
   g.spin_cycles = 2000000000LL;                  // ~1 s at 1.9 GHz
   D2DX_CUDA(cudaSetDevice(h->device));
   const size_t smem = ((size_t)peer->n_total * 64 + kPeerWarps * 4) * sizeof(double);
   if (smem > 48 * 1024) D2DX_CUDA(cudaFuncSetAttribute(colloc_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = n_prob * peer->ntiles;
-  const int grid = items < peer->resident_blocks ? items : peer->resident_blocks;
   const int warps = p->n_ac < kPeerWarps ? p->n_ac : kPeerWarps;
+  int nb = 0;                                    // co-resident blocks of THIS launch shape: every waiting block must be resident
+  D2DX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, colloc_peer_kernel, warps * 32, smem));
+  const int resident = (nb > 0 ? nb : 1) * h->sm_count;
+  const int grid = items < resident ? items : resident;
   colloc_peer_kernel<<<grid, warps * 32, smem, as_stream(stream)>>>(g);
   D2DX_LAUNCH_CHECK("colloc_peer_kernel");
   return D2DX_OK;

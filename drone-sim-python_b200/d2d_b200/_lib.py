@@ -141,6 +141,7 @@ def _load():
         "d2dx_peer_connect_ipc": (C.c_int, [H, C.c_char_p]),
         "d2dx_peer_connect_local": (C.c_int, [H, P(H)]),
         "d2dx_peer_status": (C.c_int, [H, P(i32)]),
+        "d2dx_peer_timeline": (C.c_int, [H, P(C.c_uint64)]),
         "d2dx_peer_destroy": (C.c_int, [H]),
         "d2dx_colloc_eval_peer": (C.c_int, [H, H, P(CollocProblem), i32, i32, c_dp, u32, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_shoot_forward": (C.c_int, [H, P(CollocProblem), i32, c_dp, P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),

@@ -405,6 +405,13 @@ class PeerExchange:
         check(lib.d2dx_peer_status(self.p, s), "d2dx_peer_status")
         return {"timeouts": s[0], "evaluations": s[1], "resident_blocks": s[2], "buffer_kib": s[3]}
 
+    def timeline(self):
+        """ns since kernel start of the last evaluation's phases on this rank (d2dx_peer_timeline)"""
+        s = (C.c_uint64 * 8)()
+        check(lib.d2dx_peer_timeline(self.p, s), "d2dx_peer_timeline")
+        names = ("published", "local_done", "positions_arrived", "pairs_done", "cost_sent", "cost_arrived", "block0_leaves")
+        return {n: (int(s[k + 1]) - int(s[0])) if s[k + 1] else None for k, n in enumerate(names)}
+
     def close(self):
         if getattr(self, "p", None):
             lib.d2dx_peer_destroy(self.p)

@@ -327,9 +327,10 @@ int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const do
 /* -------- aircraft-sharded evaluation over NVLink peer memory: ONE kernel per rank, no collective call --------
  * The exchange step the north star names ("all-gather aircraft positions for the cross-shard avoidance terms, reduce
  * costs") done by the evaluation kernel itself: each rank stores its aircraft's x, y straight from free_local into every
- * peer's position table (peer memory), computes everything local while the stores travel, waits on per-tile flags, adds
- * the collision terms, and the last block of a problem exchanges the four cost sums the same way, so that every rank
- * ends with the identical total cost[n_prob].  Replaces d2dx_colloc_pack_positions + all-gather + d2dx_colloc_eval_shard
+ * peer's position table (peer memory), computes everything local while the stores travel, reads the peers' tiles from its
+ * own table (every value travels with the evaluation number in the same 8-byte words, so arrival needs neither a fence nor
+ * a flag), adds the collision terms, and the block of a problem's last tile exchanges the four cost sums the same way, so
+ * that every rank ends with the identical total cost[n_prob].  Replaces d2dx_colloc_pack_positions + all-gather + d2dx_colloc_eval_shard
  * + all-reduce for the callbacks of 07_multioptyplan.py:69-78 when one problem is spread over the GPUs of a box.
  *
  * d2dx_peer_create allocates this rank's exchange buffer (the only allocation; capacity: max_prob problems of n_ac_total
@@ -348,6 +349,10 @@ int d2dx_peer_ipc_handle(d2dx_peer* p, void* handle_host64);
 int d2dx_peer_connect_ipc(d2dx_peer* p, const void* handles_host /* [world][64], rank order */);
 int d2dx_peer_connect_local(d2dx_peer* p, d2dx_peer* const* peers_host /* [world], rank order */);
 int d2dx_peer_status(d2dx_peer* p, int32_t* status_host4);
+/* %globaltimer stamps [ns] of the last evaluation on this rank (block 0 and the block that finished problem 0): 0 kernel
+ * start, 1 tiles published, 2 local work done, 3 peers' positions arrived, 4 pair terms done, 5 own cost sums sent,
+ * 6 every rank's sums arrived, 7 block 0 leaves -- where the latency of a sharded evaluation goes */
+int d2dx_peer_timeline(d2dx_peer* p, uint64_t* stamps_host8);
 int d2dx_peer_destroy(d2dx_peer* p);
 /* p_local_host / free_local / residual / jac (compact) / grad as in d2dx_colloc_eval_shard, for n_prob problems stacked on
  * a leading axis; cost[n_prob] receives the TOTAL cost of each problem (all ranks' shares, summed in rank order). */
