@@ -235,7 +235,7 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
                                  "roofline": {"bound": "launch latency", "achieved": alg1 / t1 / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg1 / t1 / 1e9 / hbm_peak}}
     out["c4_batch64_allpairs_one_gpu"] = {"evals_per_s": PB / tB, "us_per_launch": tB * 1e6}
     if world > 1 and n_ac % world == 0:
-        from d2d_b200.distributed import ShardedCollocation
+        from d2d_b200.distributed import ShardedCollocation, shard_range
         sc1 = ShardedCollocation(n_ac, N, h, (0., 0.), inst, _c4_cost(), engine=eng, max_prob=1)
         scB = ShardedCollocation(n_ac, N, h, (0., 0.), inst, _c4_cost(), engine=eng, max_prob=PB)
         fl1 = eng.to_device(free_all[0, sc1.shard.idx_free].copy())
@@ -266,11 +266,23 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
                         "roofline": {"bound": "launch + NVLink flag latency", "achieved": alg1 / ts1 / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": alg1 / ts1 / 1e9 / hbm_peak}}
         out["c4_single_sharded_by_aircraft"] = sharded_line
+        # the same 64 problems sharded by PROBLEM instead (PB / world each, no exchange at all): how a batch should be split
+        lo, hi = shard_range(PB, world, rank)
+        fdP = eng.to_device(free_all[lo:hi].copy())
+        bP = full.buffers(hi - lo)
+        sync_all()
+        tP = max_over_ranks(_timed(lambda: full.evaluate_device(fdP, _lib.EVAL_ALL, bP), 50))
+        out["c4_batch64_sharded_by_problem"] = {"evals_per_s": PB / tP, "us_per_launch": tP * 1e6, "one_gpu_us_per_launch": tB * 1e6,
+                                                "speedup_vs_one_gpu": tB / tP, "problems_per_gpu": hi - lo}
         out["c4_batch64_sharded_by_aircraft"] = {"evals_per_s": PB / tsB, "us_per_launch": tsB * 1e6, "one_gpu_us_per_launch": tB * 1e6,
                                                  "speedup_vs_one_gpu": tB / tsB,
+                                                 "exchange_bytes_in_per_gpu": 2 * 16.0 * (n_ac - n_ac // world) * N * PB,
                                                  "roofline": {"bound": "hbm", "achieved": alg1 * PB / world / tsB / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                                               "frac": alg1 * PB / world / tsB / 1e9 / hbm_peak,
-                                                              "note": "per-GPU algorithmic bytes (1/world of each problem) over the launch time"}}
+                                                              "note": "per-GPU algorithmic bytes (1/world of each problem) over the launch time; every rank "
+                                                                      "receives the positions of all other aircraft of all problems (exchange_bytes_in_per_gpu, "
+                                                                      "self-validating 16-byte words): a batch is better split by problem, aircraft "
+                                                                      "sharding is for the latency of ONE problem"}}
         del sc1, scB
     return out, checks
 

@@ -185,6 +185,7 @@ using namespace d2dx;
 extern "C" {
 
 int d2dx_math_probe(d2dx_handle* h, int32_t n, const double* x, const double* y, double* out, void* stream) {
+  D2DX_NVTX("d2dx_math_probe");
   D2DX_CHECK_ARG(h && n > 0 && x && y && out, "d2dx_math_probe: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   math_probe_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, x, y, out);
@@ -193,6 +194,7 @@ int d2dx_math_probe(d2dx_handle* h, int32_t n, const double* x, const double* y,
 }
 
 int d2dx_dfma_burn(d2dx_handle* h, int32_t blocks, int32_t threads, int32_t iters, double* sink, void* stream) {
+  D2DX_NVTX("d2dx_dfma_burn");
   D2DX_CHECK_ARG(h && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && sink, "d2dx_dfma_burn: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   dfma_burn_kernel<<<blocks, threads, 0, as_stream(stream)>>>(iters, sink);
@@ -253,6 +255,7 @@ static int check_table(const d2dx_traj_table* tt, const char* who) {
 }
 
 int d2dx_traj_eval(d2dx_handle* h, const d2dx_traj_table* tt, int32_t nT, const double* time, double* Y, void* stream) {
+  D2DX_NVTX("d2dx_traj_eval");
   D2DX_CHECK_ARG(h && time && Y && nT > 0, "d2dx_traj_eval: bad argument");
   if (int rc = check_table(tt, "d2dx_traj_eval")) return rc;
   D2DX_CUDA(cudaSetDevice(h->device));
@@ -262,6 +265,7 @@ int d2dx_traj_eval(d2dx_handle* h, const d2dx_traj_table* tt, int32_t nT, const 
 }
 
 int d2dx_norm_mpi_pi(d2dx_handle* h, int32_t n, const double* v, double* out, void* stream) {
+  D2DX_NVTX("d2dx_norm_mpi_pi");
   D2DX_CHECK_ARG(h && n > 0 && v && out, "d2dx_norm_mpi_pi: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   norm_mpi_pi_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, v, out);
@@ -271,6 +275,7 @@ int d2dx_norm_mpi_pi(d2dx_handle* h, int32_t n, const double* v, double* out, vo
 
 int d2dx_cont_dyn(d2dx_handle* h, int32_t n, const double* X, const double* U, const double* W, const double* ac,
                   double* Xdot, void* stream) {
+  D2DX_NVTX("d2dx_cont_dyn");
   D2DX_CHECK_ARG(h && n > 0 && X && U && W && ac && Xdot, "d2dx_cont_dyn: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   cont_dyn_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, X, U, W, ac, Xdot);
@@ -280,6 +285,7 @@ int d2dx_cont_dyn(d2dx_handle* h, int32_t n, const double* X, const double* U, c
 
 int d2dx_disc_dyn(d2dx_handle* h, int32_t n, const double* X, const double* U, const double* W, const double* ac,
                   double dt, int32_t nsub, double* Xnext, void* stream) {
+  D2DX_NVTX("d2dx_disc_dyn");
   D2DX_CHECK_ARG(h && n > 0 && X && U && W && ac && Xnext && nsub >= 1, "d2dx_disc_dyn: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   disc_dyn_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, X, U, W, ac, dt, nsub, Xnext);
@@ -288,6 +294,7 @@ int d2dx_disc_dyn(d2dx_handle* h, int32_t n, const double* X, const double* U, c
 }
 
 int d2dx_cont_jac(d2dx_handle* h, int32_t n, const double* Xr, const double* ac, double* A, double* Bm, void* stream) {
+  D2DX_NVTX("d2dx_cont_jac");
   D2DX_CHECK_ARG(h && n > 0 && Xr && ac && A && Bm, "d2dx_cont_jac: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   cont_jac_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, Xr, ac, A, Bm);
@@ -297,6 +304,7 @@ int d2dx_cont_jac(d2dx_handle* h, int32_t n, const double* Xr, const double* ac,
 
 int d2dx_flatness(d2dx_handle* h, int32_t n, const double* Ys, const double* W, const double* ac, double* Xr, double* Ur,
                   double* Xrdot, void* stream) {
+  D2DX_NVTX("d2dx_flatness");
   D2DX_CHECK_ARG(h && n > 0 && Ys && W && ac && Xr && Ur, "d2dx_flatness: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   flatness_kernel<<<grid_for(n), kThreads, 0, as_stream(stream)>>>(n, Ys, W, ac, Xr, Ur, Xrdot);
@@ -307,6 +315,7 @@ int d2dx_flatness(d2dx_handle* h, int32_t n, const double* Ys, const double* W, 
 int d2dx_dfff_control(d2dx_handle* h, const d2dx_traj_table* tt, const double* X, double t, const double* W,
                       const double* ac, const d2dx_dfff_gains* gains_host, double* U, double* Xr, double* K,
                       double* care_state, void* stream) {
+  D2DX_NVTX("d2dx_dfff_control");
   D2DX_CHECK_ARG(h && X && W && ac && U, "d2dx_dfff_control: bad argument");
   if (int rc = check_table(tt, "d2dx_dfff_control")) return rc;
   d2dx_dfff_gains g;

@@ -476,6 +476,7 @@ int64_t d2dx_colloc_scratch_size(const d2dx_colloc_problem* p, int32_t n_prob) {
 }
 
 int d2dx_colloc_structure(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t layout, int64_t* rows, int64_t* cols, void* stream) {
+  D2DX_NVTX("d2dx_colloc_structure");
   if (int rc = check_problem(p, "d2dx_colloc_structure")) return rc;
   D2DX_CHECK_ARG(h && rows && cols, "d2dx_colloc_structure: null argument");
   int64_t s3[3];
@@ -489,6 +490,7 @@ int d2dx_colloc_structure(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t 
 }
 
 int d2dx_colloc_init_dense(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t n_prob, double* jac, void* stream) {
+  D2DX_NVTX("d2dx_colloc_init_dense");
   if (int rc = check_problem(p, "d2dx_colloc_init_dense")) return rc;
   D2DX_CHECK_ARG(h && jac && n_prob >= 1, "d2dx_colloc_init_dense: bad argument");
   int64_t s3[3];
@@ -501,6 +503,7 @@ int d2dx_colloc_init_dense(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t
 
 int d2dx_colloc_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t n_prob, const double* free_, int32_t layout,
                      uint32_t what, double* residual, double* jac, double* cost, double* grad, double* scratch, void* stream) {
+  D2DX_NVTX("d2dx_colloc_eval");
   return launch_eval(h, p, n_prob, p ? p->n_ac : 0, 0, free_, nullptr, layout, what, residual, jac, cost, grad, scratch, stream,
                      "d2dx_colloc_eval");
 }
@@ -508,6 +511,7 @@ int d2dx_colloc_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t n_pro
 int d2dx_colloc_eval_shard(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t n_ac_total, int32_t a_lo,
                            const double* free_local, const double* pos_all, uint32_t what, double* residual, double* jac,
                            double* cost, double* grad, double* scratch, void* stream) {
+  D2DX_NVTX("d2dx_colloc_eval_shard");
   D2DX_CHECK_ARG(p && pos_all && n_ac_total >= p->n_ac && a_lo >= 0 && a_lo + p->n_ac <= n_ac_total,
                  "d2dx_colloc_eval_shard: shard [%d,+%d) of %d", a_lo, p ? p->n_ac : -1, n_ac_total);
   return launch_eval(h, p, 1, n_ac_total, a_lo, free_local, pos_all, D2DX_JAC_COMPACT, what, residual, jac, cost, grad, scratch,
@@ -516,6 +520,7 @@ int d2dx_colloc_eval_shard(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t
 
 int d2dx_cost_bank_max(d2dx_handle* h, int32_t n_prob, int32_t n_free, int32_t off_phi, int32_t N, double obj_scale, const double* free_,
                        double* cost, double* grad, void* stream) {
+  D2DX_NVTX("d2dx_cost_bank_max");
   D2DX_CHECK_ARG(h && free_ && (cost || grad), "d2dx_cost_bank_max: null argument");
   D2DX_CHECK_ARG(n_prob >= 1 && N >= 1 && off_phi >= 0 && off_phi + N <= n_free, "d2dx_cost_bank_max: n_prob=%d off_phi=%d N=%d n_free=%d", n_prob,
                  off_phi, N, n_free);
@@ -526,6 +531,7 @@ int d2dx_cost_bank_max(d2dx_handle* h, int32_t n_prob, int32_t n_free, int32_t o
 }
 
 int d2dx_colloc_pack_positions(d2dx_handle* h, int32_t n_ac, int32_t N, const double* free_local, double* pos, void* stream) {
+  D2DX_NVTX("d2dx_colloc_pack_positions");
   D2DX_CHECK_ARG(h && n_ac >= 1 && N >= 1 && free_local && pos, "d2dx_colloc_pack_positions: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   const long total = (long)n_ac * 2 * N;

@@ -173,6 +173,7 @@ using namespace d2dx;
 
 extern "C" int d2dx_rollout_formation(d2dx_handle* h, const d2dx_formations* f, double dt, int32_t i_begin, int32_t i_end,
                                       int32_t nsub, const d2dx_formation_out* out, void* stream) {
+  D2DX_NVTX("d2dx_rollout_formation");
   D2DX_CHECK_ARG(h && f && out, "d2dx_rollout_formation: null argument");
   D2DX_CHECK_ARG(f->F > 0 && f->n_ac >= 1 && f->n_ac <= kMaxAc && f->n_e >= 0 && f->n_e <= kMaxAc,
                  "d2dx_rollout_formation: F=%d n_ac=%d n_e=%d (n_ac, n_e <= %d)", f->F, f->n_ac, f->n_e, kMaxAc);
@@ -197,6 +198,7 @@ extern "C" int d2dx_rollout_formation(d2dx_handle* h, const d2dx_formations* f, 
 extern "C" int d2dx_dcf(d2dx_handle* h, int32_t F, int32_t n_ac, int32_t n_e, const double* Binc_host,
                         const double* z_des_host, double kr, const double* p, const double* c, double* Ur,
                         double* e_deg, void* stream) {
+  D2DX_NVTX("d2dx_dcf");
   D2DX_CHECK_ARG(h && F > 0 && n_ac >= 1 && n_ac <= kMaxAc && n_e >= 0 && n_e <= kMaxAc, "d2dx_dcf: bad sizes F=%d n_ac=%d n_e=%d", F, n_ac, n_e);
   D2DX_CHECK_ARG(p && c && Ur && e_deg && Binc_host && z_des_host, "d2dx_dcf: null array");
   DcfArgs a;
@@ -212,6 +214,7 @@ extern "C" int d2dx_dcf(d2dx_handle* h, int32_t F, int32_t n_ac, int32_t n_e, co
 
 extern "C" int d2dx_circle_implicit(d2dx_handle* h, int32_t n, const double* X, const double* c, const double* r, double* out,
                                     void* stream) {
+  D2DX_NVTX("d2dx_circle_implicit");
   D2DX_CHECK_ARG(h && n > 0 && X && c && r && out, "d2dx_circle_implicit: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   circle_implicit_kernel<<<(n + kFormThreads - 1) / kFormThreads, kFormThreads, 0, as_stream(stream)>>>(n, X, c, r, out);
@@ -221,6 +224,7 @@ extern "C" int d2dx_circle_implicit(d2dx_handle* h, int32_t n, const double* X, 
 
 extern "C" int d2dx_gvf(d2dx_handle* h, int32_t n, const double* X, const double* c, const double* r, double ke, double kd,
                         double* out, void* stream) {
+  D2DX_NVTX("d2dx_gvf");
   D2DX_CHECK_ARG(h && n > 0 && X && c && r && out, "d2dx_gvf: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   gvf_kernel<<<(n + kFormThreads - 1) / kFormThreads, kFormThreads, 0, as_stream(stream)>>>(n, X, c, r, ke, kd, out);

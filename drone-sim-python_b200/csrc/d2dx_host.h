@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/d2dx.h"
 
 struct d2dx_handle {
@@ -15,6 +17,16 @@ namespace d2dx {
 int set_error(int code, const char* fmt, ...);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 }  // namespace d2dx
+
+// NVTX range around every launching ABI entry: shows up under nsys / ncu --nvtx as the C-ABI call that enqueued the
+// kernels; header-only NVTX v3 is a no-op unless a profiler injects itself
+namespace d2dx {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace d2dx
+#define D2DX_NVTX(name) d2dx::NvtxRange d2dx_nvtx_range_(name)
 
 #define D2DX_CHECK_ARG(cond, ...) \
   do { if (!(cond)) return d2dx::set_error(D2DX_EINVAL, __VA_ARGS__); } while (0)

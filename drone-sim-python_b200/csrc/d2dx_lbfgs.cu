@@ -353,6 +353,7 @@ extern "C" int d2dx_lbfgs_layout(int32_t P, int32_t n, int32_t n_con, const d2dx
 
 extern "C" int d2dx_lbfgs_init(d2dx_handle* h, int32_t P, int32_t n, int32_t n_con, const d2dx_lbfgs_options* o, double* state,
                                double* lam, double* rho, void* stream) {
+  D2DX_NVTX("d2dx_lbfgs_init");
   if (int rc = lb_check(P, n, n_con, o, "d2dx_lbfgs_init")) return rc;
   D2DX_CHECK_ARG(h && state && rho && (lam || n_con == 0), "d2dx_lbfgs_init: null array");
   const LbLayout L = lb_layout(P, n, n_con, o->m, o->window);
@@ -368,6 +369,7 @@ extern "C" int d2dx_lbfgs_init(d2dx_handle* h, int32_t P, int32_t n, int32_t n_c
 extern "C" int d2dx_al_lbfgs_tick(d2dx_handle* h, int32_t P, int32_t n, int32_t n_con, const d2dx_lbfgs_options* o, double* state,
                                   double* x_trial, const double* f_parts, const double* cost_parts, int32_t n_parts, const double* grad,
                                   const double* c, double* lam, double* rho, int32_t* n_running, void* stream) {
+  D2DX_NVTX("d2dx_al_lbfgs_tick");
   if (int rc = lb_check(P, n, n_con, o, "d2dx_al_lbfgs_tick")) return rc;
   D2DX_CHECK_ARG(h && state && x_trial && f_parts && grad && rho && n_running && n_parts >= 1 && (n_con == 0 || (c && lam)),
                  "d2dx_al_lbfgs_tick: null array or n_parts=%d", n_parts);

@@ -389,6 +389,7 @@ int d2dx_peer_destroy(d2dx_peer* p) {
 int d2dx_colloc_eval_peer(d2dx_handle* h, d2dx_peer* peer, const d2dx_colloc_problem* p, int32_t n_prob, int32_t a_lo,
                           const double* free_local, uint32_t what, double* residual, double* jac, double* cost, double* grad,
                           void* stream) {
+  D2DX_NVTX("d2dx_colloc_eval_peer");
   D2DX_CHECK_ARG(h && peer && p && free_local, "d2dx_colloc_eval_peer: null argument");
   D2DX_CHECK_ARG(peer->connected, "d2dx_colloc_eval_peer: the exchange is not connected (d2dx_peer_connect_ipc / _local)");
   D2DX_CHECK_ARG(p->N == peer->N && n_prob >= 1 && n_prob <= peer->max_prob, "d2dx_colloc_eval_peer: N=%d (exchange %d), n_prob=%d (max %d)", p->N,

@@ -113,6 +113,7 @@ using namespace d2dx;
 
 extern "C" int d2dx_pursuit_control(d2dx_handle* h, const d2dx_pursuit* p, int32_t B, const double* X, double* U, int32_t* idx_closest,
                                     void* stream) {
+  D2DX_NVTX("d2dx_pursuit_control");
   if (int rc = pp_check(p, "d2dx_pursuit_control")) return rc;
   D2DX_CHECK_ARG(h && B >= 1 && X && U, "d2dx_pursuit_control: bad argument");
   PursuitArgs a = {};
@@ -126,6 +127,7 @@ extern "C" int d2dx_pursuit_control(d2dx_handle* h, const d2dx_pursuit* p, int32
 extern "C" int d2dx_rollout_pursuit(d2dx_handle* h, const d2dx_pursuit* p, int32_t B, const double* X0, const double* wind, const double* ac,
                                     double dt, int32_t i_begin, int32_t i_end, int32_t nsub, double* X_log, double* U_log,
                                     int32_t* idx_log, double* X_final, void* stream) {
+  D2DX_NVTX("d2dx_rollout_pursuit");
   if (int rc = pp_check(p, "d2dx_rollout_pursuit")) return rc;
   D2DX_CHECK_ARG(h && B >= 1 && X0 && wind && ac && dt > 0 && nsub >= 1 && i_begin >= 0 && i_end >= i_begin,
                  "d2dx_rollout_pursuit: B=%d dt=%g nsub=%d steps [%d, %d)", B, dt, nsub, i_begin, i_end);

@@ -219,6 +219,7 @@ using namespace d2dx;
 extern "C" int d2dx_rollout_dfff(d2dx_handle* h, const d2dx_scenarios* s, const double* time, int32_t i_begin,
                                  int32_t i_end, int32_t nsub, int32_t final_control,
                                  const d2dx_dfff_gains* gains_host, const d2dx_rollout_out* out, void* stream) {
+  D2DX_NVTX("d2dx_rollout_dfff");
   D2DX_CHECK_ARG(h && s && time && out, "d2dx_rollout_dfff: null argument");
   D2DX_CHECK_ARG(s->B > 0 && s->traj.n_traj == s->B, "d2dx_rollout_dfff: B=%d, traj.n_traj=%d", s->B, s->traj.n_traj);
   D2DX_CHECK_ARG(s->X0 && s->wind && s->ac && out->X_final, "d2dx_rollout_dfff: X0, wind, ac, X_final are required");

@@ -276,6 +276,7 @@ using namespace d2dx;
 
 extern "C" int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t P, const double* u, const double* bounds,
                                   const double* p0, const double* p1, double* u_phys, double* xs, double* c, void* stream) {
+  D2DX_NVTX("d2dx_shoot_forward");
   if (int rc = check(p, P, "d2dx_shoot_forward")) return rc;
   D2DX_CHECK_ARG(h && u && p0 && p1 && xs && c, "d2dx_shoot_forward: null array");
   D2DX_CHECK_ARG(!bounds || (u_phys && bounds[1] > bounds[0] && bounds[3] > bounds[2]), "d2dx_shoot_forward: bounds need u_phys and lo < hi");
@@ -292,6 +293,7 @@ extern "C" int d2dx_shoot_forward(d2dx_handle* h, const d2dx_colloc_problem* p, 
 extern "C" int d2dx_shoot_adjoint(d2dx_handle* h, const d2dx_colloc_problem* p, int32_t P, const double* u, const double* bounds,
                                   const double* state_box, const double* u_phys, const double* xs, const double* c, const double* lam,
                                   const double* rho, double* cost, double* lagr, double* grad, void* stream) {
+  D2DX_NVTX("d2dx_shoot_adjoint");
   if (int rc = check(p, P, "d2dx_shoot_adjoint")) return rc;
   D2DX_CHECK_ARG(h && u && xs && c && lam && rho && cost && lagr && grad, "d2dx_shoot_adjoint: null array");
   D2DX_CHECK_ARG(!bounds || u_phys, "d2dx_shoot_adjoint: bounds need u_phys (from d2dx_shoot_forward)");

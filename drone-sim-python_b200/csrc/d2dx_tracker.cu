@@ -208,6 +208,7 @@ int d2dx_tracker_default_gains(d2dx_tracker_gains* g) {
 }
 
 int d2dx_flatness5(d2dx_handle* h, int32_t n, const double* Ys, const double* W, const double* ac, double* Xr, double* Ur, void* stream) {
+  D2DX_NVTX("d2dx_flatness5");
   D2DX_CHECK_ARG(h && n > 0 && Ys && W && ac && Xr && Ur, "d2dx_flatness5: bad argument");
   D2DX_CUDA(cudaSetDevice(h->device));
   flatness5_kernel<<<(n + kTrkThreads - 1) / kTrkThreads, kTrkThreads, 0, as_stream(stream)>>>(n, Ys, W, ac, Xr, Ur);
@@ -218,6 +219,7 @@ int d2dx_flatness5(d2dx_handle* h, int32_t n, const double* Ys, const double* W,
 int d2dx_tracker_control(d2dx_handle* h, int32_t n, const double* X, const double* Ys, const double* W, const double* ac,
                          const d2dx_tracker_gains* gains_host, double* U, double* Xr, double* dX, double* K, double* lqr_state,
                          void* stream) {
+  D2DX_NVTX("d2dx_tracker_control");
   D2DX_CHECK_ARG(h && n > 0 && X && Ys && W && ac && U, "d2dx_tracker_control: bad argument");
   d2dx_tracker_gains g;
   if (gains_host) g = *gains_host; else d2dx_tracker_default_gains(&g);
@@ -230,6 +232,7 @@ int d2dx_tracker_control(d2dx_handle* h, int32_t n, const double* X, const doubl
 
 int d2dx_rollout_tracker(d2dx_handle* h, const d2dx_tracker* in, int32_t i_begin, int32_t i_end, int32_t nsub,
                          const d2dx_tracker_gains* gains_host, const d2dx_tracker_out* out, void* stream) {
+  D2DX_NVTX("d2dx_rollout_tracker");
   D2DX_CHECK_ARG(h && in && out, "d2dx_rollout_tracker: null argument");
   D2DX_CHECK_ARG(in->M > 0 && in->T >= 1 && in->ref && in->X0 && in->wind && in->ac && in->dt > 0 && out->X_final,
                  "d2dx_rollout_tracker: M=%d T=%d dt=%g or a missing array", in->M, in->T, in->dt);
