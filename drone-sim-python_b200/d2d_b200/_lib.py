@@ -89,6 +89,13 @@ class Pursuit(C.Structure):
                 ("K", C.c_double), ("sat_phi", C.c_double), ("v_sp", C.c_double)]
 
 
+class DdpOptions(C.Structure):
+    """d2dx_ddp_options (include/d2dx.h)."""
+    _fields_ = [("max_iter", C.c_int32), ("max_outer", C.c_int32), ("max_inner", C.c_int32), ("ls_max", C.c_int32), ("ctol", C.c_double),
+                ("rel_tol", C.c_double), ("abs_tol", C.c_double), ("rho0", C.c_double), ("rho_growth", C.c_double), ("rho_max", C.c_double),
+                ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_max", C.c_double), ("mu_factor", C.c_double), ("reg_mode", C.c_int32)]
+
+
 class LbfgsOptions(C.Structure):
     """d2dx_lbfgs_options (include/d2dx.h)."""
     _fields_ = [("m", C.c_int32), ("max_inner", C.c_int32), ("max_outer", C.c_int32), ("ls_max", C.c_int32), ("window", C.c_int32),
@@ -149,6 +156,9 @@ def _load():
         "d2dx_lbfgs_layout": (C.c_int, [i32, i32, i32, P(LbfgsOptions), P(i64)]),
         "d2dx_lbfgs_init": (C.c_int, [H, i32, i32, i32, P(LbfgsOptions), c_dp, c_dp, c_dp, c_dp]),
         "d2dx_al_lbfgs_tick": (C.c_int, [H, i32, i32, i32, P(LbfgsOptions), c_dp, c_dp, c_dp, c_dp, i32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "d2dx_ddp_default_options": (C.c_int, [P(DdpOptions)]),
+        "d2dx_ddp_work_size": (i64, [i32, i32]),
+        "d2dx_ddp_solve": (C.c_int, [H, P(CollocProblem), i32, P(dbl), P(dbl), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, P(DdpOptions), c_dp]),
         "d2dx_pursuit_control": (C.c_int, [H, P(Pursuit), i32, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_rollout_pursuit": (C.c_int, [H, P(Pursuit), i32, c_dp, c_dp, c_dp, dbl, i32, i32, i32, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "d2dx_dfma_burn": (C.c_int, [H, i32, i32, i32, c_dp, c_dp]),

@@ -327,6 +327,23 @@ class Engine:
                                      n_parts, _ptr(grad), _ptr(c), _ptr(lam), _ptr(rho), _ptr(n_running), self.stream_ptr()),
               "d2dx_al_lbfgs_tick")
 
+    # ---- second-order planner solve (control-limited DDP, one thread per problem) ------------------------------
+    def ddp_options(self, **kw):
+        o = _lib.DdpOptions()
+        check(lib.d2dx_ddp_default_options(C.byref(o)), "d2dx_ddp_default_options")
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def ddp_solve(self, prob, P, bounds, state_box, p0, p1, u, xs, info, opts=None):
+        """u (P,2,N) in/out, xs (P,3,N) out, info (P,8) out, p0 / p1 (P,3): device tensors; bounds / state_box host tuples."""
+        b = (C.c_double * 4)(*bounds)
+        sb = (C.c_double * 5)(*state_box) if state_box is not None else None
+        work = self.empty(int(lib.d2dx_ddp_work_size(P, prob.N)))
+        check(lib.d2dx_ddp_solve(self.h, C.byref(prob), P, b, sb, _ptr(p0), _ptr(p1), _ptr(u), _ptr(xs), _ptr(info), _ptr(work),
+                                 C.byref(opts) if opts is not None else None, self.stream_ptr()), "d2dx_ddp_solve")
+        self.launches += 1
+
     # ---- pure pursuit ------------------------------------------------------------------------------------
     def pursuit(self, pts, lookahead=100, K=1., sat_phi=np.deg2rad(45.), v_sp=10.):
         """device copy of a sampled path (n_pts, 2) + the controller constants -> (struct, keep-alive tensors)"""

@@ -67,13 +67,31 @@ class _PlannerBase:
         if "x" in self._bounds or "y" in self._bounds:
             bx, by = self._bounds.get("x", (-np.inf, np.inf)), self._bounds.get("y", (-np.inf, np.inf))
             box = (max(bx[0], -1e300), min(bx[1], 1e300), max(by[0], -1e300), min(by[1], 1e300), state_weight)
-        nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts, state_box=box)
         tol = getattr(self, "tol", 1e-8)
-        driver = shooting.solve_host if _.get("driver") == "host" else shooting.solve
-        kw = {} if driver is shooting.solve_host else {"min_solved": min_solved}
-        theta, info = driver(nlp, nlp.theta_of(np.clip(phi, *phi_b), np.clip(v, *v_b)), ctol=min(tol, 1e-6),
-                             max_inner=min(getattr(self, "max_iter", 3000), 500), verbose=verbose, **kw)
-        frees = nlp.free_vectors()
+        method = _.get("method", "auto")
+        frees = info = None
+        if n == 1 and method in ("auto", "ddp"):
+            # second-order solve (control-limited DDP, one GPU thread per start): the caller's start, a deterministic family of
+            # constant-bank starts (both turn directions) and random ones; milliseconds, so it always gets at least nine starts
+            n_ddp = max(n_starts, 9)
+            fam = np.array([0., 0.3, -0.3, 0.7, -0.7, 0.1, -0.1, 0.95, -0.95]) * max(abs(phi_b[0]), abs(phi_b[1]))
+            rng = np.random.default_rng(seed)
+            phi_s = np.concatenate([phi[:, 0], np.repeat(fam[:, None], N, 1), rng.uniform(phi_b[0], phi_b[1], (n_ddp, 1)) * np.ones((1, N))])[:n_ddp]
+            v_s = np.concatenate([v[:, 0], np.full((len(fam), N), float(np.clip(getattr(self, "_vref", v[0, 0].mean()), *v_b))),
+                                  rng.uniform(v_b[0], v_b[1], (n_ddp, 1)) * np.ones((1, N))])[:n_ddp]
+            nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_ddp, state_box=box)
+            frees, info = shooting.solve_ddp(nlp, phi_s, v_s, ctol=min(tol, 1e-6), verbose=verbose)
+            info["nfev"] = info["iterations"]
+            if method == "auto" and not (info["flag"] == 2).any():
+                frees = info = None                                   # no start converged: hand the problem to the first-order driver
+        if frees is None:
+            nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts, state_box=box)
+            driver = shooting.solve_host if _.get("driver") == "host" else shooting.solve
+            kw = {} if driver is shooting.solve_host else {"min_solved": min_solved}
+            theta, info = driver(nlp, nlp.theta_of(np.clip(phi, *phi_b), np.clip(v, *v_b)), ctol=min(tol, 1e-6),
+                                 max_inner=min(getattr(self, "max_iter", 3000), 500), verbose=verbose, **kw)
+            info["method"] = "lbfgs"
+            frees = nlp.free_vectors()
         if self.prob.c.perm_phi:                                                  # opty input order: place the input blocks by rank
             frees = self._to_opty_order(frees)
         feas = info["c_max"] < 100 * min(tol, 1e-6)

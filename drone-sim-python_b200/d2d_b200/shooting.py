@@ -210,3 +210,51 @@ def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner
     return theta, {"outer": int(meta_h[:, 6].max()), "iterations": int(meta_h[:, 10].max()), "nfev": int(meta_h[:, 5].max()),
                    "ticks": done_ticks, "flag": meta_h[:, 0].copy(), "iterations_each": meta_h[:, 10].copy(),
                    "c_max": nlp.c.abs().amax(dim=(1, 2)).cpu().numpy(), "cost": nlp.cost.cpu().numpy()}
+
+
+def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False):
+    """Second-order solve of P single-aircraft problems (d2dx_ddp_solve: control-limited DDP on the collocation grid, one GPU
+    thread per problem).  phi0, v0: host (P, N) (or broadcastable) start inputs.  Problems that end unsolved climb a retry
+    ladder: the same start with the other regularisation (eigenvalue-modified Newton: better on tightly saturated problems,
+    plain Levenberg-Marquardt: better elsewhere), then the mirrored bank profile (the other turn direction -- the usual reason
+    for an infeasible local minimum) with either.  Returns (frees (P, num_free) in the planner layout, info)."""
+    if nlp.n_ac != 1:
+        raise ValueError("solve_ddp handles one aircraft per problem (collision terms couple the aircraft: use solve)")
+    e, P, N = nlp.eng, nlp.P, nlp.N
+    kw = dict(ctol=ctol) if opts is None else {f: getattr(opts, f) for f, _ in opts._fields_}
+    lo, hi, vlo, vhi = nlp.bounds
+    u0 = np.stack([np.broadcast_to(np.asarray(phi0, np.float64).reshape(-1, N) if np.ndim(phi0) else np.full((1, N), float(phi0)), (P, N)),
+                   np.broadcast_to(np.asarray(v0, np.float64).reshape(-1, N) if np.ndim(v0) else np.full((1, N), float(v0)), (P, N))], 1)
+    u0 = np.clip(u0, np.array([lo, vlo])[None, :, None], np.array([hi, vhi])[None, :, None])
+    u = e.to_device(np.ascontiguousarray(u0))
+    xs, info = e.empty(P, 3, N), e.zeros(P, 8)
+    p0, p1 = nlp.p0.reshape(P, 3).contiguous(), nlp.p1.reshape(P, 3).contiguous()
+    mode0 = int(kw.get("reg_mode", 0))
+    e.ddp_solve(nlp.c_prob, P, nlp.bounds, nlp.state_box, p0, p1, u, xs, info, e.ddp_options(**{**kw, "reg_mode": mode0}))
+    ih = info.cpu().numpy()
+    total_its = ih[:, 1].copy()
+    ladder = [(1.0, 1 - mode0), (-1.0, mode0), (-1.0, 1 - mode0)][:retries]
+    for r, (sign, mode) in enumerate(ladder):
+        bad = np.nonzero(ih[:, 0] != 2)[0]
+        if len(bad) == 0:
+            break
+        seed = u0[bad].copy()
+        seed[:, 0] *= sign
+        if sign < 0 and not np.any(seed[:, 0]):
+            seed[:, 0] = 0.3 * hi
+        idx = torch.from_numpy(bad).to(e.device)
+        ub, xb, ib = e.to_device(np.ascontiguousarray(seed)), e.empty(len(bad), 3, N), e.zeros(len(bad), 8)
+        e.ddp_solve(nlp.c_prob, len(bad), nlp.bounds, nlp.state_box, p0[idx].contiguous(), p1[idx].contiguous(), ub, xb, ib,
+                    e.ddp_options(**{**kw, "reg_mode": mode}))
+        ibh = ib.cpu().numpy()
+        better = torch.from_numpy((ibh[:, 0] == 2) | (ibh[:, 4] < ih[bad, 4])).to(e.device)
+        sel = idx[better]
+        u[sel], xs[sel], info[sel] = ub[better], xb[better], ib[better]
+        total_its[bad] += ibh[:, 1]
+        ih = info.cpu().numpy()
+        if verbose:
+            print(f"retry {r} (bank sign {sign:+.0f}, regularisation {mode}): {len(bad)} problems re-seeded, {(ibh[:, 0] == 2).sum()} of them solved")
+    frees = torch.cat([xs.reshape(P, 3 * N), u.reshape(P, 2 * N)], dim=1).cpu().numpy()
+    nlp.xs.copy_(xs.reshape(P, 3, 1, N)); nlp.u_phys.copy_(u.reshape(P, 2, 1, N))
+    return frees, {"flag": ih[:, 0].astype(int), "iterations_each": total_its.astype(int), "iterations": int(total_its.max()), "outer": int(ih[:, 2].max()),
+                   "cost": ih[:, 3].copy(), "c_max": ih[:, 4].copy(), "method": "ddp"}

@@ -415,6 +415,34 @@ int d2dx_al_lbfgs_tick(d2dx_handle* h, int32_t P, int32_t n, int32_t n_con, cons
                        double* x_trial, const double* f_parts, const double* cost_parts, int32_t n_parts, const double* grad,
                        const double* c, double* lam, double* rho, int32_t* n_running, void* stream);
 
+/* -------- second-order solve of the single-aircraft planner NLP (replaces prob.solve -> IPOPT, 06_optyplan.py:117-125) --------
+ * Control-limited differential dynamic programming on the collocation grid (exact second-order model of the backward-Euler
+ * transition, the 2-variable box QP of every node solved exactly: phi / v bounds hold at every iterate), terminal conditions by
+ * an augmented Lagrangian, state box as a quadratic penalty of the excess.  One THREAD solves one problem; P problems (multi-start,
+ * many boundary conditions) per launch.  p_host: n_ac must be 1; N, h, wind and the cost description are used.
+ *   bounds_host4    {phi_lo, phi_hi, v_lo, v_hi} (host)          state_box_host5  {x_lo, x_hi, y_lo, y_hi, weight} or NULL (host)
+ *   p0[P][3], p1[P][3]  initial state and terminal target (x, y, psi)
+ *   u[P][2][N]      in: start (phi, v per node), out: solution     xs[P][3][N]  out: states of the solution
+ *   info[P][8]      out: flag (2 solved, 3 stopped unsolved), iterations, multiplier updates, cost, max |terminal error|,
+ *                   augmented Lagrangian, final regularisation, final penalty
+ *   work            device doubles, at least d2dx_ddp_work_size(P, N) */
+typedef struct {
+  int32_t max_iter;      /* sweeps (backward + line search) per problem in total */
+  int32_t max_outer;     /* multiplier updates */
+  int32_t max_inner;     /* sweeps per multiplier update */
+  int32_t ls_max;        /* halvings per line search */
+  double ctol;           /* solved when max |terminal error| < ctol at a converged inner loop */
+  double rel_tol, abs_tol;   /* inner loop converged when the (predicted or achieved) decrease <= rel_tol |L| + abs_tol */
+  double rho0, rho_growth, rho_max;
+  double mu0, mu_min, mu_max, mu_factor;   /* Levenberg-Marquardt regularisation of Quu and its adaptation */
+  int32_t reg_mode;      /* 0: plain mu (raised until every node's Quu is definite); 1: eigenvalues of Quu replaced by their magnitude, plus mu */
+} d2dx_ddp_options;
+int d2dx_ddp_default_options(d2dx_ddp_options* o_host);
+int64_t d2dx_ddp_work_size(int32_t P, int32_t N);
+int d2dx_ddp_solve(d2dx_handle* h, const d2dx_colloc_problem* p_host, int32_t P, const double* bounds_host4,
+                   const double* state_box_host5, const double* p0, const double* p1, double* u, double* xs, double* info,
+                   double* work, const d2dx_ddp_options* o_host, void* stream);
+
 /* -------- pure-pursuit guidance on a sampled path (PurePursuitControler, d2d/guidance.py:204-245) --------
  * nearest sample of the path to the aircraft (first minimum of the Euclidean distance, as np.argmin), carrot `lookahead`
  * samples further (wrapping at the end), phi_c = clip(-K wrap(psi - atan2(carrot - position)), +-sat_phi), v_c = v_sp.

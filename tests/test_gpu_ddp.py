@@ -1,0 +1,76 @@
+"""Second-order planner solve on the GPU (d2dx_ddp_solve: control-limited DDP, one thread per problem) through the planner
+front ends: feasibility under the reference's own constraints (the parity-tested collocation kernel), IPOPT's optima on the
+experiments whose solutions the reference ships, all 64 multi-starts of C3, a population of 4096 problems."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+
+def test_exp0_second_order_solve_matches_host_build_and_ipopt_optimum():
+    from d2d_b200 import planner as pl
+    import ddp_host as dh
+    p = pl.Planner(pl.exp_0)
+    p.configure(tol=1e-8)
+    info = p.run(method="ddp")
+    assert info["method"] == "ddp" and info["feasible"]
+    assert abs(info["cost"][info["best"]] - 0.752912) < 2e-6
+    assert np.abs(p.prob.con(p.solution)).max() < 1e-7                  # defects and the six instance constraints
+    assert abs(p.prob.obj(p.solution) - info["cost"][info["best"]]) < 1e-12
+    # the same start through the host build of the same source
+    b = (pl.exp_0.phi_constraint[0], pl.exp_0.phi_constraint[1], pl.exp_0.v_constraint[0], pl.exp_0.v_constraint[1])
+    u, xs, hi = dh.solve(p.num_nodes, p.time_step, (0., 0.), 12., 1., 0., b, pl.exp_0.p0[:3], pl.exp_0.p1[:3], 0., 12.)
+    k = 0                                                                 # start 0 = the caller's (triangle) guess: phi = 0, v = vref
+    assert info["flag"][k] == hi["flag"] == 2 and abs(info["cost"][k] - hi["cost"]) < 1e-7
+
+
+@pytest.mark.parametrize("t1,ipopt_cost", [(7., 3.908415), (10., 0.758672), (15., 1.04e-6), (20., 8.1e-8), (30., 4.0e-7)])
+def test_cost_not_above_the_cached_ipopt_solutions(t1, ipopt_cost):
+    """exp_0_1 on the 50 Hz grid (src/cache/optyplan_exp0_1_*.npz; their costs recomputed from sol_v)"""
+    from d2d_b200 import planner as pl
+
+    class exp(pl.exp_0):
+        hz = 50.
+    exp.t1 = t1
+    p = pl.Planner(exp)
+    p.configure(tol=1e-8)
+    info = p.run(method="ddp")
+    assert info["feasible"] and np.abs(p.prob.con(p.solution)).max() < 1e-7
+    assert info["cost"][info["best"]] <= ipopt_cost * (1 + 1e-5) + 1e-9
+
+
+def test_c3_all_64_starts_end_feasible():
+    from d2d_b200 import planner as pl
+
+    class exp_c3(pl.exp_0):
+        t1, hz = 20., 50.
+    p = pl.Planner(exp_c3)
+    p.configure(tol=1e-8)
+    info = p.run(n_starts=64, method="ddp")
+    assert (info["c_max"] < 1e-6).sum() == 64, int((info["c_max"] < 1e-6).sum())
+    assert info["cost"][info["best"]] <= 8.1e-8
+    assert np.median(info["iterations_each"]) < 150
+
+
+def test_population_of_4096_problems():
+    from d2d_b200 import planner as pl
+    from d2d_b200.shooting import ShootingNLP, solve_ddp
+    rng = np.random.default_rng(12345)
+    Pp = 4096
+    pe = pl.Planner(pl.exp_0)
+    p1 = np.stack([rng.uniform(-10, 10, Pp), rng.uniform(28, 40, Pp), np.pi + rng.uniform(-0.5, 0.5, Pp)], 1).reshape(Pp, 3, 1)
+    nlp = ShootingNLP(pe.prob, np.zeros((3, 1)), p1, pl.exp_0.phi_constraint, pl.exp_0.v_constraint, P=Pp)
+    frees, info = solve_ddp(nlp, 0.1, 12., ctol=1e-8)
+    solved = int((info["flag"] == 2).sum())
+    print("population:", solved, "of", Pp, "solved, median sweeps", np.median(info["iterations_each"]))
+    assert solved >= 4050 and np.median(info["iterations_each"]) < 150
+    for k in (0, 1234, Pp - 1):
+        inst = [(j, 0, 0.) for j in range(3)] + [(j, pe.num_nodes - 1, float(p1[k, j, 0])) for j in range(3)]
+        from d2d_b200.collocation import CollocationProblem
+        chk = CollocationProblem(1, pe.num_nodes, pe.time_step, inst=inst)
+        assert np.abs(chk.con(frees[k])).max() < 1e-7
