@@ -66,9 +66,10 @@ int d2dx_host_ddp_solve(const double* prob9, int n_obs, const double* obs, const
   if (o) opt = *o;
   else {
     opt.max_iter = 400; opt.max_outer = 30; opt.max_inner = 40; opt.ls_max = 12; opt.ctol = 1e-8; opt.rel_tol = 1e-10; opt.abs_tol = 1e-14;
-    opt.rho0 = 10.0; opt.rho_growth = 10.0; opt.rho_max = 1e8; opt.mu0 = 1e-6; opt.mu_min = 1e-8; opt.mu_max = 1e10; opt.mu_factor = 1.6; opt.reg_mode = 0;
+    opt.rho0 = 10.0; opt.rho_growth = 10.0; opt.rho_max = 1e8; opt.mu0 = 1e-6; opt.mu_min = 1e-8; opt.mu_max = 1e10; opt.mu_factor = 1.6; opt.reg_mode = 0; opt.min_solved = 0;
   }
-  const DdpResult r = ddp_solve(P, W, z0, zt, opt);
+  DdpSerial sweeps(P, W, zt);
+  const DdpResult r = ddp_solve(sweeps, z0, opt);
   const double* us = (r.swaps & 1) ? W.un : W.u;
   const double* zs = (r.swaps & 1) ? W.zn : W.z;
   for (int i = 0; i < 2 * N; ++i) u[i] = us[i];

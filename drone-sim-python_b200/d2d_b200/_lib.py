@@ -93,7 +93,7 @@ class DdpOptions(C.Structure):
     """d2dx_ddp_options (include/d2dx.h)."""
     _fields_ = [("max_iter", C.c_int32), ("max_outer", C.c_int32), ("max_inner", C.c_int32), ("ls_max", C.c_int32), ("ctol", C.c_double),
                 ("rel_tol", C.c_double), ("abs_tol", C.c_double), ("rho0", C.c_double), ("rho_growth", C.c_double), ("rho_max", C.c_double),
-                ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_max", C.c_double), ("mu_factor", C.c_double), ("reg_mode", C.c_int32)]
+                ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_max", C.c_double), ("mu_factor", C.c_double), ("reg_mode", C.c_int32), ("min_solved", C.c_int32)]
 
 
 class LbfgsOptions(C.Structure):

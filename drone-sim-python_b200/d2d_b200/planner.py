@@ -80,7 +80,9 @@ class _PlannerBase:
             v_s = np.concatenate([v[:, 0], np.full((len(fam), N), float(np.clip(getattr(self, "_vref", v[0, 0].mean()), *v_b))),
                                   rng.uniform(v_b[0], v_b[1], (n_ddp, 1)) * np.ones((1, N))])[:n_ddp]
             nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_ddp, state_box=box)
-            frees, info = shooting.solve_ddp(nlp, phi_s, v_s, ctol=min(tol, 1e-6), verbose=verbose)
+            # asked for one solution (n_starts = 1): stop as soon as three starts have converged; asked for many: run them all out
+            k_enough = (min_solved if min_solved is not None else (3 if n_starts == 1 else 0))
+            frees, info = shooting.solve_ddp(nlp, phi_s, v_s, ctol=min(tol, 1e-6), verbose=verbose, min_solved=k_enough)
             info["nfev"] = info["iterations"]
             if method == "auto" and not (info["flag"] == 2).any():
                 frees = info = None                                   # no start converged: hand the problem to the first-order driver

@@ -212,16 +212,17 @@ def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner
                    "c_max": nlp.c.abs().amax(dim=(1, 2)).cpu().numpy(), "cost": nlp.cost.cpu().numpy()}
 
 
-def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False):
+def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False, min_solved=0):
     """Second-order solve of P single-aircraft problems (d2dx_ddp_solve: control-limited DDP on the collocation grid, one GPU
     thread per problem).  phi0, v0: host (P, N) (or broadcastable) start inputs.  Problems that end unsolved climb a retry
     ladder: the same start with the other regularisation (eigenvalue-modified Newton: better on tightly saturated problems,
     plain Levenberg-Marquardt: better elsewhere), then the mirrored bank profile (the other turn direction -- the usual reason
-    for an infeasible local minimum) with either.  Returns (frees (P, num_free) in the planner layout, info)."""
+    for an infeasible local minimum) with either.  `min_solved=k` (multi-start of ONE problem): the launch ends as soon as k starts
+    have converged and the ladder is only climbed when none has.  Returns (frees (P, num_free) in the planner layout, info)."""
     if nlp.n_ac != 1:
         raise ValueError("solve_ddp handles one aircraft per problem (collision terms couple the aircraft: use solve)")
     e, P, N = nlp.eng, nlp.P, nlp.N
-    kw = dict(ctol=ctol) if opts is None else {f: getattr(opts, f) for f, _ in opts._fields_}
+    kw = dict(ctol=ctol, min_solved=int(min_solved)) if opts is None else {f: getattr(opts, f) for f, _ in opts._fields_}
     lo, hi, vlo, vhi = nlp.bounds
     u0 = np.stack([np.broadcast_to(np.asarray(phi0, np.float64).reshape(-1, N) if np.ndim(phi0) else np.full((1, N), float(phi0)), (P, N)),
                    np.broadcast_to(np.asarray(v0, np.float64).reshape(-1, N) if np.ndim(v0) else np.full((1, N), float(v0)), (P, N))], 1)
@@ -236,7 +237,7 @@ def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False):
     ladder = [(1.0, 1 - mode0), (-1.0, mode0), (-1.0, 1 - mode0)][:retries]
     for r, (sign, mode) in enumerate(ladder):
         bad = np.nonzero(ih[:, 0] != 2)[0]
-        if len(bad) == 0:
+        if len(bad) == 0 or (min_solved > 0 and len(bad) < P):
             break
         seed = u0[bad].copy()
         seed[:, 0] *= sign

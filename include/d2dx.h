@@ -436,6 +436,8 @@ typedef struct {
   double rho0, rho_growth, rho_max;
   double mu0, mu_min, mu_max, mu_factor;   /* Levenberg-Marquardt regularisation of Quu and its adaptation */
   int32_t reg_mode;      /* 0: plain mu (raised until every node's Quu is definite); 1: eigenvalues of Quu replaced by their magnitude, plus mu */
+  int32_t min_solved;    /* > 0: problems still iterating stop (flag 3) once this many problems of the launch have converged --
+                            multi-start, where the stragglers are the starts in an infeasible local minimum; 0: every problem runs out */
 } d2dx_ddp_options;
 int d2dx_ddp_default_options(d2dx_ddp_options* o_host);
 int64_t d2dx_ddp_work_size(int32_t P, int32_t N);

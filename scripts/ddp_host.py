@@ -12,11 +12,11 @@ LIB = os.path.join(ROOT, "tests", "native", "libd2dx_hostcheck.so")
 class DdpOptions(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("max_outer", C.c_int32), ("max_inner", C.c_int32), ("ls_max", C.c_int32), ("ctol", C.c_double),
                 ("rel_tol", C.c_double), ("abs_tol", C.c_double), ("rho0", C.c_double), ("rho_growth", C.c_double), ("rho_max", C.c_double),
-                ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_max", C.c_double), ("mu_factor", C.c_double), ("reg_mode", C.c_int32)]
+                ("mu0", C.c_double), ("mu_min", C.c_double), ("mu_max", C.c_double), ("mu_factor", C.c_double), ("reg_mode", C.c_int32), ("min_solved", C.c_int32)]
 
 
 def default_options(**kw):
-    o = DdpOptions(400, 30, 40, 12, 1e-8, 1e-10, 1e-14, 10., 10., 1e8, 1e-6, 1e-8, 1e10, 1.6, 0)
+    o = DdpOptions(400, 30, 40, 12, 1e-8, 1e-10, 1e-14, 10., 10., 1e8, 1e-6, 1e-8, 1e10, 1.6, 0, 0)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
