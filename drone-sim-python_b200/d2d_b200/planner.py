@@ -68,7 +68,7 @@ class _PlannerBase:
             bx, by = self._bounds.get("x", (-np.inf, np.inf)), self._bounds.get("y", (-np.inf, np.inf))
             box = (max(bx[0], -1e300), min(bx[1], 1e300), max(by[0], -1e300), min(by[1], 1e300), state_weight)
         tol = getattr(self, "tol", 1e-8)
-        method = _.get("method", "auto")
+        method = _.get("method", "lbfgs" if _.get("driver") == "host" else "auto")
         frees = info = None
         if n == 1 and method in ("auto", "ddp"):
             # second-order solve (control-limited DDP, one GPU thread per start): the caller's start, a deterministic family of
@@ -97,6 +97,8 @@ class _PlannerBase:
         if self.prob.c.perm_phi:                                                  # opty input order: place the input blocks by rank
             frees = self._to_opty_order(frees)
         feas = info["c_max"] < 100 * min(tol, 1e-6)
+        if info.get("method") == "ddp" and (info["flag"] == 2).any():
+            feas = info["flag"] == 2                                              # starts cut short by the early exit are not candidates
         best = int(np.argmin(np.where(feas, info["cost"], np.inf))) if feas.any() else int(np.argmin(info["c_max"]))
         self.solution = frees[best].copy()
         info.update(best=best, feasible=bool(feas[best]), solutions=frees)

@@ -159,7 +159,7 @@ def test_device_and_host_drivers_agree_and_population_solves():
     from d2d_b200 import shooting
     p = pl.Planner(pl.exp_0)
     p.configure(tol=1e-8)
-    info_d = p.run()
+    info_d = p.run(method="lbfgs")
     cost_d = p.prob.obj(p.solution)
     assert np.abs(p.prob.con(p.solution)).max() < 1e-7
     info_h = p.run(driver="host")
