@@ -339,6 +339,28 @@ def secondary_metrics(eng, hbm_peak):
     out["c5_minsnap_population"] = {"aircraft_steps_per_s": Bp * Tp / dtp, "scenarios": Bp, "steps": Tp, "ms_per_sweep": dtp * 1e3,
                                     "unconverged_or_nonfinite": int(mcp.d_flags.ne(0).sum().item())}
     del mcp
+    # the generic (mixed / composite) instantiation rollout_dfff_kernel<-1>: patrol_3-style composites (line, circle arc, slalom),
+    # 75 776 scenarios x 2942 steps; the segment table is walked per step (fmod + search) and the parameter column reloaded on a switch
+    try:
+        from d2d_b200 import scenario as dds
+        scen = dds.get("patrol_3")
+        Bc = eng.sm_count * 512
+        trajs = [scen.trajs[k % len(scen.trajs)] for k in range(Bc)]
+        X0c = np.stack([np.asarray(scen.X0s[k % len(scen.trajs)], dtype=np.float64) for k in range(Bc)]) + rng.normal(0, 1, (Bc, 5)) * np.array([2, 2, .1, .02, .2])
+        tabc = eng.table(ddt.pack(trajs))
+        Wc = scen.windfield.sample(0, None)
+        X0d, Wd = eng.to_device(np.ascontiguousarray(X0c.T)), eng.to_device(np.ascontiguousarray(np.tile(np.asarray(Wc, float), (Bc, 1)).T))
+        acd, tdc = eng.to_device(np.stack([np.full(Bc, 0.01), np.full(Bc, 1.)])), eng.to_device(np.ascontiguousarray(scen.time, dtype=np.float64))
+        Xfc, flc = eng.empty(5, Bc), eng.zeros(Bc, dtype=torch.int32)
+        Tc = len(scen.time) - 1
+        dtc = timed(lambda: eng.rollout_dfff(tabc, X0d, Wd, acd, tdc, 0, Tc, nsub=1, final_control=True, X_final=Xfc, flags=flc), 2)
+        out["composite_patrol3_batch"] = {"aircraft_steps_per_s": Bc * Tc / dtc, "scenarios": Bc, "steps": Tc, "ms_per_launch": dtc * 1e3,
+                                          "kernel": "rollout_dfff_kernel<-1> (generic: composite trajectories, segment table per step)",
+                                          "roofline": {"bound": "fp64", "achieved": Bc * Tc * FP64_FLOP_PER_STEP / dtc / 1e12, "unit": "TFLOP/s",
+                                                       "note": "lower bound: counted with the circle kernel's 700 flop per step"}}
+        del tabc, X0d, Wd, Xfc
+    except Exception as e:
+        out["composite_patrol3_batch"] = {"error": f"{type(e).__name__}: {e}"}
     # 5-state LQR tracker on sampled circle references: dt 0.1 s, RK4 nsub 10, T = 101 samples
     Mt, Tt = eng.sm_count * 1024, 101
     tt = np.arange(Tt) * 0.1
