@@ -344,6 +344,7 @@ def secondary_metrics(eng, hbm_peak):
     try:
         from d2d_b200 import scenario as dds
         scen = dds.get("patrol_3")
+        scen = scen[0] if isinstance(scen, tuple) else scen
         Bc = eng.sm_count * 512
         trajs = [scen.trajs[k % len(scen.trajs)] for k in range(Bc)]
         X0c = np.stack([np.asarray(scen.X0s[k % len(scen.trajs)], dtype=np.float64) for k in range(Bc)]) + rng.normal(0, 1, (Bc, 5)) * np.array([2, 2, .1, .02, .2])
@@ -452,7 +453,7 @@ def secondary_metrics(eng, hbm_peak):
     out["planner_population_4096"] = {"seconds": dt_pop, "solved": int((info["flag"] == 2).sum()), "problems": Pp,
                                       "solved_problems_per_s": float((info["flag"] == 2).sum() / dt_pop),
                                       "median_iterations": float(np.median(info["iterations_each"])),
-                                      "method": "control-limited DDP, one thread per problem (d2dx_ddp_solve)"}
+                                      "method": "control-limited DDP, one warp per problem (d2dx_ddp_solve)"}
     del nlp
     # pure-pursuit closed loop: 4096 aircraft on the square patrol, 1500 steps, 2000 path samples searched per step
     from d2d_b200 import guidance as ddg, trajectory_factory as ddtf
@@ -621,6 +622,27 @@ def main():
         e2e = {"value": total_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(mc.h2d_bytes), "d2h_bytes_per_step": int(mc.d2h_bytes),
                "ms_per_step": ms_e2e, "host_log": host_log, "api": "d2d_b200.simulation.MonteCarloRollout.run (pinned host buffers in/out)"}
 
+    # ---- the same end-to-end sweep with only the STATE log copied out (north_star: "state logs"; the input log stays in HBM) ----
+    if e2e is not None and host_log:
+        try:
+            del mc
+            torch.cuda.empty_cache()
+            mc = MonteCarloRollout(B, time, _lib.SEG_CIRCLE, nsub=1, log_every=args.log_every, n_chunks=args.chunks, host_log=True, host_log_u=False)
+            mc.set_inputs(par, w["wind"], X0)
+            mc.run()
+            barrier()
+            t0 = _time.perf_counter()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(n_e2e):
+                mc.run()
+            c1.record()
+            barrier()
+            ms_x = reduce_max(max(c0.elapsed_time(c1), 1e3 * (_time.perf_counter() - t0))) / n_e2e
+            e2e["state_log_only"] = {"value": total_steps / (ms_x * 1e-3), "ms_per_step": ms_x, "d2h_bytes_per_step": int(mc.d2h_bytes),
+                                     "note": "X log only (5 of the 7 logged doubles per sample); U log left in HBM"}
+        except Exception as e:
+            e2e["state_log_only"] = {"error": f"{type(e).__name__}: {e}"}
     # ---- the rest of the metric (collocation evals/s, formation, aircraft-sharded C4) on every rank, at every N ----
     hbm_peak = None
     try:
@@ -630,7 +652,7 @@ def main():
     peak_tf, probe = eng.measure_fp64_peak(details=True)
     core, core_checks = None, {}
     if not args.no_secondary:
-        del mc                                             # the sweep's 6 GB of logs are no longer needed
+        mc = None                                          # the sweep's 6 GB of logs are no longer needed
         torch.cuda.empty_cache()
         try:
             core, core_checks = core_metrics(eng, hbm_peak or 6650.0, peak_tf, world, rank, args.seed)

@@ -271,7 +271,7 @@ class MonteCarloRollout:
     it returns NumPy views of the pinned result buffers.  `run_device()` is the same sweep with the inputs
     already resident in HBM and nothing copied back."""
 
-    def __init__(self, B, time, seg_type, nsub=1, log_every=100, n_chunks=10, log_u=True, host_log=True, engine=None):
+    def __init__(self, B, time, seg_type, nsub=1, log_every=100, n_chunks=10, log_u=True, host_log=True, engine=None, host_log_u=True):
         from . import _lib
         from .engine import PackedTrajectories
         self.eng = eng = engine or get_engine()
@@ -289,7 +289,7 @@ class MonteCarloRollout:
         self.h_pop = pin(2)
         self.host_log, self.log_u = host_log, log_u
         self.h_Xlog = pin(self.n_rows, 5, B) if host_log else None
-        self.h_Ulog = pin(self.n_rows, 2, B) if (host_log and log_u) else None
+        self.h_Ulog = pin(self.n_rows, 2, B) if (host_log and log_u and host_log_u) else None      # host_log_u=False: only the STATE log travels
         # device buffers
         self.d_X0, self.d_wind, self.d_ac = eng.empty(5, B), eng.empty(2, B), eng.empty(2, B)
         par = eng.zeros(_lib.SEG_NPAR, B)
