@@ -326,7 +326,7 @@ struct DdpSerial {
   }
 };
 
-struct DdpResult { int flag, iterations, outer, swaps; double cost, cmax, lagr, mu, rho; };   // flag 2 solved, 3 stopped unsolved; swaps odd: the solution sits in (un, zn)
+struct DdpResult { int flag, iterations, outer, swaps; double cost, cmax, lagr, mu, rho; };   // flag 2 solved, 3 stopped unsolved, 4 feasible at the sweep limit; swaps odd: the solution sits in (un, zn)
 
 // The solver: augmented-Lagrangian loop around regularised second-order sweeps.  `S` supplies the sweeps over one problem's
 // arrays (DdpSerial on the host, the warp-cooperative DdpWarp in d2dx_ddp.cu); every decision below is a scalar one.
@@ -389,6 +389,7 @@ __host__ __device__ inline DdpResult ddp_solve(S& sw_, const double* z0, const d
     mu = o.mu0; dmu = 1.0;
     J = cost + lam[0] * c[0] + lam[1] * c[1] + lam[2] * c[2] + 0.5 * rho * (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
   }
+  if (res.flag != 2 && !stop && cmax < o.ctol) res.flag = 4;       // feasible, but the sweep budget ran out before the cost settled
   res.iterations = it; res.cost = cost; res.cmax = cmax; res.lagr = J; res.mu = mu; res.rho = rho;
   return res;
 }

@@ -84,7 +84,7 @@ class _PlannerBase:
             k_enough = (min_solved if min_solved is not None else (3 if n_starts == 1 else 0))
             frees, info = shooting.solve_ddp(nlp, phi_s, v_s, ctol=min(tol, 1e-6), verbose=verbose, min_solved=k_enough)
             info["nfev"] = info["iterations"]
-            if method == "auto" and not (info["flag"] == 2).any():
+            if method == "auto" and not np.isin(info["flag"], (2, 4)).any():
                 frees = info = None                                   # no start converged: hand the problem to the first-order driver
         if frees is None:
             nlp = shooting.ShootingNLP(self.prob, p0, p1, phi_b, v_b, P=n_starts, state_box=box)
@@ -97,8 +97,8 @@ class _PlannerBase:
         if self.prob.c.perm_phi:                                                  # opty input order: place the input blocks by rank
             frees = self._to_opty_order(frees)
         feas = info["c_max"] < 100 * min(tol, 1e-6)
-        if info.get("method") == "ddp" and (info["flag"] == 2).any():
-            feas = info["flag"] == 2                                              # starts cut short by the early exit are not candidates
+        if info.get("method") == "ddp" and np.isin(info["flag"], (2, 4)).any():
+            feas = np.isin(info["flag"], (2, 4))                                  # starts cut short by the early exit are not candidates
         best = int(np.argmin(np.where(feas, info["cost"], np.inf))) if feas.any() else int(np.argmin(info["c_max"]))
         self.solution = frees[best].copy()
         info.update(best=best, feasible=bool(feas[best]), solutions=frees)

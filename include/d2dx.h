@@ -423,7 +423,8 @@ int d2dx_al_lbfgs_tick(d2dx_handle* h, int32_t P, int32_t n, int32_t n_con, cons
  *   bounds_host4    {phi_lo, phi_hi, v_lo, v_hi} (host)          state_box_host5  {x_lo, x_hi, y_lo, y_hi, weight} or NULL (host)
  *   p0[P][3], p1[P][3]  initial state and terminal target (x, y, psi)
  *   u[P][2][N]      in: start (phi, v per node), out: solution     xs[P][3][N]  out: states of the solution
- *   info[P][8]      out: flag (2 solved, 3 stopped unsolved), iterations, multiplier updates, cost, max |terminal error|,
+ *   info[P][8]      out: flag (2 solved, 3 stopped unsolved, 4 terminal conditions met but the sweep limit reached before the cost
+ *                   settled), iterations, multiplier updates, cost, max |terminal error|,
  *                   augmented Lagrangian, final regularisation, final penalty
  *   work            device doubles, at least d2dx_ddp_work_size(P, N) */
 typedef struct {

@@ -74,3 +74,21 @@ def test_population_of_4096_problems():
         from d2d_b200.collocation import CollocationProblem
         chk = CollocationProblem(1, pe.num_nodes, pe.time_step, inst=inst)
         assert np.abs(chk.con(frees[k])).max() < 1e-7
+
+
+def test_exp14_and_exp13_against_the_cached_ipopt_outputs():
+    """The two other experiments whose IPOPT output the reference ships (src/cache/optyplan_exp 14 - joining 2 points.npz: cost
+    5.029728; optyplan_exp13 - some traj.npz: IPOPT stopped INFEASIBLE there -- its heading misses both instance constraints by
+    0.031 / 0.0087 rad at cost 6.043): exp_14 is solved to IPOPT's cost, exp_13 is reported infeasible with a smaller violation-cost
+    pair than IPOPT's."""
+    from d2d_b200 import optyplan_scenarios as S, planner as pl
+    p = pl.Planner(S.exp_14)
+    p.configure(tol=1e-8)
+    info = p.run(method="ddp", min_solved=0)
+    assert info["feasible"] and np.abs(p.prob.con(p.solution)).max() < 1e-7
+    assert info["cost"][info["best"]] <= 5.029728 * (1 + 2e-6)
+    q = pl.Planner(S.exp_13)
+    q.configure(tol=1e-8)
+    info = q.run(method="ddp", min_solved=0)
+    assert not info["feasible"]
+    assert info["c_max"].min() < 0.04 and info["cost"][np.argmin(info["c_max"])] < 6.05
