@@ -42,6 +42,24 @@ def _worker(rank, world, port, free, inst, ret):
     for a_, b_, tol in ((res2, res, 1e-14), (jac2, jac, 1e-14), (grad2, grad, 1e-13)):      # two different kernels: same values, not same bits
         assert torch.allclose(a_, b_, rtol=tol, atol=1e-16), float((a_ - b_).abs().max())
     assert abs(float(cost2[0]) - float(cost[0])) <= 1e-13 * abs(float(cost[0]))
+    # a batch larger than the co-resident grid (160 problems x 16 tiles = 2560 items; 12 blocks x 148 SMs are resident): the
+    # persistent item loop of the fused kernel, every rank against its own unsharded evaluation of the same batch
+    from d2d_b200.collocation import CollocationProblem
+    PB = 160
+    rngb = np.random.default_rng(99)
+    freeB = free[None] + rngb.normal(0, 0.3, (PB, free.size))
+    scB = ShardedCollocation(16, 500, 0.02, (0., 0.), inst, copy.copy(cs), engine=eng, max_prob=PB)
+    flB = eng.to_device(np.ascontiguousarray(freeB[:, scB.shard.idx_free]))
+    rB, jB, cB, gB = scB.evaluate(flB)
+    rB, jB, cB, gB = (t.clone() for t in scB.evaluate(flB))                                      # second evaluation: next epoch, same answer
+    assert scB.check()["timeouts"] == 0
+    fullB = CollocationProblem(16, 500, 0.02, inst=inst, cost=copy.copy(cs), engine=eng)
+    ob = fullB.evaluate_device(eng.to_device(freeB))
+    dev = lambda idx: torch.from_numpy(idx).to(eng.device)
+    assert float((rB - ob["res"][:, dev(scB.shard.idx_con)]).abs().max()) < 1e-13
+    assert torch.allclose(jB, ob["jac"][:, dev(scB.shard.idx_jac)], rtol=1e-14, atol=0)
+    assert torch.allclose(gB, ob["grad"][:, dev(scB.shard.idx_free)], rtol=1e-12, atol=1e-15)
+    assert torch.allclose(cB, ob["cost"], rtol=1e-13, atol=0)
     # scenario-sharded rollout: each rank its contiguous half of 64 circles, then the one final all-reduce
     rng = np.random.default_rng(0)
     B = 64
