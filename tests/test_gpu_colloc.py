@@ -354,3 +354,53 @@ def test_cost_bank_max_mode_against_reference_golden(golden):
     tie = np.zeros(5 * N); tie[3 * N + 7] = -0.3; tie[3 * N + 400] = 0.3          # equal squares: np.argmax takes the first
     gr = c.cost_grad(tie, P)
     assert gr[3 * N + 7] == 2.5 * 2 * -0.3 and np.count_nonzero(gr) == 1
+
+
+@pytest.mark.parametrize("mode", ["pair01", "nocol", "cost_only"])
+def test_fused_peer_evaluation_other_cost_modes(golden, mode):
+    """The fused sharded kernel in the reference's own collision mode (aircraft 0 and 1 only -- they live on different ranks
+    here), without any collision term (only the cost sums are exchanged), and asked for the cost alone."""
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    from d2d_b200 import distributed, _lib
+    n_ac, N, h, world = 4, 75, 0.05, 4
+    rng = np.random.default_rng(21)
+    free = rng.normal(0, 5., (2, 5 * n_ac * N)); free[:, 4 * n_ac * N:] = 12 + rng.normal(0, 1, (2, n_ac * N))
+    inst = [(k, 0, 0.25 * k) for k in range(3 * n_ac)]
+    if mode == "nocol":
+        cs = CostSpec(vsp=12., kvel=3., kbank=2., kobs=1.5, obstacles=[(1., 2., 6.)], obs_kind=1)
+    else:
+        cs = CostSpec(vsp=12., kvel=3., kbank=2., kcol=10., rcol=8., all_pairs=False, kobs=1.5, obstacles=[(1., 2., 6.)], obs_kind=0)
+    full = CollocationProblem(n_ac, N, h, wind=(0.5, -1.), inst=inst, cost=cs)
+    res, jac, cost, grad = full.evaluate(free)
+    out = distributed.emulate_peer_eval(n_ac, N, h, (0.5, -1.), inst, cs, free, world=world, replays=2)
+    assert all(st["timeouts"] == 0 for st in out["status"])
+    np.testing.assert_allclose(out["residual"], res, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["jac"], jac, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(out["grad"], grad, rtol=1e-12, atol=1e-15)
+    for r in range(world):
+        np.testing.assert_allclose(out["cost"][r], cost, rtol=1e-13)
+
+
+def test_new_entry_points_reject_bad_arguments():
+    """d2dx_peer_create / d2dx_colloc_eval_peer / d2dx_ddp_solve / d2dx_cost_bank_max validate before they launch."""
+    import ctypes as C
+    from d2d_b200 import _lib, get_engine
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    eng = get_engine()
+    lib = _lib.lib
+    p = C.c_void_p()
+    assert lib.d2dx_peer_create(eng.h, 0, 0, 1, 4, 10, C.byref(p)) == 1            # world 0
+    assert lib.d2dx_peer_create(eng.h, 2, 2, 1, 4, 10, C.byref(p)) == 1            # rank out of range
+    assert lib.d2dx_peer_create(eng.h, 17, 0, 1, 4, 10, C.byref(p)) == 1           # more ranks than the exchange supports
+    prob = CollocationProblem(2, 10, 0.1, cost=CostSpec(vsp=12., kvel=1.))
+    pe = eng.peer_create(2, 0, 1, 2, 10)                                           # never connected
+    with pytest.raises(_lib.D2dxError, match="not connected"):
+        eng.colloc_eval_peer(pe, prob.c, 1, 0, eng.zeros(50), _lib.EVAL_ALL, eng.zeros(60), eng.zeros(220), eng.zeros(1), eng.zeros(50))
+    pe.close()
+    with pytest.raises(_lib.D2dxError, match="n_ac = 1"):
+        eng.ddp_solve(prob.c, 1, (-0.5, 0.5, 9., 14.), None, eng.zeros(1, 3), eng.zeros(1, 3), eng.zeros(1, 2, 10), eng.zeros(1, 3, 10), eng.zeros(1, 8))
+    one = CollocationProblem(1, 10, 0.1, cost=CostSpec(vsp=12., kvel=1.))
+    with pytest.raises(_lib.D2dxError):
+        eng.ddp_solve(one.c, 1, (0.5, -0.5, 9., 14.), None, eng.zeros(1, 3), eng.zeros(1, 3), eng.zeros(1, 2, 10), eng.zeros(1, 3, 10), eng.zeros(1, 8))
+    with pytest.raises(_lib.D2dxError):
+        eng.cost_bank_max(eng.zeros(1, 50), 45, 10, 1.0)                           # phi slice runs past the free vector
