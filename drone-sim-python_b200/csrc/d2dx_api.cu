@@ -176,6 +176,11 @@ __global__ void math_probe_kernel(int n, const double* __restrict__ x, const dou
   fm::sincos(x[i], s, c);
   out[i] = s; out[(size_t)n + i] = c; out[2 * (size_t)n + i] = fm::atan2(y[i], x[i]); out[3 * (size_t)n + i] = fm::atan(x[i]);
   out[4 * (size_t)n + i] = fm::div(y[i], x[i]); out[5 * (size_t)n + i] = fm::sqrt(fabs(x[i])); out[6 * (size_t)n + i] = fm::rsqrt(fabs(x[i]));
+  out[7 * (size_t)n + i] = fm::rcp(x[i]);
+  out[8 * (size_t)n + i] = fma(-x[i], fm::rcp_seed(x[i]), 1.0);                 // residuals of the two MUFU seeds
+  const double ax = fabs(x[i]), ys = fm::rsqrt_seed(ax);
+  out[9 * (size_t)n + i] = fma(-ax * ys, ys, 1.0);
+  out[10 * (size_t)n + i] = wrap_pi(x[i]);
 }
 
 }  // namespace d2dx

@@ -29,7 +29,7 @@ __device__ __forceinline__ void sincos_b(double x, double& s, double& c) { fm::s
 struct SinCos { double s, c; };
 static __device__ __noinline__ SinCos sincos_slow(double x) { SinCos r; ::sincos(x, &r.s, &r.c); return r; }
 __device__ __forceinline__ void sincos_any(double x, double& s, double& c) {
-  if (fabs(x) < 1.0e5) fm::sincos(x, s, c);
+  if ((__double2hiint(x) & 0x7fffffff) < 0x40F86A00) fm::sincos(x, s, c);      // |x| < 1e5, decided on the high word (0x40F86A00 = hi(1e5))
   else { const SinCos r = sincos_slow(x); s = r.s; c = r.c; }
 }
 __device__ __forceinline__ double atan2_f(double y, double x) { return fm::atan2(y, x); }
@@ -56,18 +56,40 @@ constexpr double kG = 9.81;                      // d2d/dynamic.py:9, d2d/guidan
 // norm_mpi_pi, d2d/utils.py:7: (v + pi) % (2 pi) - pi with NumPy's floored float modulo
 // (npy_remainder: fmod, then += b when the signs differ).  The three branches are bit-identical to
 // fmod for |a| < 4 pi (a - 2pi is exact there by Sterbenz) and skip CUDA's iterative fmod.
-__device__ __forceinline__ double wrap_pi(double v) {
-  double a = v + kPi, m;
-  // common case first, decided by ONE unsigned compare of the high word: hi(a) < hi(2 pi) = 0x401921FB implies 0 <= a < 2 pi
-  // (sign bit clear, magnitude below); the exact comparisons below take everything else, including hi(a) == hi(2 pi)
-  if (static_cast<unsigned>(__double2hiint(a)) < 0x401921FBu) m = a;
-  else if (a >= 0.0 && a < kTwoPi) m = a;
+static __device__ __noinline__ double wrap_2pi_slow(double a) {
+  double m;
+  if (a >= 0.0 && a < kTwoPi) m = a;
   else if (a >= kTwoPi && a < 2.0 * kTwoPi) m = a - kTwoPi;
   else if (a < 0.0 && a > -kTwoPi) m = a + kTwoPi;
   else {
     m = fmod(a, kTwoPi);
     if (m != 0.0) { if (m < 0.0) m += kTwoPi; } else m = 0.0;
   }
+  return m;
+}
+// The three cases a feedback error or an integrated heading produces are decided on the HIGH WORD of a = v + pi by the integer
+// pipe (the rollout kernels are bound by the fp64 pipe) and cost one DADD with a selected addend:
+//   |a| < 2 pi for certain (|hi| < hi(2 pi) = 0x401921FB):  a >= 0 -> a;   a < 0 -> a + 2 pi (npy_remainder's sign fix)
+//   2 pi < a < 4 pi for certain (0x401921FB < hi < 0x402921FB):  a - 2 pi  (exact by Sterbenz = fmod)
+// everything else -- hi(a) equal to a boundary word, a = -0.0 (remainder +0.0), larger magnitudes, NaN -- is not `fast`.
+__device__ __forceinline__ double wrap_2pi_fast(double a, bool& fast) {
+  const int h = __double2hiint(a);
+  const unsigned am = h & 0x7fffffff;
+  const bool lap1 = static_cast<unsigned>(h - 0x401921FC) < 0x000FFFFFu;          // h in [0x401921FC, 0x402921FB)
+  fast = (am < 0x401921FBu && !(h < 0 && am == 0)) || lap1;
+  return a + (lap1 ? -kTwoPi : (h < 0 ? kTwoPi : 0.0));
+}
+__device__ __forceinline__ double wrap_pi(double v) {
+  const double a = v + kPi;
+  bool fast;
+  const double m = wrap_2pi_fast(a, fast);
+  return (fast ? m : wrap_2pi_slow(a)) - kPi;
+}
+// for callers with their own exact fallback: ok &= fast, the value is only meaningful when ok stays true
+__device__ __forceinline__ double wrap_pi_or_flag(double v, bool& ok) {
+  bool fast;
+  const double m = wrap_2pi_fast(v + kPi, fast);
+  ok = ok && fast;
   return m - kPi;
 }
 
@@ -77,7 +99,10 @@ __device__ __forceinline__ double clip(double v, double lo, double hi) {
   const double t = v < lo ? lo : v;
   return t > hi ? hi : t;
 }
-// clip(v, -s, s) for s >= 0: one compare on |v| and the sign copied back (NaN passes through, like np.clip)
+// clip(v, -s, s) for s >= 0: one compare on |v| and the sign copied back (NaN passes through, like np.clip).
+// (Deciding these saturations on the integer pipe -- high-word keys with an out-of-line exact path, or full 64-bit integer
+//  compares -- was measured in round 2: each fp64 compare saved costs more ALU issue slots than it frees on the fp64 pipe;
+//  the rollout kernel ran 1.5 - 7 % slower.  profiles/README.md.)
 __device__ __forceinline__ double clip_sym(double v, double s) {
   const double m = fabs(v) > s ? s : fabs(v);
   return copysign(m, v);
@@ -329,11 +354,12 @@ __device__ __forceinline__ void rk4_step(const AcPar& a, double* X, double phi_c
     phi += h6 * (k1f + 2.0 * k2f + 2.0 * k3f + k4f);
     v += h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
   }
+  psi = wrap_pi_or_flag(psi, fast_ok);       // a heading outside the wrap's three common cases also goes the generic way
   if (!fast_ok) {                            // NaN compares false: also caught
     rk4_generic_inplace(a, X, phi_c, v_c, dt, nsub);
     return;
   }
-  X[0] = x; X[1] = y; X[2] = wrap_pi(psi); X[3] = phi; X[4] = v;
+  X[0] = x; X[1] = y; X[2] = psi; X[3] = phi; X[4] = v;
 }
 #endif
 

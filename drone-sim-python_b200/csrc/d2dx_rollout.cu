@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kRolloutThreads, D2DX_ROLLOUT_MIN_BLOCKS) roll
     double u_phi, u_v;
     feedback(ref, X, a.g, u_phi, u_v);
     const double ex = X[0] - ref.xr, ey = X[1] - ref.yr, d2 = ex * ex + ey * ey;
-    sum_sq += d2; max_sq = d2 > max_sq ? d2 : max_sq;
+    sum_sq += d2; max_sq = __double_as_longlong(d2) > __double_as_longlong(max_sq) ? d2 : max_sq;   // both >= 0: the integer order is the fp64 order
     const bool log_now = LOGGING && log_in == 0;
     log_in = log_now ? log_every - 1 : log_in - 1;
     if (log_now && active) {

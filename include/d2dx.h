@@ -472,7 +472,9 @@ int d2dx_rollout_pursuit(d2dx_handle* h, const d2dx_pursuit* p, int32_t B, const
  * thread); the caller times it with CUDA events.  sink: device double[1] (keeps the chains alive). */
 int d2dx_dfma_burn(d2dx_handle* h, int32_t blocks, int32_t threads, int32_t iters, double* sink, void* stream);
 /* the engine's straight-line fp64 elementary functions on n argument pairs (x[n], y[n] device):
- * out[7][n] = sin x, cos x, atan2(y, x), atan x, y / x, sqrt|x|, 1/sqrt|x|   (accuracy tests) */
+ * out[11][n] = sin x, cos x, atan2(y, x), atan x, y / x, sqrt|x|, 1/sqrt|x|, 1/x, and the residuals 1 - x y0, 1 - |x| y0^2 of the
+ * hardware reciprocal / reciprocal-square-root seeds the last four start from, and norm_mpi_pi(x) (bit-exact against NumPy's
+ * (x + pi) % (2 pi) - pi)   (accuracy tests) */
 int d2dx_math_probe(d2dx_handle* h, int32_t n, const double* x, const double* y, double* out, void* stream);
 
 #ifdef __cplusplus

@@ -247,15 +247,31 @@ def test_engine_elementary_functions_accuracy(d2d):
     x = np.concatenate([rng.uniform(-8, 8, n // 2), rng.uniform(-1e4, 1e4, n // 4), rng.normal(0, 1e-3, n // 8), rng.normal(0, 50, n // 8)])
     y = rng.normal(0, 5, n) * np.exp(rng.uniform(-6, 6, n))
     x[:8] = [0.4375, -0.4375, 0.6875, 1.1875, 2.4375, 1.0, -1.0, np.pi / 4]
+    # the heading wrap's case boundaries: a = x + pi at 0, -0.0, 2 pi, 4 pi, the neighbouring doubles, a few laps out
+    edge = np.array([-np.pi, np.pi, 3 * np.pi, -3 * np.pi, 5 * np.pi, -5 * np.pi, 0.0, -0.0, 1e-300, -1e-300, 40.0, -40.0, 1e6, -1e6])
+    edge = np.concatenate([edge, np.nextafter(edge, np.inf), np.nextafter(edge, -np.inf), np.nextafter(np.nextafter(edge, -np.inf), -np.inf)])
+    x[8:8 + len(edge)] = edge
+    x[100:4196] = rng.uniform(-4 * np.pi, 4 * np.pi, 4096)
     out = eng.math_probe(eng.to_device(x), eng.to_device(y)).cpu().numpy()
-    ref = [np.sin(x), np.cos(x), np.arctan2(y, x), np.arctan(x), y / x, np.sqrt(np.abs(x)), 1 / np.sqrt(np.abs(x))]
-    names = ["sin", "cos", "atan2", "atan", "div", "sqrt", "rsqrt"]
+    with np.errstate(all="ignore"):
+        ref = [np.sin(x), np.cos(x), np.arctan2(y, x), np.arctan(x), y / x, np.sqrt(np.abs(x)), 1 / np.sqrt(np.abs(x)), 1 / x]
+    names = ["sin", "cos", "atan2", "atan", "div", "sqrt", "rsqrt", "rcp"]
+    wrapped = (x + np.pi) % (2 * np.pi) - np.pi                      # d2d/utils.py:7
+    assert np.array_equal(out[10], wrapped), (x[out[10] != wrapped][:5], out[10][out[10] != wrapped][:5], wrapped[out[10] != wrapped][:5])
+    # the two correction polynomials are truncated for seed residuals of 2^-20 (reciprocal) and 2^-19 (1 - a y^2): the error after
+    # the correction is the cube of that
+    seed = np.abs(out[8:10, 8 + len(edge):]).max(axis=1)
+    print("seed residuals: rcp %.3g rsqrt %.3g (2^-20 = %.3g)" % (seed[0], seed[1], 2.**-20))
+    assert seed[0] < 1.1 * 2.**-20 and seed[1] < 2.**-19, seed
+    keep = np.ones(n, bool); keep[8:8 + len(edge)] = False          # the wrap's edge values are outside the other functions' domains
+    x, y, out = x[keep], y[keep], out[:, keep]
     for k, (r, nm) in enumerate(zip(ref, names)):
+        r = r[keep]
         ulp = np.abs(out[k] - r) / np.spacing(np.abs(r))
         if nm in ("sin", "cos"):            # absolute accuracy near zeros of sin/cos for large |x| is bounded by the 3-term reduction
             ok = (ulp <= 4) | (np.abs(out[k] - r) < 1e-15)
         else:
-            ok = ulp <= 4
+            ok = ulp <= (2 if nm in ('div', 'rcp', 'sqrt', 'rsqrt') else 4)
         assert ok.all(), (nm, float(ulp.max()), x[np.argmax(ulp)], y[np.argmax(ulp)])
         print(nm, "max ulp", float(ulp[ok].max()))
 
