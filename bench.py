@@ -27,12 +27,12 @@ METRIC = "closed-loop aircraft-steps/s"
 UNIT = "aircraft-steps/s"
 # Executed fp64 flop per aircraft-step of rollout_dfff_kernel<CIRCLE> (DADD + DMUL + 2 x DFMA thread-instructions
 # from the ncu capture under profiles/, divided by scenarios x steps); see DESIGN.md "Roofline accounting".
-FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "700"))
-# From the same capture (profiles/r2_rollout_dfff_circle.md, one launch of 1e6 scenarios x 400 steps, log x100 = the default
+FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "672"))
+# From the same capture (profiles/r2f_rollout_dfff_circle.md, one launch of 1e6 scenarios x 400 steps, log x100 = the default
 # bench launch): dram__bytes_read.sum + dram__bytes_write.sum, and the fp64 pipe's active fraction.
-NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 181.31e6 + 325.77e6
+NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 181.16e6 + 323.91e6
 NCU_TRAFFIC_CONFIG = (10 ** 6, 10 ** 4, 100, 25)       # (scenarios, steps, log_every, chunks) the capture was taken at
-NCU_FP64_PIPE_ACTIVE = 0.756
+NCU_FP64_PIPE_ACTIVE = 0.747
 LOG_BYTES_PER_LOGGED_SAMPLE = 56          # 5 state + 2 input doubles
 
 
@@ -193,9 +193,9 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
                 "roofline": {"bound": "hbm", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / dt / 1e9 / hbm_peak,
                              "algorithmic_bytes_per_launch": bytes_alg}}
         if n_ac > 1:       # the pair terms make this launch fp64 / issue work as well: executed fp64 flop from the ncu capture
-            flop = 557.0 * n_ac * N * n_prob                       # profiles/r2_colloc_c4_batch256_allpairs.md (16 aircraft, all pairs)
+            flop = 551.0 * n_ac * N * n_prob                       # profiles/r2f_colloc_c4_batch256_allpairs.md (16 aircraft, all pairs)
             line["roofline"]["fp64"] = {"achieved": flop / dt / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flop / dt / 1e12 / fp64_peak,
-                                        "flop_per_aircraft_node": 557.0}
+                                        "flop_per_aircraft_node": 551.0}
             line["roofline"]["note"] = ("neither roof binds: 1064 warp instructions per warp and aircraft-node at 60 % of the issue slots, 32 resident "
                                         "warps per SM (64 registers, 49 KB of shared memory per block) -- latency of the dependent fp64 chains")
         out[tag] = line
@@ -211,11 +211,11 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
     sync_all()
     dt = max_over_ranks(_timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3))
     # executed fp64 flop per aircraft-step (5 RK4 sub-steps + DCF + GVF), ncu: profiles/r1_final_formation_c2.md
-    flop = 1949.0 * M * (T - 1)
+    flop = 1871.0 * M * (T - 1)                  # profiles/r2f_formation_c2.md
     out["formation_c2_batch"] = {"aircraft_steps_per_s": world * M * (T - 1) / dt, "rk4_substeps_per_s": world * M * (T - 1) * 5 / dt,
                                  "formations_per_gpu": F, "ms_per_launch": dt * 1e3, "sharding": f"by formation x{world}, no collective",
                                  "roofline": {"bound": "fp64", "achieved": flop / dt / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                                              "frac": flop / dt / 1e12 / fp64_peak, "flop_per_aircraft_step": 1949.0}}
+                                              "frac": flop / dt / 1e12 / fp64_peak, "flop_per_aircraft_step": 1871.0}}
     del X0, c, r, ac, Xf
     # (3) ONE C4 problem (and a batch of 64) sharded by aircraft over the ranks: fused peer-memory kernel, CUDA graph
     rng0 = np.random.default_rng(seed)                                # the same problems on every rank
@@ -362,7 +362,7 @@ def secondary_metrics(eng, hbm_peak):
         out["composite_patrol3_batch"] = {"aircraft_steps_per_s": Bc * Tc / dtc, "scenarios": Bc, "steps": Tc, "ms_per_launch": dtc * 1e3,
                                           "kernel": "rollout_dfff_kernel<-1> (generic: composite trajectories, segment table per step)",
                                           "roofline": {"bound": "fp64", "achieved": Bc * Tc * FP64_FLOP_PER_STEP / dtc / 1e12, "unit": "TFLOP/s",
-                                                       "note": "lower bound: counted with the circle kernel's 700 flop per step"}}
+                                                       "note": "lower bound: counted with the circle kernel's executed flop per step"}}
         del tabc, X0d, Wd, Xfc
     except Exception as e:
         out["composite_patrol3_batch"] = {"error": f"{type(e).__name__}: {e}"}
@@ -699,7 +699,7 @@ def main():
                 "peak_probe": probe,
                 "flop_per_aircraft_step": FP64_FLOP_PER_STEP, "kernel_ms": kernel_ms, "steps_per_launch": steps_per_launch,
                 "traffic": NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH if (B, T_steps, args.log_every, args.chunks) == NCU_TRAFFIC_CONFIG else None,
-                "traffic_note": "ncu dram bytes of one launch at the default sizes (profiles/r2_rollout_dfff_circle.md); algorithmic bytes = log_bytes_per_launch",
+                "traffic_note": "ncu dram bytes of one launch at the default sizes (profiles/r2f_rollout_dfff_circle.md); algorithmic bytes = log_bytes_per_launch",
                 "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE, "log_bytes_per_launch": log_bytes,
                 "hbm": {"achieved_gbs": log_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak or 6650.0,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if hbm_peak else "fallback"}}
