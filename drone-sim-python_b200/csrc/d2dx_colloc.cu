@@ -7,6 +7,8 @@
 //   colloc_pairs_kernel    all-pairs collision of one unsharded problem: one warp = one aircraft x 32 nodes, every unordered
 //                          pair evaluated once, its exponential handed to the partner through a write-once shared-memory slot.
 // Every global load and store is coalesced along the node index.
+#include <type_traits>
+
 #include "d2dx_colloc_dev.cuh"
 #include "d2dx_host.h"
 
@@ -137,95 +139,149 @@ __global__ void __launch_bounds__(kCollocThreads, EXTRA ? 5 : 8) colloc_kernel(c
 // Two block barriers, no read-modify-write in shared memory, every sum in a fixed order.
 // REGS: every warp owns at most two aircraft (n_ac <= 16): their phase-A gradients wait in registers, not in shared memory
 // (49 KB per block and 64 registers: four resident blocks = 32 warps per SM instead of 24).
-template <bool REGS>
+// NAC > 0: the aircraft count is a compile-time constant with NAC = 2 kPairWarps (C4's 16 aircraft): every warp owns aircraft w
+// of the lower half and w + NAC / 2 of the upper half, the round counts of both phases are constants, the pair loops unroll
+// completely and every shared-memory access of a pair is base + immediate (no pointer or counter arithmetic per pair).
+template <bool REGS, int NAC = 0>
 __global__ void __launch_bounds__(kPairWarps * 32, REGS ? 4 : 3) colloc_pairs_kernel(const __grid_constant__ CollocArgs a) {
   extern __shared__ double sm[];
   const d2dx_colloc_problem& P = a.p;
-  const int N = P.N, n = P.n_ac, half = n / 2;
+  const int N = P.N, n = NAC ? NAC : P.n_ac, half = n / 2;
   const bool even = (n & 1) == 0;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = NAC ? kPairWarps : blockDim.x >> 5;
   const int tile = blockIdx.x % a.ntiles, prob = blockIdx.x / a.ntiles;
   const int i = tile * 32 + lane;
   const bool valid = i < N;
   const double* fr = a.free_ + (size_t)prob * a.n_free;
-  double* spos = sm + lane;                        // [2n][2][32]
-  double* sE = spos + 2 * n * 64;                  // [half][n][32]
+  // positions: [2n rows of aircraft a and a + n][x, y][1 + 32]: column 0 of a row is the node BEFORE the tile (the backward
+  // difference of node 0 needs it), so the node work reads its previous node from shared memory, not from DRAM again
+  constexpr int R = 33;
+  double* spos = sm + 1 + lane;
+  double* sE = sm + 2 * n * 2 * R + lane;          // [half][n][32]
   double* sg = sE + half * n * 32;                 // [n][2][32]  own-side position gradient of phase A (!REGS)
-  double* sred = sm + (2 * n * 64 + half * n * 32 + (REGS ? 0 : n * 64));   // [W][4]
+  double* sred = sm + (2 * n * 2 * R + half * n * 32 + (REGS ? 0 : n * 64));   // [W][4]
   const bool use_obs = enabled(P.kobs) && P.n_obs > 0;
 
+  // heading, bank and speed of a node are requested ahead of their use -- as L1 prefetches, which hold no registers (keeping the
+  // values live across phase B cost 40 B of spills at the 64-register budget and 5 % of the launch time)
+  auto prefetch = [&](int a_l) {
+    const NodeOff o = colloc_offsets(P, a_l, i);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(fr + o.ox + 2 * N));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(fr + o.ophi));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(fr + o.ov));
+  };
   for (int g = w; g < n; g += W) {
     double x = 0.0, y = 0.0;
-    if (valid) { x = fr[(3 * g) * N + i]; y = fr[(3 * g + 1) * N + i]; }
-    spos[(g * 2) * 32] = x; spos[(g * 2 + 1) * 32] = y;
-    spos[((g + n) * 2) * 32] = x; spos[((g + n) * 2 + 1) * 32] = y;
+    if (valid) { x = fr[(3 * g) * N + i]; y = fr[(3 * g + 1) * N + i]; if (REGS) prefetch(g); }
+    spos[(g * 2) * R] = x; spos[(g * 2 + 1) * R] = y;
+    spos[((g + n) * 2) * R] = x; spos[((g + n) * 2 + 1) * R] = y;
+  }
+  {                                                // halo column of this warp's rows: lane q -> aircraft w + (q / 2) W, component q % 2
+    const int g = w + (lane >> 1) * W, c = lane & 1, ih = tile * 32 - 1;
+    if (g < n) {
+      const double hv = ih >= 0 ? fr[(3 * g + c) * N + ih] : 0.0;
+      sm[(g * 2 + c) * R] = hv; sm[((g + n) * 2 + c) * R] = hv;
+    }
   }
   __syncthreads();
 
   const double sN = a.sN, nkr2 = a.nkr2, cw = a.cw;
   double s_v = 0.0, s_phi = 0.0, s_obs = 0.0, s_col = 0.0;
 
-  auto phase_a = [&](int a_l, double& gx, double& gy) {
-    const double* pa = spos + (a_l * 2) * 32;
-    const double xa = pa[0], ya = pa[32];
+  // `upper` (a std::bool_constant) tells the NAC instantiation which half a_l is in; the generic one ignores it
+  auto phase_a = [&](int a_l, double& gx, double& gy, auto upper) {
+    const double* pa = spos + (a_l * 2) * R;
+    const double xa = pa[0], ya = pa[R];
     gx = 0.0; gy = 0.0;
     if (use_obs && a_l == 0 && valid) obstacle_terms(P, sN, xa, ya, s_obs, gx, gy);
+    if constexpr (NAC > 0) {
+      constexpr int kmax = (NAC % 2 == 0 && decltype(upper)::value) ? NAC / 2 - 1 : NAC / 2;
+      double* e = sE + a_l * 32;
+#pragma unroll
+      for (int k = 1; k <= kmax; ++k) {
+        const double dx = xa - pa[k * 2 * R], dy = ya - pa[k * 2 * R + R];
+        const double es = fm::exp_neg(nkr2 * fma(dx, dx, dy * dy));
+        e[(k - 1) * NAC * 32] = es;
+        s_col += es;
+        const double wgt = cw * es;
+        gx = fma(wgt, dx, gx); gy = fma(wgt, dy, gy);
+      }
+      return;
+    }
     const int kmax = (even && a_l >= half) ? half - 1 : half;
-    const double* pb = pa + 64;                    // partner a_l + 1
+    const double* pb = pa + 2 * R;                 // partner a_l + 1
     double* e = sE + a_l * 32;
 #pragma unroll 4
     for (int k = 1; k <= kmax; ++k) {
-      const double dx = xa - pb[0], dy = ya - pb[32];
+      const double dx = xa - pb[0], dy = ya - pb[R];
       const double es = fm::exp_neg(nkr2 * fma(dx, dx, dy * dy));
       *e = es;
       s_col += es;
       const double wgt = cw * es;
       gx = fma(wgt, dx, gx); gy = fma(wgt, dy, gy);
-      pb += 64; e += n * 32;
+      pb += 2 * R; e += n * 32;
     }
   };
-  auto phase_b = [&](int a_l, double gx, double gy) {
-    const double* pa = spos + ((a_l + n) * 2) * 32;
-    const double xa = pa[0], ya = pa[32];
+  auto phase_b = [&](int a_l, double gx, double gy, auto upper) {
+    const double* pa = spos + ((a_l + n) * 2) * R;
+    const double xa = pa[0], ya = pa[R];
+    if constexpr (NAC > 0) {
+      constexpr bool up = decltype(upper)::value;
+      constexpr int kmax = (NAC % 2 == 0 && !up) ? NAC / 2 - 1 : NAC / 2;
+      // slot of round k: sE[(k-1) n + a_l - k], n entries further when a_l - k wraps below 0 -- never for the upper half
+      // (a_l >= NAC / 2 >= k), one select per round for the lower half
+      const double* pe = sE + (a_l - 1) * 32;
+#pragma unroll
+      for (int k = 1; k <= kmax; ++k) {
+        const double* q = (!up && k > a_l) ? pe + NAC * 32 : pe;
+        const double wgt = cw * q[(k - 1) * (NAC - 1) * 32];
+        gx = fma(wgt, xa - pa[-k * 2 * R], gx); gy = fma(wgt, ya - pa[-k * 2 * R + R], gy);
+      }
+    } else {
     const int kmax = (even && a_l < half) ? half - 1 : half;
-    const double* pb = pa - 64;                    // partner a_l - 1 (upper copy: no wrap)
+    const double* pb = pa - 2 * R;                 // partner a_l - 1 (upper copy: no wrap)
     // the slot of round k was written by aircraft a_l - k (mod n): sE[(k-1) n + a_l - k] while a_l - k >= 0, n entries
     // further once it wraps -- two runs with the same constant stride instead of a modulo per pair
     const int k1 = kmax < a_l ? kmax : a_l;
     const int stride = (n - 1) * 32;
     const double* pe = sE + (a_l - 1) * 32;
 #pragma unroll 4
-    for (int k = 1; k <= k1; ++k, pe += stride, pb -= 64) {
+    for (int k = 1; k <= k1; ++k, pe += stride, pb -= 2 * R) {
       const double wgt = cw * pe[0];
-      gx = fma(wgt, xa - pb[0], gx); gy = fma(wgt, ya - pb[32], gy);
+      gx = fma(wgt, xa - pb[0], gx); gy = fma(wgt, ya - pb[R], gy);
     }
     pe += n * 32;
 #pragma unroll 4
-    for (int k = k1 + 1; k <= kmax; ++k, pe += stride, pb -= 64) {
+    for (int k = k1 + 1; k <= kmax; ++k, pe += stride, pb -= 2 * R) {
       const double wgt = cw * pe[0];
-      gx = fma(wgt, xa - pb[0], gx); gy = fma(wgt, ya - pb[32], gy);
+      gx = fma(wgt, xa - pb[0], gx); gy = fma(wgt, ya - pb[R], gy);
     }
-    if (valid) colloc_node(a, fr, prob, a_l, i, xa, ya, gx, gy, true, s_v, s_phi);
+    }
+    if (valid) {                                   // 32-bit flat output indices: launch_eval checks
+      const NodeOff o = colloc_offsets(P, a_l, i);
+      const NodeIn in = {fr[o.ox + 2 * N], fr[o.ophi], fr[o.ov], pa[-1], pa[R - 1], i >= 1 ? fr[o.ox + 2 * N - 1] : 0.0};
+      colloc_node_in<true, true>(a, prob, a_l, i, xa, ya, in, o, gx, gy, true, s_v, s_phi);
+    }
   };
 
   if (REGS) {
     const bool h0 = w < n, h1 = w + W < n;
     double gx0 = 0.0, gy0 = 0.0, gx1 = 0.0, gy1 = 0.0;
-    if (h0) phase_a(w, gx0, gy0);
-    if (h1) phase_a(w + W, gx1, gy1);
+    if (h0) phase_a(w, gx0, gy0, std::false_type{});
+    if (h1) phase_a(w + W, gx1, gy1, std::true_type{});
     if (!valid) s_col = 0.0;                       // overhanging lanes of the last tile evaluated zeros
     __syncthreads();
-    if (h0) phase_b(w, gx0, gy0);
-    if (h1) phase_b(w + W, gx1, gy1);
+    if (h0) phase_b(w, gx0, gy0, std::false_type{});
+    if (h1) phase_b(w + W, gx1, gy1, std::true_type{});
   } else {
     for (int a_l = w; a_l < n; a_l += W) {
       double gx, gy;
-      phase_a(a_l, gx, gy);
+      phase_a(a_l, gx, gy, std::false_type{});
       sg[(a_l * 2) * 32] = gx; sg[(a_l * 2 + 1) * 32] = gy;
     }
     if (!valid) s_col = 0.0;
     __syncthreads();
-    for (int a_l = w; a_l < n; a_l += W) phase_b(a_l, sg[(a_l * 2) * 32], sg[(a_l * 2 + 1) * 32]);
+    for (int a_l = w; a_l < n; a_l += W) phase_b(a_l, sg[(a_l * 2) * 32], sg[(a_l * 2 + 1) * 32], std::false_type{});
   }
 
   if (tile == 0) {                                 // instance constraints: first tile of each problem
@@ -250,7 +306,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, REGS ? 4 : 3) colloc_pairs_ke
 
 static size_t pairs_smem_bytes(int n) {
   const bool regs = n <= 2 * kPairWarps;
-  return ((size_t)(2 * n * 64 + (n / 2) * n * 32 + (regs ? 0 : n * 64)) + kPairWarps * 4) * sizeof(double);
+  return ((size_t)(2 * n * 2 * 33 + (n / 2) * n * 32 + (regs ? 0 : n * 64)) + kPairWarps * 4) * sizeof(double);
 }
 
 
@@ -425,11 +481,13 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
   const bool obs = want_cg && enabled_h(p->kobs) && p->n_obs > 0;
   cudaStream_t st = as_stream(stream);
   const bool all_pairs_local = col && p->col_all_pairs && pos_all == nullptr;
-  if (all_pairs_local && pairs_smem_bytes(p->n_ac) <= 200 * 1024) {
+  const long per_max = a.nnz > a.n_free ? a.nnz : a.n_free;                    // n_con < n_free
+  const bool idx32 = (long)n_prob * per_max < (1L << 31);
+  if (all_pairs_local && idx32 && pairs_smem_bytes(p->n_ac) <= 200 * 1024) {
     a.TN = 32; a.APP = kPairWarps; a.ntiles = (p->N + 31) / 32; a.nparts = a.ntiles;
     const size_t smem = pairs_smem_bytes(p->n_ac);
     const bool regs = p->n_ac <= 2 * kPairWarps;
-    auto kern = regs ? colloc_pairs_kernel<true> : colloc_pairs_kernel<false>;
+    auto kern = p->n_ac == 2 * kPairWarps ? colloc_pairs_kernel<true, 2 * kPairWarps> : regs ? colloc_pairs_kernel<true> : colloc_pairs_kernel<false>;
     if (smem > 48 * 1024) D2DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int warps = p->n_ac < kPairWarps ? p->n_ac : kPairWarps;
     kern<<<(unsigned)((long)n_prob * a.ntiles), warps * 32, smem, st>>>(a);

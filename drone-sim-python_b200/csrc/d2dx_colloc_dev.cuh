@@ -59,37 +59,50 @@ __device__ __forceinline__ void obstacle_terms(const d2dx_colloc_problem& P, dou
 
 // inputs of one (aircraft, node) beyond its position: heading, bank, speed and the previous node's x, y, psi
 struct NodeIn { double psi, phi, v, xp, yp, pp; };
+// offsets of the node's x, bank and speed entries inside one problem's free vector (5 n_ac N entries: they fit 32 bits)
+struct NodeOff { int ox, ophi, ov; };
 
-__device__ __forceinline__ void colloc_offsets(const d2dx_colloc_problem& P, int a_l, int i, int& ox, int& ophi, int& ov) {
+__device__ __forceinline__ NodeOff colloc_offsets(const d2dx_colloc_problem& P, int a_l, int i) {
   const int N = P.N, n_ac = P.n_ac, n = 3 * n_ac;
   const int bphi = P.perm_phi ? P.perm_phi[a_l] : a_l;
   const int bv = P.perm_v ? P.perm_v[a_l] : n_ac + a_l;
-  ox = 3 * a_l * N + i; ophi = (n + bphi) * N + i; ov = (n + bv) * N + i;
+  NodeOff o;
+  o.ox = 3 * a_l * N + i; o.ophi = (n + bphi) * N + i; o.ov = (n + bv) * N + i;
+  return o;
 }
 
-__device__ __forceinline__ NodeIn colloc_load(const CollocArgs& a, const double* __restrict__ fr, int a_l, int i) {
-  int ox, ophi, ov;
-  colloc_offsets(a.p, a_l, i, ox, ophi, ov);
+__device__ __forceinline__ NodeIn colloc_load(const CollocArgs& a, const double* __restrict__ fr, const NodeOff& o, int i) {
   const int N = a.p.N;
   NodeIn in;
-  in.psi = fr[ox + 2 * N]; in.phi = fr[ophi]; in.v = fr[ov];
+  in.psi = fr[o.ox + 2 * N]; in.phi = fr[o.ophi]; in.v = fr[o.ov];
   in.xp = in.yp = in.pp = 0.0;
-  if ((a.what & D2DX_EVAL_RESIDUAL) && i >= 1) { in.xp = fr[ox - 1]; in.yp = fr[ox + N - 1]; in.pp = fr[ox + 2 * N - 1]; }
+  if ((a.what & D2DX_EVAL_RESIDUAL) && i >= 1) { in.xp = fr[o.ox - 1]; in.yp = fr[o.ox + N - 1]; in.pp = fr[o.ox + 2 * N - 1]; }
   return in;
+}
+
+// element `off` of problem `prob` in an output array with `per` elements per problem.  IDX32: the whole batch of that array has
+// fewer than 2^31 elements (the launcher checks), so one 32-bit multiply-add and one widening add replace the 64-bit index chain
+template <bool IDX32>
+__device__ __forceinline__ double* colloc_out(double* base, int prob, long per, int off) {
+  if (IDX32) return base + static_cast<unsigned>(prob * static_cast<int>(per) + off);
+  return base + ((size_t)prob * per + off);
+}
+// base + k * stride doubles as ONE widening multiply-add (k is a compile-time constant after unrolling)
+__device__ __forceinline__ double* colloc_row(double* base, int stride, int k) {
+  double* r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(stride), "r"(8 * k), "l"(base));
+  return r;
 }
 
 // One (aircraft a_l, node i < N) of problem `prob`: backward-Euler defects (equation-major, opty layout), the 12 structural
 // Jacobian entries (compact or opty-dense), the input cost sums and every gradient entry of the node; (gx, gy) = the
 // position gradient the caller accumulated (obstacles, collisions; STORE_XY = false leaves those two entries to the caller).
-// Offsets inside one problem fit 32 bits.
-template <bool STORE_XY = true>
+template <bool STORE_XY = true, bool IDX32 = false>
 __device__ __forceinline__ void colloc_node_in(const CollocArgs& a, int prob, int a_l, int i, double x, double y, const NodeIn& in,
-                                               double gx, double gy, bool want_cg, double& s_v, double& s_phi) {
+                                               const NodeOff& o, double gx, double gy, bool want_cg, double& s_v, double& s_phi) {
   const d2dx_colloc_problem& P = a.p;
   const int N = P.N, n_ac = P.n_ac, n = 3 * n_ac;
-  int ox, ophi, ov;
-  colloc_offsets(P, a_l, i, ox, ophi, ov);
-  const int oy = ox + N, ops = oy + N;
+  const int ox = o.ox, ophi = o.ophi, ov = o.ov, oy = ox + N, ops = oy + N;
   const double psi = in.psi, phi = in.phi, v = in.v;
 
   if ((a.what & (D2DX_EVAL_RESIDUAL | D2DX_EVAL_JAC)) && i >= 1) {
@@ -101,17 +114,17 @@ __device__ __forceinline__ void colloc_node_in(const CollocArgs& a, int prob, in
     const double tn = sp * rcp_f(cp);            // tan(phi)
     const double gtv = kG * tn * iv;             // g tan(phi) / v
     if (a.what & D2DX_EVAL_RESIDUAL) {           // equation-major, node-minor (opty layout)
-      double* r = a.res + (size_t)prob * a.n_con + (3 * a_l * (N - 1) + (i - 1));
+      double* r = colloc_out<IDX32>(a.res, prob, a.n_con, 3 * a_l * (N - 1) + (i - 1));
       r[0] = (x - in.xp) * ih - v * c + P.wind[0];
-      r[N - 1] = (y - in.yp) * ih - v * s + P.wind[1];
-      r[2 * (N - 1)] = (psi - in.pp) * ih - gtv;
+      *colloc_row(r, N - 1, 1) = (y - in.yp) * ih - v * s + P.wind[1];
+      *colloc_row(r, N - 1, 2) = (psi - in.pp) * ih - gtv;
     }
     if (a.what & D2DX_EVAL_JAC) {
       const double j[12] = {ih, v * s, -ih, -c, ih, -v * c, -ih, -s, ih, -ih, -kG * fma(tn, tn, 1.0) * iv, gtv * iv};
       if (a.layout == D2DX_JAC_COMPACT) {        // [n_ac][12][N-1]: coalesced along the node
-        double* jo = a.jac + (size_t)prob * a.nnz + (a_l * 12 * (N - 1) + (i - 1));
+        double* jo = colloc_out<IDX32>(a.jac, prob, a.nnz, a_l * 12 * (N - 1) + (i - 1));
 #pragma unroll
-        for (int k = 0; k < 12; ++k) jo[k * (N - 1)] = j[k];
+        for (int k = 0; k < 12; ++k) *colloc_row(jo, N - 1, k) = j[k];
       } else {                                   // opty-dense: [(N-1)][3 n_ac][8 n_ac]
         const int bphi = P.perm_phi ? P.perm_phi[a_l] : a_l, bv = P.perm_v ? P.perm_v[a_l] : n_ac + a_l;
         const int q = 2 * n_ac, W = 2 * n + q;
@@ -134,7 +147,7 @@ __device__ __forceinline__ void colloc_node_in(const CollocArgs& a, int prob, in
     s_v += dv * dv; s_phi += phi * phi;
     if (a.what & D2DX_EVAL_GRAD) {
       const double norm_in = a.norm_in;
-      double* go = a.grad + (size_t)prob * a.n_free;
+      double* go = colloc_out<IDX32>(a.grad, prob, a.n_free, 0);
       if (STORE_XY) { go[ox] = gx; go[oy] = gy; }
       go[ops] = 0.0;
       go[ophi] = (P.kbank * 2.0 * phi) * norm_in;
@@ -143,11 +156,12 @@ __device__ __forceinline__ void colloc_node_in(const CollocArgs& a, int prob, in
   }
 }
 
-template <bool STORE_XY = true>
+template <bool STORE_XY = true, bool IDX32 = false>
 __device__ __forceinline__ void colloc_node(const CollocArgs& a, const double* __restrict__ fr, int prob, int a_l, int i,
                                             double x, double y, double gx, double gy, bool want_cg, double& s_v, double& s_phi) {
-  const NodeIn in = colloc_load(a, fr, a_l, i);
-  colloc_node_in<STORE_XY>(a, prob, a_l, i, x, y, in, gx, gy, want_cg, s_v, s_phi);
+  const NodeOff o = colloc_offsets(a.p, a_l, i);
+  const NodeIn in = colloc_load(a, fr, o, i);
+  colloc_node_in<STORE_XY, IDX32>(a, prob, a_l, i, x, y, in, o, gx, gy, want_cg, s_v, s_phi);
 }
 
 // cost of one problem from the four summed partials (CostComposit, multiopty_utils.py:156-174 / opty_utils.py:147-165)

@@ -150,7 +150,7 @@ __device__ __forceinline__ void sincos_small(double d, double& s, double& c) {
 }
 
 // exp(y) for y <= 0 (Gaussian-type penalties): k = rint(y log2 e), r = y - k ln2 (two-term), degree-13 Taylor polynomial
-// on |r| <= ln2/2 (truncation 4e-18 relative), scaling through the exponent field; flushes to 0 below 2^-1000.
+// on |r| <= ln2/2 (truncation 4e-18 relative), scaling through the exponent field (saturating at 2^-1000).
 // The polynomial is evaluated by Estrin's scheme: 16 fp64 instructions instead of Horner's 13, but a dependency depth of 5
 // instead of 13 -- the collision kernels are bound by the latency of this chain, not by its instruction count.
 __device__ __forceinline__ double exp_neg(double y) {
@@ -172,9 +172,10 @@ __device__ __forceinline__ double exp_neg(double y) {
   const double r8 = r4 * r4;
   const double s0 = fma(q1, r4, q0), s1 = fma(pcd, r4, q2);
   const double p = fma(s1, r8, s0);
-  const int hi = __double2hiint(p) + (k << 20);
-  const double v = __hiloint2double(hi, __double2loint(p));
-  return (k < -1000) ? 0.0 : v;
+  // exponent clamped at -1000 instead of a compare and two selects: below e^-693 the result is p 2^-1000 ~ 1e-301 rather than
+  // the true (sub-1e-301) value -- the same thing to every sum these penalties enter
+  const int hi = __double2hiint(p) + (max(k, -1000) << 20);
+  return __hiloint2double(hi, __double2loint(p));
 }
 
 // atan(num/den) for den > 0 ... folded into atan2 below: one division in total.
