@@ -193,10 +193,10 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
                 "roofline": {"bound": "hbm", "achieved": bytes_alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / dt / 1e9 / hbm_peak,
                              "algorithmic_bytes_per_launch": bytes_alg}}
         if n_ac > 1:       # the pair terms make this launch fp64 / issue work as well: executed fp64 flop from the ncu capture
-            flop = 551.0 * n_ac * N * n_prob                       # profiles/r2f_colloc_c4_batch256_allpairs.md (16 aircraft, all pairs)
+            flop = 548.0 * n_ac * N * n_prob                       # profiles/r2h_colloc_c4_batch256_allpairs.md (16 aircraft, all pairs)
             line["roofline"]["fp64"] = {"achieved": flop / dt / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flop / dt / 1e12 / fp64_peak,
-                                        "flop_per_aircraft_node": 551.0}
-            line["roofline"]["note"] = ("neither roof binds: 1064 warp instructions per warp and aircraft-node at 60 % of the issue slots, 32 resident "
+                                        "flop_per_aircraft_node": 548.0}
+            line["roofline"]["note"] = ("neither roof binds: 847 warp instructions per warp and aircraft-node at 56 % of the issue slots, 32 resident "
                                         "warps per SM (64 registers, 49 KB of shared memory per block) -- latency of the dependent fp64 chains")
         out[tag] = line
         del prob, free, bufs

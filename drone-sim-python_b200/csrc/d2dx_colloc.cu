@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(kPairWarps * 32, REGS ? 4 : 3) colloc_pairs_ke
   const int N = P.N, n = NAC ? NAC : P.n_ac, half = n / 2;
   const bool even = (n & 1) == 0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = NAC ? kPairWarps : blockDim.x >> 5;
-  const int tile = blockIdx.x % a.ntiles, prob = blockIdx.x / a.ntiles;
+  // grid (tiles, problems); one-dimensional (tile fastest) only beyond 65535 problems: no integer division per thread
+  const bool grid2 = gridDim.x == (unsigned)a.ntiles;
+  const int tile = grid2 ? blockIdx.x : blockIdx.x % a.ntiles, prob = grid2 ? blockIdx.y : blockIdx.x / a.ntiles;
   const int i = tile * 32 + lane;
   const bool valid = i < N;
   const double* fr = a.free_ + (size_t)prob * a.n_free;
@@ -490,7 +492,8 @@ static int launch_eval(d2dx_handle* h, const d2dx_colloc_problem* p, int n_prob,
     auto kern = p->n_ac == 2 * kPairWarps ? colloc_pairs_kernel<true, 2 * kPairWarps> : regs ? colloc_pairs_kernel<true> : colloc_pairs_kernel<false>;
     if (smem > 48 * 1024) D2DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int warps = p->n_ac < kPairWarps ? p->n_ac : kPairWarps;
-    kern<<<(unsigned)((long)n_prob * a.ntiles), warps * 32, smem, st>>>(a);
+    const dim3 grid = n_prob <= 65535 ? dim3((unsigned)a.ntiles, (unsigned)n_prob) : dim3((unsigned)((long)n_prob * a.ntiles));
+    kern<<<grid, warps * 32, smem, st>>>(a);
     D2DX_LAUNCH_CHECK("colloc_pairs_kernel");
   } else {
     tile_shape(p->n_ac, a.TN, a.APP);

@@ -87,13 +87,6 @@ __device__ __forceinline__ double* colloc_out(double* base, int prob, long per, 
   if (IDX32) return base + static_cast<unsigned>(prob * static_cast<int>(per) + off);
   return base + ((size_t)prob * per + off);
 }
-// base + k * stride doubles as ONE widening multiply-add (k is a compile-time constant after unrolling)
-__device__ __forceinline__ double* colloc_row(double* base, int stride, int k) {
-  double* r;
-  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(stride), "r"(8 * k), "l"(base));
-  return r;
-}
-
 // One (aircraft a_l, node i < N) of problem `prob`: backward-Euler defects (equation-major, opty layout), the 12 structural
 // Jacobian entries (compact or opty-dense), the input cost sums and every gradient entry of the node; (gx, gy) = the
 // position gradient the caller accumulated (obstacles, collisions; STORE_XY = false leaves those two entries to the caller).
@@ -107,6 +100,7 @@ __device__ __forceinline__ void colloc_node_in(const CollocArgs& a, int prob, in
 
   if ((a.what & (D2DX_EVAL_RESIDUAL | D2DX_EVAL_JAC)) && i >= 1) {
     const double ih = a.ih;
+    const int nm1 = N - 1;
     double s, c, sp, cp;
     sincos_any(psi, s, c);
     sincos_any(phi, sp, cp);
@@ -116,15 +110,15 @@ __device__ __forceinline__ void colloc_node_in(const CollocArgs& a, int prob, in
     if (a.what & D2DX_EVAL_RESIDUAL) {           // equation-major, node-minor (opty layout)
       double* r = colloc_out<IDX32>(a.res, prob, a.n_con, 3 * a_l * (N - 1) + (i - 1));
       r[0] = (x - in.xp) * ih - v * c + P.wind[0];
-      *colloc_row(r, N - 1, 1) = (y - in.yp) * ih - v * s + P.wind[1];
-      *colloc_row(r, N - 1, 2) = (psi - in.pp) * ih - gtv;
+      r[nm1] = (y - in.yp) * ih - v * s + P.wind[1];
+      r[2 * nm1] = (psi - in.pp) * ih - gtv;
     }
     if (a.what & D2DX_EVAL_JAC) {
       const double j[12] = {ih, v * s, -ih, -c, ih, -v * c, -ih, -s, ih, -ih, -kG * fma(tn, tn, 1.0) * iv, gtv * iv};
       if (a.layout == D2DX_JAC_COMPACT) {        // [n_ac][12][N-1]: coalesced along the node
         double* jo = colloc_out<IDX32>(a.jac, prob, a.nnz, a_l * 12 * (N - 1) + (i - 1));
 #pragma unroll
-        for (int k = 0; k < 12; ++k) *colloc_row(jo, N - 1, k) = j[k];
+        for (int k = 0; k < 12; ++k) jo[k * nm1] = j[k];
       } else {                                   // opty-dense: [(N-1)][3 n_ac][8 n_ac]
         const int bphi = P.perm_phi ? P.perm_phi[a_l] : a_l, bv = P.perm_v ? P.perm_v[a_l] : n_ac + a_l;
         const int q = 2 * n_ac, W = 2 * n + q;
