@@ -404,3 +404,42 @@ def test_new_entry_points_reject_bad_arguments():
         eng.ddp_solve(one.c, 1, (0.5, -0.5, 9., 14.), None, eng.zeros(1, 3), eng.zeros(1, 3), eng.zeros(1, 2, 10), eng.zeros(1, 3, 10), eng.zeros(1, 8))
     with pytest.raises(_lib.D2dxError):
         eng.cost_bank_max(eng.zeros(1, 50), 45, 10, 1.0)                           # phi slice runs past the free vector
+
+
+def test_sixteen_aircraft_instantiation_with_opty_order_and_partial_calls():
+    """The 16-aircraft instantiation of colloc_pairs_kernel (compile-time round counts, halo column, prefetched node inputs)
+    under opty's name-sorted input order (phi10 .. phi15 before phi2): equal to the numeric-order problem on the permuted free
+    vector, equal to the oracle, and consistent between fused and partial (residual only / Jacobian only / gradient only)
+    calls; N = 70 leaves a ragged last tile and a first tile whose halo column is unused."""
+    from oracle import d2d_oracle as orc
+    from d2d_b200.collocation import CollocationProblem, CostSpec
+    n_ac, N, h, n_prob = 16, 70, 0.05, 3
+    rng = np.random.default_rng(16)
+    free = rng.normal(0, 6., (n_prob, 5 * n_ac * N)); free[:, 4 * n_ac * N:] = 12 + rng.normal(0, 1, (n_prob, n_ac * N))
+    cs = CostSpec(vsp=12., kvel=3., kbank=2., kcol=10., rcol=8., all_pairs=True, kobs=1.5, obstacles=[(1., 2., 6.)], obs_kind=1)
+    inst = [(k, 0, 0.5 * k) for k in range(3 * n_ac)]
+    a = CollocationProblem(n_ac, N, h, wind=(1., 2.), inst=inst, cost=cs)
+    b = CollocationProblem(n_ac, N, h, wind=(1., 2.), inst=inst, cost=cs, input_order="opty")
+    numeric = [f"phi{i}(t)" for i in range(n_ac)] + [f"v{i}(t)" for i in range(n_ac)]
+    names = sorted(numeric)                                     # opty sorts the input symbols by name
+    src = [numeric.index(nm) for nm in names]
+    fp = free.copy()
+    for k, s_ in enumerate(src):
+        fp[:, (3 * n_ac + k) * N:(3 * n_ac + k + 1) * N] = free[:, (3 * n_ac + s_) * N:(3 * n_ac + s_ + 1) * N]
+    ra, ja, ca, ga = a.evaluate(free)
+    rb, jb, cb, gb = b.evaluate(fp)
+    np.testing.assert_array_equal(ra, rb); np.testing.assert_array_equal(ja, jb); np.testing.assert_array_equal(ca, cb)
+    np.testing.assert_array_equal(gb[:, :3 * n_ac * N], ga[:, :3 * n_ac * N])
+    for k, s_ in enumerate(src):
+        np.testing.assert_array_equal(gb[:, (3 * n_ac + k) * N:(3 * n_ac + k + 1) * N], ga[:, (3 * n_ac + s_) * N:(3 * n_ac + s_ + 1) * N])
+    spec = dict(vsp=12., kvel=3., kbank=2., kcol=10., rcol=8., pairs="all", kobs=1.5, obstacles=[(1., 2., 6.)], obs_kind=1)
+    for p in range(n_prob):
+        np.testing.assert_allclose(ra[p], orc.colloc_residual(free[p], N, n_ac, h, (1., 2.), inst), rtol=RTOL, atol=1e-10)
+        np.testing.assert_allclose(ja[p][:-len(inst)], orc.colloc_jac_compact(free[p], N, n_ac, h).reshape(-1), rtol=RTOL)
+        co, go = orc.cost_and_grad(free[p], N, n_ac, spec, multi=True)
+        np.testing.assert_allclose(ca[p], co, rtol=RTOL)
+        np.testing.assert_allclose(ga[p], go, rtol=RTOL, atol=1e-13)
+    np.testing.assert_array_equal(a.con(free), ra)
+    np.testing.assert_array_equal(a.con_jac(free), ja)
+    np.testing.assert_array_equal(a.obj(free), ca)
+    np.testing.assert_array_equal(a.obj_grad(free), ga)
