@@ -29,8 +29,10 @@ __device__ __forceinline__ void sincos_b(double x, double& s, double& c) { fm::s
 struct SinCos { double s, c; };
 static __device__ __noinline__ SinCos sincos_slow(double x) { SinCos r; ::sincos(x, &r.s, &r.c); return r; }
 __device__ __forceinline__ void sincos_any(double x, double& s, double& c) {
-  if ((__double2hiint(x) & 0x7fffffff) < 0x40F86A00) fm::sincos(x, s, c);      // |x| < 1e5, decided on the high word (0x40F86A00 = hi(1e5))
-  else { const SinCos r = sincos_slow(x); s = r.s; c = r.c; }
+  // the straight-line path runs unconditionally (its block joins the caller's: the scheduler may interleave it with independent
+  // work); |x| >= 1e5 -- decided on the high word, 0x40F86A00 = hi(1e5) -- is redone out of line afterwards
+  fm::sincos(x, s, c);
+  if ((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00) { const SinCos r = sincos_slow(x); s = r.s; c = r.c; }
 }
 __device__ __forceinline__ double atan2_f(double y, double x) { return fm::atan2(y, x); }
 __device__ __forceinline__ double atan_f(double v) { return fm::atan(v); }
@@ -471,41 +473,39 @@ __host__ __device__ __forceinline__ bool care_gain(const CareConst& cc, double v
   const double c1q = c1 * cc.sq;                                   // c1 = sqrt(r1)/b1, e = b2 c1
   CareStep k;
   k.k1 = c1q * cc.isr2; k.ba = e * cc.isr2; k.vc2 = v * cc.sr2; k.ve = v * e; k.k2 = 2.0 * v * c1q; k.q3 = cc.q3;
-  double C = st.C, S = st.S, al = st.al;
-  bool ok;
-  if (cold) {
-    C = 0.0; S = 1.0; al = sqrt_f(cc.q3 + k.k2);                   // decoupled (b2 = 0) solution
-    ok = care_newton_loop(k, C, S, al, 60);
-    st.dth = 0.0; st.dal = 0.0;
-  } else {
-    const double C0 = C, S0 = S, al0 = al;
-    care_update(C, S, al, st.dth, st.dal);                         // extrapolate
-    double be, F1, F2;
-    care_residual(k, C, S, al, be, F1, F2);
-    const double bt = -k.k1 * S;
-    const double J11 = fma(-S, al, fma(C, be, fma(S, bt, fma(k.ve, C, -k.vc2 * S)))), J12 = fma(S, k.ba, C);
-    const double J21 = 2.0 * fma(be, bt, -0.5 * k.k2 * C), J22 = 2.0 * fma(be, k.ba, al);
-    const double idet = rcp_f(fma(J11, J22, -J12 * J21));
-    const double i11 = J22 * idet, i12 = -J12 * idet, i21 = -J21 * idet, i22 = J11 * idet;   // J^-1
-    double dth = -fma(i11, F1, i12 * F2), dal = -fma(i21, F1, i22 * F2);
-    care_update(C, S, al, dth, dal);                               // Newton step
-    care_residual(k, C, S, al, be, F1, F2);
-    dth = -fma(i11, F1, i12 * F2); dal = -fma(i21, F1, i22 * F2);
-    care_update(C, S, al, dth, dal);                               // chord step
-    // accept when the chord step is tiny AND the root is on the stabilising branch (S > 0, al > 0 there: kappa_2's
-    // first component and K_13 are positive for every v, b1 > 0)
-    // (sign tests and the fixed threshold on the integer pipe: hi word of 3e-8 = 0x3E601B2B; S, al > 0 <=> sign bit clear, not zero)
-    ok = (hi_word(dth) & 0x7fffffff) < 0x3E601B2B && fabs(dal) < 3e-8 * fabs(al) && hi_word(S) > 0 && hi_word(al) > 0;
-    if (!ok) {                                                     // corner of the reference, big jump: iterate from the
+  // The warm path runs unconditionally and in straight-line code (a cold state -- C = 0, S = 1, al = 1 -- only produces numbers
+  // that are thrown away): its instructions share one block with the flatness / arctangent work before it, and ONE branch
+  // afterwards takes the cold start, a failed acceptance test and the restart.
+  const double C0 = st.C, S0 = st.S, al0 = st.al;
+  double C = C0, S = S0, al = al0;
+  care_update(C, S, al, st.dth, st.dal);                           // extrapolate
+  double be_, F1, F2;
+  care_residual(k, C, S, al, be_, F1, F2);
+  const double bt = -k.k1 * S;
+  const double J11 = fma(-S, al, fma(C, be_, fma(S, bt, fma(k.ve, C, -k.vc2 * S)))), J12 = fma(S, k.ba, C);
+  const double J21 = 2.0 * fma(be_, bt, -0.5 * k.k2 * C), J22 = 2.0 * fma(be_, k.ba, al);
+  const double idet = rcp_f(fma(J11, J22, -J12 * J21));
+  const double i11 = J22 * idet, i12 = -J12 * idet, i21 = -J21 * idet, i22 = J11 * idet;   // J^-1
+  double dth = -fma(i11, F1, i12 * F2), dal = -fma(i21, F1, i22 * F2);
+  care_update(C, S, al, dth, dal);                                 // Newton step
+  care_residual(k, C, S, al, be_, F1, F2);
+  dth = -fma(i11, F1, i12 * F2); dal = -fma(i21, F1, i22 * F2);
+  care_update(C, S, al, dth, dal);                                 // chord step
+  // accept when the chord step is tiny AND the root is on the stabilising branch (S > 0, al > 0 there: kappa_2's
+  // first component and K_13 are positive for every v, b1 > 0)
+  // (sign tests and the fixed threshold on the integer pipe: hi word of 3e-8 = 0x3E601B2B; S, al > 0 <=> sign bit clear, not zero)
+  bool ok = !cold && (hi_word(dth) & 0x7fffffff) < 0x3E601B2B && fabs(dal) < 3e-8 * fabs(al) && hi_word(S) > 0 && hi_word(al) > 0;
+  if (!ok) {
+    if (!cold) {                                                   // corner of the reference, big jump: iterate from the
       C = C0; S = S0; al = al0;                                    // previous solution, not from the failed extrapolation
       ok = care_newton_loop(k, C, S, al, 40) && S > 0.0 && al > 0.0;
     }
-    if (!ok) { C = 0.0; S = 1.0; al = sqrt_f(cc.q3 + k.k2); ok = care_newton_loop(k, C, S, al, 60); }   // restart cold once
-    // change over this control step (angle from the cross product of the unit vectors); only a small, smooth change
-    // is worth extrapolating
-    st.dth = fma(C0, S, -S0 * C); st.dal = al - al0;
-    if (!((hi_word(st.dth) & 0x7fffffff) < 0x3F947AE1 && fabs(st.dal) < 0.02 * al)) { st.dth = 0.0; st.dal = 0.0; }   // hi(0.02)
+    if (!ok) { C = 0.0; S = 1.0; al = sqrt_f(cc.q3 + k.k2); ok = care_newton_loop(k, C, S, al, 60); }   // cold start: decoupled (b2 = 0) solution
   }
+  // change over this control step (angle from the cross product of the unit vectors); only a small, smooth change is worth
+  // extrapolating -- and none after a cold start
+  st.dth = fma(C0, S, -S0 * C); st.dal = al - al0;
+  if (cold || !((hi_word(st.dth) & 0x7fffffff) < 0x3F947AE1 && fabs(st.dal) < 0.02 * al)) { st.dth = 0.0; st.dal = 0.0; }   // hi(0.02)
   st.C = C; st.S = S; st.al = al;
   const double be = fma(k.k1, C, k.ba * al);
   K0[0] = cc.sq * C * cc.isr1; K0[1] = cc.sq * S * cc.isr1; K0[2] = al * cc.isr1;
