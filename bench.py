@@ -28,11 +28,11 @@ UNIT = "aircraft-steps/s"
 # Executed fp64 flop per aircraft-step of rollout_dfff_kernel<CIRCLE> (DADD + DMUL + 2 x DFMA thread-instructions
 # from the ncu capture under profiles/, divided by scenarios x steps); see DESIGN.md "Roofline accounting".
 FP64_FLOP_PER_STEP = float(os.environ.get("D2DX_FLOP_PER_STEP", "672"))
-# From the same capture (profiles/r2f_rollout_dfff_circle.md, one launch of 1e6 scenarios x 400 steps, log x100 = the default
+# From the same capture (profiles/r2i_rollout_dfff_circle.md, one launch of 1e6 scenarios x 400 steps, log x100 = the default
 # bench launch): dram__bytes_read.sum + dram__bytes_write.sum, and the fp64 pipe's active fraction.
-NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 181.16e6 + 323.91e6
+NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH = 181.10e6 + 323.17e6
 NCU_TRAFFIC_CONFIG = (10 ** 6, 10 ** 4, 100, 25)       # (scenarios, steps, log_every, chunks) the capture was taken at
-NCU_FP64_PIPE_ACTIVE = 0.747
+NCU_FP64_PIPE_ACTIVE = 0.770
 LOG_BYTES_PER_LOGGED_SAMPLE = 56          # 5 state + 2 input doubles
 
 
@@ -699,7 +699,7 @@ def main():
                 "peak_probe": probe,
                 "flop_per_aircraft_step": FP64_FLOP_PER_STEP, "kernel_ms": kernel_ms, "steps_per_launch": steps_per_launch,
                 "traffic": NCU_TRAFFIC_BYTES_DEFAULT_LAUNCH if (B, T_steps, args.log_every, args.chunks) == NCU_TRAFFIC_CONFIG else None,
-                "traffic_note": "ncu dram bytes of one launch at the default sizes (profiles/r2f_rollout_dfff_circle.md); algorithmic bytes = log_bytes_per_launch",
+                "traffic_note": "ncu dram bytes of one launch at the default sizes (profiles/r2i_rollout_dfff_circle.md); algorithmic bytes = log_bytes_per_launch",
                 "fp64_pipe_active_ncu": NCU_FP64_PIPE_ACTIVE, "log_bytes_per_launch": log_bytes,
                 "hbm": {"achieved_gbs": log_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak or 6650.0,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if hbm_peak else "fallback"}}
