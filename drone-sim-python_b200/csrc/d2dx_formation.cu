@@ -51,6 +51,7 @@ __device__ __forceinline__ double dcf_warp(const double* sB, const double* sz, i
 __global__ void __launch_bounds__(kFormThreads) rollout_formation_kernel(const __grid_constant__ FormArgs a) {
   __shared__ double sB[kMaxAc * kMaxAc];
   __shared__ double sz[kMaxAc];
+  __shared__ double slag[8][kFormThreads];               // stage factors of the bank / air-speed lags (rk4_step, LagCoef), per thread
   for (int k = threadIdx.x; k < a.n_ac * a.n_e; k += kFormThreads) sB[k] = a.Binc[k];
   for (int k = threadIdx.x; k < a.n_e; k += kFormThreads) sz[k] = a.zdes[k];
   __syncthreads();
@@ -67,6 +68,11 @@ __global__ void __launch_bounds__(kFormThreads) rollout_formation_kernel(const _
   AcPar ap;
   ap.wx = 0.0; ap.wy = 0.0;                              // WindField() default, 08_CircularFormation_Full.py:27
   ap.n_inv_tau_phi = -1.0 / a.ac[g]; ap.n_inv_tau_v = -1.0 / a.ac[M + g];
+  {                                                      // dt, nsub and the time constants are fixed for the launch
+    const LagCoef L = lag_coef(a.nsub == 1 ? a.dt : a.dt * (1.0 / a.nsub), ap);
+    const int t = threadIdx.x;
+    slag[0][t] = L.f2; slag[1][t] = L.f3; slag[2][t] = L.f4; slag[3][t] = L.ff; slag[4][t] = L.v2; slag[5][t] = L.v3; slag[6][t] = L.v4; slag[7][t] = L.vf;
+  }
   const double cx = a.c[g], cy = a.c[M + g], R = a.r[g];
   double X[5];
 #pragma unroll
@@ -95,7 +101,11 @@ __global__ void __launch_bounds__(kFormThreads) rollout_formation_kernel(const _
       if (a.o.U_log) a.o.U_log[row * M + g] = phi_c;
       if (a.o.Rr_log) a.o.Rr_log[row * M + g] = Rr;
     }
-    rk4_step(ap, X, phi_c, a.v_c, a.dt, a.nsub);         // :90
+    {
+      const int t = threadIdx.x;
+      const LagCoef L = {slag[0][t], slag[1][t], slag[2][t], slag[3][t], slag[4][t], slag[5][t], slag[6][t], slag[7][t]};
+      rk4_step<false, true>(ap, X, phi_c, a.v_c, a.dt, a.nsub, &L);   // :90
+    }
     if (log_in == 0) { log_in = log_every; ++row; }
     --log_in;
   }
@@ -124,6 +134,7 @@ struct DcfArgs {
 __global__ void __launch_bounds__(kFormThreads) dcf_kernel(const __grid_constant__ DcfArgs a) {
   __shared__ double sB[kMaxAc * kMaxAc];
   __shared__ double sz[kMaxAc];
+  __shared__ double slag[8][kFormThreads];               // stage factors of the bank / air-speed lags (rk4_step, LagCoef), per thread
   for (int k = threadIdx.x; k < a.n_ac * a.n_e; k += kFormThreads) sB[k] = a.Binc[k];
   for (int k = threadIdx.x; k < a.n_e; k += kFormThreads) sz[k] = a.zdes[k];
   __syncthreads();

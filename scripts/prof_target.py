@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small single-kernel drivers for ncu captures (round 2): python scripts/prof_target.py <target> [reps]
-targets: c4batch (256 x C4 all-pairs), c3batch (4096 x C3), rollout (1e6 circles x 400 steps, log x100), poly, composite, formation"""
+targets: c4batch (256 x C4 all-pairs), c3batch (4096 x C3), rollout (1e6 circles x 400 steps, log x100), poly, composite, formation, tracker"""
 import os
 import sys
 
@@ -76,6 +76,17 @@ elif target == "formation":
     Xf = eng.empty(5, M)
     ms = timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf))
     print(f"formation: {ms:.3f} ms, {M * (T - 1)} aircraft-steps")
+elif target == "tracker":
+    Mt, Tt = eng.sm_count * 1024, 101
+    tt = np.arange(Tt) * 0.1
+    rr, vv = rng.uniform(30, 60, Mt), rng.uniform(10, 14, Mt)
+    om = vv / rr
+    al = om[None, :] * tt[:, None]
+    ref = np.stack([rr * np.cos(al), rr * np.sin(al), -vv * np.sin(al), vv * np.cos(al), -vv * om * np.cos(al), -vv * om * np.sin(al)], 1)
+    X0t = eng.to_device(np.ascontiguousarray(np.stack([rr + 1., 0 * rr - 1., 0 * rr + np.pi / 2, 0 * rr, vv], 0)))
+    refd, wz, act, Xft = eng.to_device(ref), eng.zeros(2, Mt), eng.to_device(np.stack([np.full(Mt, 0.01), np.full(Mt, 1.)])), eng.empty(5, Mt)
+    ms = timed(lambda: eng.rollout_tracker(refd, X0t, wz, act, 0.1, 0, Tt - 1, 10, X_final=Xft))
+    print(f"tracker: {ms:.3f} ms, {Mt * (Tt - 1)} aircraft-steps, {Mt * (Tt - 1) / ms / 1e6:.2f} G steps/s")
 elif target == "composite":
     from d2d_b200 import scenario as dds, simulation
     scen = dds.get("patrol_3")
