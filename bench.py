@@ -211,11 +211,11 @@ def core_metrics(eng, hbm_peak, fp64_peak, world, rank, seed):
     sync_all()
     dt = max_over_ranks(_timed(lambda: eng.rollout_formation(n_ac, chain_incidence(n_ac), z, X0, c, r, ac, 4e-4, 15, 20, 15., 0.05, 0, T - 1, 5, X_final=Xf), 3))
     # executed fp64 flop per aircraft-step (5 RK4 sub-steps + DCF + GVF), ncu: profiles/r1_final_formation_c2.md
-    flop = 1871.0 * M * (T - 1)                  # profiles/r2f_formation_c2.md
+    flop = 1743.0 * M * (T - 1)                  # profiles/r2i_formation_c2.md
     out["formation_c2_batch"] = {"aircraft_steps_per_s": world * M * (T - 1) / dt, "rk4_substeps_per_s": world * M * (T - 1) * 5 / dt,
                                  "formations_per_gpu": F, "ms_per_launch": dt * 1e3, "sharding": f"by formation x{world}, no collective",
                                  "roofline": {"bound": "fp64", "achieved": flop / dt / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                                              "frac": flop / dt / 1e12 / fp64_peak, "flop_per_aircraft_step": 1871.0}}
+                                              "frac": flop / dt / 1e12 / fp64_peak, "flop_per_aircraft_step": 1743.0}}
     del X0, c, r, ac, Xf
     # (3) ONE C4 problem (and a batch of 64) sharded by aircraft over the ranks: fused peer-memory kernel, CUDA graph
     rng0 = np.random.default_rng(seed)                                # the same problems on every rank
