@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(kPairWarps * 32, REGS ? 4 : 3) colloc_pairs_ke
   }
 
   if (a.what & D2DX_EVAL_COST) {
-    const double v4[4] = {warp_sum(s_v), warp_sum(s_phi), warp_sum(s_obs), warp_sum(s_col)};
-    if (lane == 0) { sred[w * 4 + 0] = v4[0]; sred[w * 4 + 1] = v4[1]; sred[w * 4 + 2] = v4[2]; sred[w * 4 + 3] = v4[3]; }
+    const double tot = warp_sum4(s_v, s_phi, s_obs, s_col, lane);     // lanes 0 / 8 / 16 / 24 hold the four sums
+    if ((lane & 7) == 0) sred[w * 4 + (lane >> 3)] = tot;
     __syncthreads();
     if (w == 0) {
       double b4[4] = {0.0, 0.0, 0.0, 0.0};

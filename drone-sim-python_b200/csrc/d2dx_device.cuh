@@ -615,6 +615,21 @@ __device__ __forceinline__ void gvf_control(double px, double py, double psi, do
   U = U1 + U2;
 }
 
+// Four warp sums at once: two exchange steps leave every lane with ONE of the four quantities (which one: lane bits 4 and 3),
+// three butterfly steps finish it -- 6 double shuffles and adds instead of 20.  The totals end in lanes 0 (v0), 8 (v1), 16 (v2)
+// and 24 (v3); the summation order is fixed, like warp_sum's.
+__device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8;
+  double k0 = h16 ? v2 : v0, k1 = h16 ? v3 : v1;              // lanes 0-15 keep (v0, v1), lanes 16-31 keep (v2, v3)
+  k0 += __shfl_xor_sync(0xffffffffu, h16 ? v0 : v2, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, h16 ? v1 : v3, 16);
+  double k = h8 ? k1 : k0;                                    // bit 3 picks the second of the pair
+  k += __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
