@@ -284,11 +284,12 @@ def test_reference_csv_solutions_are_feasible_and_round_trip(golden, tmp_path):
 
 
 @pytest.mark.parametrize("n_ac,N,n_prob", [(2, 33, 1), (3, 64, 2), (8, 100, 3), (16, 97, 2), (17, 40, 1), (5, 31, 70), (33, 20, 1),
-                                           (16, 97, 200), (3, 65, 300), (7, 150, 120), (2, 500, 40), (9, 100, 200)])
+                                           (16, 97, 200), (3, 65, 300), (7, 150, 120), (2, 500, 40), (9, 100, 200), (2, 20, 65536)])
 def test_all_pairs_kernel_shapes_against_oracle(n_ac, N, n_prob):
     """colloc_pairs_kernel (every unordered pair once, exponentials handed over through shared-memory slots): even / odd
     aircraft counts, fewer aircraft than warps, more than two aircraft per warp, ragged last tile, the two-kernel cost
-    reduction of large batches (n_prob >= 64), and the ordered fallback beyond the shared-memory budget (33 aircraft).
+    reduction of large batches (n_prob >= 64), the one-dimensional grid of the largest call (65536 problems), and the ordered fallback beyond
+    the shared-memory budget (33 aircraft).
     n_ac <= 16 takes the instantiation whose phase-A gradients wait in registers, larger counts the shared-memory one."""
     from oracle import d2d_oracle as orc
     from d2d_b200.collocation import CollocationProblem, CostSpec
