@@ -212,12 +212,13 @@ def solve(nlp, theta, ctol=1e-8, gtol=1e-10, ftol=1e-10, max_outer=30, max_inner
                    "c_max": nlp.c.abs().amax(dim=(1, 2)).cpu().numpy(), "cost": nlp.cost.cpu().numpy()}
 
 
-def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False, min_solved=0):
+def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=4, opts=None, verbose=False, min_solved=0):
     """Second-order solve of P single-aircraft problems (d2dx_ddp_solve: control-limited DDP on the collocation grid, one GPU
     thread per problem).  phi0, v0: host (P, N) (or broadcastable) start inputs.  Problems that end unsolved climb a retry
     ladder: the same start with the other regularisation (eigenvalue-modified Newton: better on tightly saturated problems,
     plain Levenberg-Marquardt: better elsewhere), then the mirrored bank profile (the other turn direction -- the usual reason
-    for an infeasible local minimum) with either.  `min_solved=k` (multi-start of ONE problem): the launch ends as soon as k starts
+    for an infeasible local minimum) with either, and last the original start with four times the sweep budget (the clipped
+    exponential obstacles of exp_4 converge in ~500 sweeps, beyond the default 400).  `min_solved=k` (multi-start of ONE problem): the launch ends as soon as k starts
     have converged and the ladder is only climbed when none has.  Returns (frees (P, num_free) in the planner layout, info)."""
     if nlp.n_ac != 1:
         raise ValueError("solve_ddp handles one aircraft per problem (collision terms couple the aircraft: use solve)")
@@ -234,8 +235,9 @@ def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False, min
     e.ddp_solve(nlp.c_prob, P, nlp.bounds, nlp.state_box, p0, p1, u, xs, info, e.ddp_options(**{**kw, "reg_mode": mode0}))
     ih = info.cpu().numpy()
     total_its = ih[:, 1].copy()
-    ladder = [(1.0, 1 - mode0), (-1.0, mode0), (-1.0, 1 - mode0)][:retries]
-    for r, (sign, mode) in enumerate(ladder):
+    base = e.ddp_options(**kw)
+    ladder = [(1.0, 1 - mode0, 1), (-1.0, mode0, 1), (-1.0, 1 - mode0, 1), (1.0, mode0, 4)][:retries]
+    for r, (sign, mode, scale) in enumerate(ladder):
         bad = np.nonzero(ih[:, 0] != 2)[0]
         if len(bad) == 0 or (min_solved > 0 and len(bad) < P):
             break
@@ -246,7 +248,7 @@ def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False, min
         idx = torch.from_numpy(bad).to(e.device)
         ub, xb, ib = e.to_device(np.ascontiguousarray(seed)), e.empty(len(bad), 3, N), e.zeros(len(bad), 8)
         e.ddp_solve(nlp.c_prob, len(bad), nlp.bounds, nlp.state_box, p0[idx].contiguous(), p1[idx].contiguous(), ub, xb, ib,
-                    e.ddp_options(**{**kw, "reg_mode": mode}))
+                    e.ddp_options(**{**kw, "reg_mode": mode, "max_iter": int(base.max_iter) * scale, "max_outer": int(base.max_outer) * (2 if scale > 1 else 1)}))
         ibh = ib.cpu().numpy()
         better = torch.from_numpy((ibh[:, 0] == 2) | (ibh[:, 4] < ih[bad, 4])).to(e.device)
         sel = idx[better]
@@ -254,7 +256,7 @@ def solve_ddp(nlp, phi0, v0, ctol=1e-8, retries=3, opts=None, verbose=False, min
         total_its[bad] += ibh[:, 1]
         ih = info.cpu().numpy()
         if verbose:
-            print(f"retry {r} (bank sign {sign:+.0f}, regularisation {mode}): {len(bad)} problems re-seeded, {(ibh[:, 0] == 2).sum()} of them solved")
+            print(f"retry {r} (bank sign {sign:+.0f}, regularisation {mode}, sweep budget x{scale}): {len(bad)} problems re-seeded, {(ibh[:, 0] == 2).sum()} of them solved")
     frees = torch.cat([xs.reshape(P, 3 * N), u.reshape(P, 2 * N)], dim=1).cpu().numpy()
     nlp.xs.copy_(xs.reshape(P, 3, 1, N)); nlp.u_phys.copy_(u.reshape(P, 2, 1, N))
     return frees, {"flag": ih[:, 0].astype(int), "iterations_each": total_its.astype(int), "iterations": int(total_its.max()), "outer": int(ih[:, 2].max()),

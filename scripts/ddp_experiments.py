@@ -39,7 +39,7 @@ def run(exp, n_starts=9, hz=None, t1=None, opts=None, verbose=True):
     box = None
     if exp.x_constraint is not None or exp.y_constraint is not None:
         bx, by = exp.x_constraint or (-1e300, 1e300), exp.y_constraint or (-1e300, 1e300)
-        box = (bx[0], bx[1], by[0], by[1], 1000.)
+        box = (bx[0], bx[1], by[0], by[1], float(os.environ.get("BOXW", "1000")))
     bounds = (exp.phi_constraint[0], exp.phi_constraint[1], exp.v_constraint[0], exp.v_constraint[1])
     w = exp.wind.sample_num(0, 0, 0)
     res = []
