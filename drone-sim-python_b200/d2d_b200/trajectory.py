@@ -206,6 +206,17 @@ class CompositeTraj(Trajectory):
         return segs
 
 
+class TabulatedTraj(Trajectory):
+    """d2d/trajectory.py:212-217: an unfinished stub upstream (the constructor ignores its file name, `get` returns zeros), kept
+    for import compatibility.  The working tabulated reference is `trajectory_factory.TrajTabulated`."""
+
+    def __init__(self, filename='/tmp/optyplan.npz'):
+        pass
+
+    def get(self, t):
+        return np.zeros((self.nder + 1, self.ncomp))
+
+
 class SpaceIndexedTraj(Trajectory):
     """Geometry g(lambda) driven by a scalar dynamic lambda(t) (d2d/trajectory.py:220-241).  On the engine: line or
     circle geometry with polynomial (PolynomialOne, AffineOne, CstOne) or sinusoidal (SinOne) dynamics -- TrajSiDemo
