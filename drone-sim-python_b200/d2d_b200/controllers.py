@@ -20,6 +20,23 @@ def ComputeDerivatives(x_ref, y_ref, dt):
     return Fdx, Fdy, Fddx, Fddy
 
 
+class CircleTraj:
+    """Controllers.py:17-32: circle reference sampled at one time (only used from commented-out code upstream; the tracker
+    follows tabulated planner output).  As written: the third derivative carries no omega^3 factor."""
+
+    def __init__(self, v, r=40, c=[0, 0]):
+        self.c, self.r, self.v = c, r, v
+        self.omega = self.v / self.r
+
+    def TrajPoints(self, t):
+        th, r, om = self.omega * t, self.r, self.omega
+        Y_ref = [r * np.cos(th), r * np.sin(th)]
+        Yd_ref = [-r * np.sin(th) * om, r * np.cos(th) * om]
+        Ydd_ref = [-r * np.cos(th) * om ** 2, -r * np.sin(th) * om ** 2]
+        Yddd_ref = [r * np.sin(th), -r * np.cos(th)]
+        return Y_ref, Yd_ref, Ydd_ref, Yddd_ref
+
+
 class DiffFlatness:
     """Reference state and input from the flat output and three derivatives (Controllers.py:50-108)."""
 
