@@ -42,7 +42,7 @@ elif target in ("rollout", "poly"):
     sys.path.insert(0, ROOT)
     import bench
     from d2d_b200.simulation import MonteCarloRollout
-    B, T = 10 ** 6, 400
+    B, T = int(os.environ.get("PROF_B", 10 ** 6)), 400
     if target == "rollout":
         w = bench.workload(B, 12345)
         X0 = bench.flat_state0(w) + w["noise"]
